@@ -1,0 +1,364 @@
+#!/usr/bin/env python
+"""Benchmark of the trie-mass hot path (BASELINE.json metric: trie weight_sum/max distributions/sec at 128k vocab).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One "step" = batch_weight_sum + batch_weight_max over one batch of 64 synthetic Dirichlet rows on the
+128,256-token synthetic byte vocabulary (BASELINE.json configs[1]); a "distribution" is one row put through
+both reductions.  Under torchrun every rank runs the same per-GPU workload on its own rows (weak scaling,
+no collective on the data path); `value` is the whole-job rate, timed on the device, max over ranks.
+
+  value      device-resident: inputs in HBM, CUDA events around exactly K steps (CUDA-graph replays of
+             one step per buffer set), rotating over buffer sets larger than L2
+  e2e        the same step through the public, reference-shaped API: pinned HOST rows in, numpy arrays
+             out (ParallelTokenCharacterTrie.batch_weight_sum_max), H2D and D2H inside the timed region
+  roofline   dominant kernel (tile_kernel): algorithmic bytes (4V + 4N per distribution) / its CUDA-event time
+  cpu_baseline / --impl reference
+             the reference's CPU algorithm (oracle C restatement of the numba loops, OpenMP over rows)
+             timed on this box's host cores
+"""
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "trie weight_sum+weight_max distributions/sec at 128k vocab"
+UNIT = "distributions/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--vocab", type=int, default=128256)
+    ap.add_argument("--batch", type=int, default=64)
+    ap.add_argument("--alpha", type=float, default=1.0)
+    ap.add_argument("--sets", type=int, default=4, help="rotating buffer sets (each 33 MB in + 176 MB out)")
+    ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 10)")
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def workload_name(args):
+    return (f"batch_weight_sum + batch_weight_max, synthetic byte vocab V={args.vocab}, batch {args.batch} "
+            f"Dirichlet({args.alpha:g}) fp32 rows per GPU")
+
+
+# ---- the reference's CPU algorithm (oracle) -----------------------------------------------------------------
+def cpu_rate(args, layout, idx_to_leaf, seconds_target=12.0):
+    """Times oracle weight_sum + weight_max (numba loops restated in C) with all host threads on a bounded sample."""
+    import oracle
+    from genlm_backend_b200.synthetic import dirichlet_rows
+
+    o = oracle.OracleLayout(idx_to_leaf, layout["child_ptr"], layout["child_idx"])
+    threads = oracle.max_threads()
+    probe = dirichlet_rows(2, args.vocab, alpha=args.alpha, seed=99)
+    o.weight_sum(probe, threads=1)  # warm
+    t0 = time.perf_counter()
+    o.weight_sum(probe, threads=1)
+    o.weight_max(probe, threads=1)
+    per_row = (time.perf_counter() - t0) / 2
+    rows = int(max(threads * 2, min(threads * 64, seconds_target * threads / max(per_row, 1e-6))))
+    rows = max(rows, args.batch)
+    rows = min(rows, 4096)
+    ws = dirichlet_rows(rows, args.vocab, alpha=args.alpha, seed=100)
+    best = float("inf")
+    for _ in range(2):
+        t0 = time.perf_counter()
+        o.weight_sum(ws, threads=threads)
+        o.weight_max(ws, threads=threads)
+        best = min(best, time.perf_counter() - t0)
+    return {
+        "value": rows / best, "unit": UNIT, "cores": int(o.last_threads), "kind": "port",
+        "sample": f"{rows} rows x (sum+max), V={args.vocab}, oracle/trie_oracle.c (numba loops of base.py:346-393 in C, "
+                  f"fp64), OpenMP over rows, best of 2, host has {os.cpu_count()} logical cpus",
+        "single_thread_rows_per_s": 1.0 / per_row,
+    }
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from genlm_backend_b200 import TokenCharacterTrie
+    from genlm_backend_b200.synthetic import synth_vocab
+
+    trie = TokenCharacterTrie(synth_vocab(args.vocab))  # host builder only: no GPU work in this arm
+    t0 = time.perf_counter()
+    cb = cpu_rate(args, trie._layout, trie.idx_to_leaf, seconds_target=8.0)
+    wall = time.perf_counter() - t0
+    line = {
+        "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * args.batch / cb["value"],
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(args), "vocab": args.vocab, "batch": args.batch,
+                   "note": "reference CPU algorithm (oracle port of the numba path) on host cores; "
+                           "a step is a bounded sample of the workload"},
+        "cpu_baseline": cb,
+        "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "wall_s": wall,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---- clocks ------------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    def __init__(self, index, period=0.02):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self.loaded = False
+        self._stop_evt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(visible.split(",")[index]) if visible and visible.split(",")[index].isdigit() else index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4): "sw_power_cap",
+            getattr(nv, "nvmlClocksThrottleReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake_slowdown",
+        }
+        while not self._stop_evt.is_set():
+            try:
+                if self.loaded:
+                    self.samples.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                    bits = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                    for bit, name in names.items():
+                        if bits & bit:
+                            self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def stop(self):
+        self._stop_evt.set()
+
+    def summary(self):
+        if not self.ok or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0}
+        return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ---- our arm -------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from genlm_backend_b200 import ParallelTokenCharacterTrie, _lib
+    from genlm_backend_b200.synthetic import synth_vocab, dirichlet_rows
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    V, B, K, W = args.vocab, args.batch, args.steps, max(args.warmup, 3)
+    trie = ParallelTokenCharacterTrie(synth_vocab(V), devices=[local_rank])
+    eng = trie._engine
+    N = len(trie)
+    eng.ensure_device(local_rank)
+    info = eng.plan_info()
+
+    base = dirichlet_rows(B, V, alpha=args.alpha, seed=1 + rank)
+    nsets = max(1, args.sets)
+    ws_sets = [torch.tensor(np.roll(base, k, axis=0)).to(dev) for k in range(nsets)]
+    sum_sets = [torch.empty((B, N), dtype=torch.float32, device=dev) for _ in range(nsets)]
+    max_sets = [torch.empty((B, N), dtype=torch.float32, device=dev) for _ in range(nsets)]
+    set_bytes = B * V * 4 + 2 * B * N * 4
+    l2_bytes = torch.cuda.get_device_properties(dev).L2_cache_size
+
+    def step(k, phases=0, ops=("sum", "max")):
+        eng.reduce(ws_sets[k], ops, out_sum=sum_sets[k], out_max=max_sets[k], phases=phases)
+
+    launches_per_step = 1 + 2 * (1 + (1 if info["n_span"] > 0 else 0))
+
+    # warm-up (also sets kernel attributes, allocates the scratch) ------------------------------------------------
+    for i in range(W):
+        step(i % nsets)
+    torch.cuda.synchronize()
+
+    graphs = None
+    if not args.no_graph:
+        graphs = []
+        for k in range(nsets):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                step(k)
+            graphs.append(g)
+        for k in range(nsets):
+            graphs[k].replay()
+        torch.cuda.synchronize()
+
+    def run_step(i):
+        if graphs is not None:
+            graphs[i % nsets].replay()
+        else:
+            step(i % nsets)
+
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+
+    # timed region: exactly K steps ---------------------------------------------------------------------------------
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    clocks.loaded = True
+    ev0.record()
+    for i in range(K):
+        run_step(i)
+    ev1.record()
+    torch.cuda.synchronize()
+    clocks.loaded = False
+    barrier()
+    ms_total = max_over_ranks(ev0.elapsed_time(ev1))
+    value = world * B * K / (ms_total / 1e3)
+
+    # per-kernel timing for the roofline (one op, one phase at a time), same buffers ----------------------------------
+    def time_phase(phases, ops, iters):
+        for i in range(3):
+            step(i % nsets, phases, ops)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for i in range(iters):
+            step(i % nsets, phases, ops)
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / iters
+
+    clocks.loaded = True
+    iters = max(50, min(K, 400))
+    ms_tile = time_phase(_lib.GT_FLAG_PHASE_TILE, ("sum",), iters)
+    ms_tile_max = time_phase(_lib.GT_FLAG_PHASE_TILE, ("max",), iters)
+    ms_permute = time_phase(_lib.GT_FLAG_PHASE_PERMUTE, ("sum",), iters)
+    ms_span = time_phase(_lib.GT_FLAG_PHASE_SPAN, ("sum",), iters) if info["n_span"] else 0.0
+    ms_sum_op = time_phase(0, ("sum",), iters)
+    clocks.loaded = False
+
+    # end to end through the public API: pinned host rows in, numpy out -----------------------------------------------
+    E = args.e2e_steps or min(K, 10)
+    host_sets = [torch.tensor(np.roll(base, k, axis=0)).pin_memory() for k in range(2)]
+    for i in range(2):
+        trie.batch_weight_sum_max(host_sets[i % 2])
+    barrier()
+    clocks.loaded = True
+    t0 = time.perf_counter()
+    for i in range(E):
+        sums, maxes = trie.batch_weight_sum_max(host_sets[i % 2])
+        _ = float(sums[0, N - 1]) + float(maxes[B - 1, N - 1])  # results are on the host
+    torch.cuda.synchronize()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    clocks.loaded = False
+    barrier()
+    clocks.stop()
+
+    if world > 1:
+        dist.destroy_process_group()
+    if rank != 0:
+        return
+
+    peak, peak_src = peaks()
+    bytes_per_dist = 4 * V + 4 * N
+    achieved = B * bytes_per_dist / (ms_tile / 1e3) / 1e9
+    path_achieved = 2 * B * bytes_per_dist * K / (ms_total / 1e3) / 1e9
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {
+            "workload": workload_name(args), "vocab": V, "nodes": N, "batch_per_gpu": B, "global_batch": B * world,
+            "parallelism": f"rows sharded, {world} independent GPU(s), no collective",
+            "l2_policy": f"rotating {nsets} buffer sets of {set_bytes / 1e6:.0f} MB ({nsets * set_bytes / 1e6:.0f} MB total) "
+                         f"vs L2 {l2_bytes / 1e6:.0f} MB",
+            "launch": "one CUDA graph replay per step" if graphs is not None else "direct launches",
+            "tile_leaves": info["tile_leaves"], "seg_positions": info["seg_positions"], "n_span": info["n_span"],
+        },
+        "e2e": {
+            "value": world * B * E / e2e_s, "unit": UNIT, "h2d_bytes_per_step": B * V * 4,
+            "d2h_bytes_per_step": 2 * B * N * 4, "steps": E,
+            "api": "ParallelTokenCharacterTrie.batch_weight_sum_max(pinned host tensor) -> numpy",
+        },
+        "gpu_launches": launches_per_step * K,
+        "roofline": {
+            "bound": "hbm", "kernel": "tile_kernel<float,2,SUM>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+            "bytes_per_launch": B * bytes_per_dist, "ms_per_launch": ms_tile,
+            "note": "algorithmic bytes = (4V + 4N) per distribution x batch; kernel timed alone with CUDA events",
+        },
+        "path_roofline": {
+            "achieved": path_achieved, "peak": peak, "unit": "GB/s", "frac": path_achieved / peak,
+            "note": "whole step (permute + 2 x (tile + span)) against 2 x (4V + 4N) bytes per distribution",
+        },
+        "kernel_ms": {"permute": ms_permute, "tile_sum": ms_tile, "tile_max": ms_tile_max, "span": ms_span,
+                      "sum_op_all_phases": ms_sum_op},
+        "clocks": clocks.summary(),
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_rate(args, trie._layout, trie.idx_to_leaf)
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,310 @@
+// Fused SMC row op for sm_100a: masked logsumexp + one categorical draw per row, one HBM pass.
+//
+// Replaces the per-particle torch sequence of the reference idiom (README.md:82-91, docs/index.md:61-70;
+// temperature variant genlm/backend/llm/base.py:131-146):
+//     masked = logp + mask;  logZ = masked.logsumexp(-1);  tok = multinomial((masked - logZ).exp(), 1)
+//
+// One CTA per row.  Thread t owns the 16-byte groups g = t, t+512, ... of the row and keeps an online
+// (max, sum-exp) pair for them; after a block reduction (fp64) a Philox uniform picks first the owning
+// thread, then the element among that thread's ~V/512 elements, which are re-read from L2 (a few KB).
+// The draw is an exact inverse CDF over a fixed permutation of the vocabulary, so it is distributed as
+// the reference's multinomial but is not stream-identical to torch's generator.
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <cuda_bf16.h>
+
+#include <cstdint>
+
+#include "trie_internal.h"
+
+namespace gt {
+
+constexpr int kSThreads = 512;
+constexpr float kLog2e = 1.4426950408889634f;
+
+struct SampleArgs {
+    const void* logp; int64_t ld_logp; int64_t V; int n_rows;
+    const void* mask; int mask_kind; int64_t mask_ld;
+    float inv_temp; uint64_t seed, offset;
+    float* logZ; int32_t* tok;
+};
+
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                              uint32_t k1, uint32_t out[4]) {
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        c0 = hi1 ^ c1 ^ k0; c1 = lo1; c2 = hi0 ^ c3 ^ k1; c3 = lo0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+template <typename T> __device__ __forceinline__ float elem_to_float(T x);
+template <> __device__ __forceinline__ float elem_to_float<float>(float x) { return x; }
+template <> __device__ __forceinline__ float elem_to_float<double>(double x) { return (float)x; }
+template <> __device__ __forceinline__ float elem_to_float<__half>(__half x) { return __half2float(x); }
+template <> __device__ __forceinline__ float elem_to_float<__nv_bfloat16>(__nv_bfloat16 x) { return __bfloat162float(x); }
+
+// Per-row view: groups of EPV elements aligned to 16 bytes in global memory.
+template <typename IN_T> struct RowView {
+    static constexpr int EPV = 16 / (int)sizeof(IN_T);
+    const IN_T* row;        // first element of the row
+    int phase;              // element offset of `row` inside its 16-byte line
+    int V;
+    const void* mrow; int mask_kind; bool mask_vec;
+    float inv_temp;
+
+    __device__ __forceinline__ int n_groups() const { return (phase + V + EPV - 1) / EPV; }
+
+    __device__ __forceinline__ float mask_apply(float x, int i) const {
+        if (mask_kind == GT_MASK_ADD_F32) return x + static_cast<const float*>(mrow)[i];
+        if (mask_kind == GT_MASK_BOOL_U8) return static_cast<const uint8_t*>(mrow)[i] ? x : -INFINITY;
+        if (mask_kind == GT_MASK_BITS_U32) return (static_cast<const uint32_t*>(mrow)[i >> 5] >> (i & 31)) & 1u ? x : -INFINITY;
+        return x;
+    }
+
+    // x[k] = masked, temperature-scaled value of element (g*EPV - phase + k), -inf outside the row.
+    __device__ __forceinline__ void fetch(int g, float x[EPV]) const {
+        const int i0 = g * EPV - phase;
+        if (i0 >= 0 && i0 + EPV <= V) {
+            uint4 raw;
+            asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                         : "=r"(raw.x), "=r"(raw.y), "=r"(raw.z), "=r"(raw.w) : "l"(row + i0));
+            const IN_T* e = reinterpret_cast<const IN_T*>(&raw);
+#pragma unroll
+            for (int k = 0; k < EPV; ++k) x[k] = elem_to_float<IN_T>(e[k]) * inv_temp;
+            if (mask_kind == GT_MASK_ADD_F32 && mask_vec) {
+                const float4* m4 = reinterpret_cast<const float4*>(static_cast<const float*>(mrow) + i0);
+#pragma unroll
+                for (int q = 0; q < EPV / 4; ++q) {
+                    const float4 m = __ldg(m4 + q);
+                    x[4 * q] += m.x; x[4 * q + 1] += m.y; x[4 * q + 2] += m.z; x[4 * q + 3] += m.w;
+                }
+            } else if (mask_kind != GT_MASK_NONE) {
+#pragma unroll
+                for (int k = 0; k < EPV; ++k) x[k] = mask_apply(x[k], i0 + k);
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < EPV; ++k) {
+                const int i = i0 + k;
+                x[k] = (i >= 0 && i < V) ? mask_apply(elem_to_float<IN_T>(row[i]) * inv_temp, i) : -INFINITY;
+            }
+        }
+    }
+};
+
+// Warp-wide search over arr[0..n) (shared memory).  target >= 0: first index whose inclusive prefix sum
+// exceeds target.  target < 0, or rounding pushed target past the total: the last index with positive
+// mass, flagged by before = -1.  idx = -1 only when nothing has mass.
+__device__ __forceinline__ void warp_find(const double* arr, int n, double target, int& idx, double& before) {
+    const int lane = threadIdx.x & 31;
+    const int per = (n + 31) / 32;
+    const int a = min(n, lane * per), b = min(n, a + per);
+    double local = 0.0;
+    int last_pos = -1;
+    for (int i = a; i < b; ++i) { const double v = arr[i]; local += v; if (v > 0.0) last_pos = i; }
+    double incl = local;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const double y = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += y;
+    }
+    const unsigned hit = __ballot_sync(0xffffffffu, target >= 0.0 && incl > target && last_pos >= 0);
+    if (hit) {
+        const int src = __ffs(hit) - 1;
+        int found = -1; double bef = 0.0;
+        if (lane == src) {
+            double run = incl - local;
+            for (int i = a; i < b; ++i) {
+                const double v = arr[i];
+                if (v > 0.0) { found = i; bef = run; if (run + v > target) break; }
+                run += v;
+            }
+        }
+        idx = __shfl_sync(0xffffffffu, found, src);
+        before = __shfl_sync(0xffffffffu, bef, src);
+    } else {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) last_pos = max(last_pos, __shfl_xor_sync(0xffffffffu, last_pos, o));
+        idx = last_pos; before = -1.0;
+    }
+}
+
+template <typename IN_T>
+__global__ void __launch_bounds__(kSThreads) lse_sample_kernel(SampleArgs A) {
+    constexpr int EPV = RowView<IN_T>::EPV;
+    __shared__ double s_mass[kSThreads];
+    __shared__ float s_wmax[kSThreads / 32];
+    __shared__ float s_M;
+    __shared__ int s_pick;
+    __shared__ double s_resid;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int b = blockIdx.x; b < A.n_rows; b += gridDim.x) {
+        RowView<IN_T> rv;
+        rv.row = static_cast<const IN_T*>(A.logp) + (size_t)b * A.ld_logp;
+        rv.phase = (int)((reinterpret_cast<uintptr_t>(rv.row) & 15) / sizeof(IN_T));
+        rv.V = (int)A.V; rv.mask_kind = A.mask_kind; rv.inv_temp = A.inv_temp;
+        rv.mrow = nullptr; rv.mask_vec = false;
+        if (A.mask_kind == GT_MASK_ADD_F32) {
+            const float* m = static_cast<const float*>(A.mask) + (size_t)b * A.mask_ld;
+            rv.mrow = m;
+            // group g starts at element g*EPV - phase: its mask address is 16-byte aligned iff the mask row
+            // has the same phase (mod 4 floats) as the group grid
+            rv.mask_vec = EPV >= 4 && ((((reinterpret_cast<uintptr_t>(m) >> 2) + 4u - (unsigned)(rv.phase & 3)) & 3u) == 0);
+        } else if (A.mask_kind == GT_MASK_BOOL_U8) {
+            rv.mrow = static_cast<const uint8_t*>(A.mask) + (size_t)b * A.mask_ld;
+        } else if (A.mask_kind == GT_MASK_BITS_U32) {
+            rv.mrow = static_cast<const uint32_t*>(A.mask) + (size_t)b * A.mask_ld;
+        }
+        const int ng = rv.n_groups();
+
+        // ---- pass 1: online (max, sum exp) per thread ------------------------------------------------
+        float m = -INFINITY, s = 0.f;
+        for (int g = tid; g < ng; g += kSThreads) {
+            float x[EPV];
+            rv.fetch(g, x);
+            float gm = x[0];
+#pragma unroll
+            for (int k = 1; k < EPV; ++k) gm = fmaxf(gm, x[k]);
+            if (gm > m) {  // rare once the running max has settled
+                s *= exp2f((m - gm) * kLog2e);  // m = -inf: s is still 0
+                m = gm;
+            }
+            if (m > -INFINITY) {
+                const float ml = m * kLog2e;
+#pragma unroll
+                for (int k = 0; k < EPV; ++k) s += exp2f(fmaf(x[k], kLog2e, -ml));
+            }
+        }
+        // A NaN element poisons s (fmaxf ignores it, so m stays finite): logZ becomes NaN, tok = -1.
+
+        // ---- block reduction (fp64) ------------------------------------------------------------------
+        float wm = m;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) wm = fmaxf(wm, __shfl_xor_sync(0xffffffffu, wm, o));
+        if (lane == 0) s_wmax[warp] = wm;
+        __syncthreads();
+        if (tid == 0) {
+            float M0 = s_wmax[0];
+            for (int w = 1; w < kSThreads / 32; ++w) M0 = fmaxf(M0, s_wmax[w]);
+            s_M = M0;
+        }
+        __syncthreads();
+        const float M = s_M;
+        s_mass[tid] = (m > -INFINITY) ? (double)s * exp2((double)(m - M) * (double)kLog2e) : 0.0;
+        __syncthreads();
+
+        if (warp == 0) {
+            double tot = 0.0;
+            for (int i = lane; i < kSThreads; i += 32) tot += s_mass[i];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+            // 53-bit uniform in [0,1): Philox4x32-10, counter = offset + row, key = seed
+            const uint64_t ctr = A.offset + (uint64_t)b;
+            uint32_t r[4];
+            philox4x32_10((uint32_t)ctr, (uint32_t)(ctr >> 32), 0u, 0u, (uint32_t)A.seed, (uint32_t)(A.seed >> 32), r);
+            const double u = (double)(((uint64_t)(r[0] >> 5) << 26) | (uint64_t)(r[1] >> 6)) * (1.0 / 9007199254740992.0);
+            const bool ok = (M > -INFINITY) && (tot > 0.0) && (tot < (double)INFINITY);  // false for NaN
+            int pick = -1; double before = 0.0;
+            if (ok) warp_find(s_mass, kSThreads, u * tot, pick, before);
+            if (lane == 0) {
+                s_pick = pick;
+                s_resid = before < 0.0 ? -1.0 : u * tot - before;
+                A.logZ[b] = (M == -INFINITY) ? -INFINITY : (float)((double)M + log(tot));
+            }
+        }
+        __syncthreads();
+        const int pick = s_pick;
+        const double resid = s_resid;
+        __syncthreads();  // s_pick / s_resid / s_mass are reused below
+        if (pick < 0) {
+            if (tid == 0) A.tok[b] = -1;
+            continue;
+        }
+
+        // ---- pass 2: re-read the picked thread's groups (L2-hot, a few KB) and locate the element ------
+        float x[EPV];
+        const int g = pick + tid * kSThreads;
+        double local = 0.0;
+        if (g < ng) {
+            rv.fetch(g, x);
+            const float ml = M * kLog2e;
+#pragma unroll
+            for (int k = 0; k < EPV; ++k) { x[k] = exp2f(fmaf(x[k], kLog2e, -ml)); local += (double)x[k]; }
+        } else {
+#pragma unroll
+            for (int k = 0; k < EPV; ++k) x[k] = 0.f;
+        }
+        s_mass[tid] = local;
+        __syncthreads();
+        if (warp == 0) {
+            const int n_cand = (ng - pick + kSThreads - 1) / kSThreads;  // threads holding a group
+            int k2; double before2;
+            warp_find(s_mass, n_cand, resid, k2, before2);
+            if (lane == 0) { s_pick = k2; s_resid = (before2 < 0.0) ? -1.0 : resid - before2; }
+        }
+        __syncthreads();
+        const int k2 = s_pick;
+        if (k2 < 0) {  // exp underflow relative to the global max wiped the picked thread's mass
+            if (tid == 0) A.tok[b] = -1;
+        } else if (tid == k2) {
+            const double rr = s_resid;
+            int chosen = -1; double run = 0.0;
+#pragma unroll
+            for (int k = 0; k < EPV; ++k) {
+                if (x[k] > 0.f && (chosen < 0 || rr < 0.0 || run <= rr)) {
+                    // first positive element always qualifies; later ones while the running sum has not
+                    // passed the residual (rr < 0: keep going to the last positive element)
+                    chosen = k;
+                    run += (double)x[k];
+                } else if (x[k] > 0.f) {
+                    run += (double)x[k];
+                }
+            }
+            A.tok[b] = g * EPV - rv.phase + chosen;
+        }
+        __syncthreads();
+    }
+}
+
+template <typename IN_T> static int launch_sampler(const SampleArgs& A, cudaStream_t st) {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int grid = A.n_rows < sms * 8 ? A.n_rows : sms * 8;
+    lse_sample_kernel<IN_T><<<grid, kSThreads, 0, st>>>(A);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { set_error("lse_sample launch failed: %s", cudaGetErrorString(e)); return GT_ERR_CUDA; }
+    return GT_OK;
+}
+
+}  // namespace gt
+
+extern "C" int gt_lse_sample(const void* logp, int in_type, int64_t n_rows, int64_t n_vocab, int64_t ld_logp,
+                             const void* mask, int mask_kind, int64_t mask_ld, float temperature, uint64_t seed,
+                             uint64_t offset, float* logZ_out, int32_t* tok_out, gt_stream stream) {
+    if (n_rows < 0 || n_vocab <= 0 || n_vocab >= (int64_t)1 << 30 || ld_logp < n_vocab || !logp || !logZ_out || !tok_out) {
+        gt::set_error("gt_lse_sample: bad argument"); return GT_ERR_ARG;
+    }
+    if (mask_kind != GT_MASK_NONE && !mask) { gt::set_error("gt_lse_sample: mask kind %d needs a mask pointer", mask_kind); return GT_ERR_ARG; }
+    if (mask_kind < GT_MASK_NONE || mask_kind > GT_MASK_BITS_U32) { gt::set_error("gt_lse_sample: unknown mask kind %d", mask_kind); return GT_ERR_ARG; }
+    if (!(temperature > 0.f)) { gt::set_error("gt_lse_sample: temperature must be > 0"); return GT_ERR_ARG; }
+    if (n_rows == 0) return GT_OK;
+    if (n_rows > INT32_MAX) { gt::set_error("gt_lse_sample: too many rows"); return GT_ERR_LIMIT; }
+    gt::SampleArgs A;
+    A.logp = logp; A.ld_logp = ld_logp; A.V = n_vocab; A.n_rows = (int)n_rows;
+    A.mask = mask; A.mask_kind = mask_kind; A.mask_ld = mask_ld;
+    A.inv_temp = 1.0f / temperature; A.seed = seed; A.offset = offset; A.logZ = logZ_out; A.tok = tok_out;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    switch (in_type) {
+        case GT_F32: return gt::launch_sampler<float>(A, st);
+        case GT_F64: return gt::launch_sampler<double>(A, st);
+        case GT_F16: return gt::launch_sampler<__half>(A, st);
+        case GT_BF16: return gt::launch_sampler<__nv_bfloat16>(A, st);
+        default: gt::set_error("gt_lse_sample: unknown input type %d", in_type); return GT_ERR_ARG;
+    }
+}

@@ -1,0 +1,163 @@
+"""Device-side driver shared by the trie classes: owns the C handle, keeps the plan metadata resident
+per GPU, caches scratch buffers, and launches ``gt_weight_reduce`` on torch's current stream.
+
+PyTorch is used for device memory, streams and host<->device copies only; every reduction runs in the
+hand-written kernels behind the C ABI (``csrc/trie_kernels.cu``).  There is no CPU path.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from .. import _lib
+from .._lib import lib, check
+
+_IN_TYPES = {
+    torch.float32: _lib.GT_F32,
+    torch.float64: _lib.GT_F64,
+    torch.float16: _lib.GT_F16,
+    torch.bfloat16: _lib.GT_BF16,
+}
+_OUT_TYPES = {torch.float32: _lib.GT_F32, torch.float64: _lib.GT_F64}
+OPS = {"sum": _lib.GT_OP_SUM, "max": _lib.GT_OP_MAX}
+
+# rows whose staging scratch we keep per stream slot (the C side chunks larger batches itself)
+_WORKSPACE_ROWS = 128
+
+
+def require_cuda():
+    if not torch.cuda.is_available():
+        raise RuntimeError(
+            "genlm_backend_b200 computes trie masses with CUDA kernels only (sm_100a); "
+            "no CUDA device is available and there is no CPU fallback"
+        )
+
+
+class TrieEngine:
+    """Owns a ``gt_trie*`` and everything resident on the GPUs for it."""
+
+    def __init__(self, symbols, offsets, n_tokens):
+        symbols = np.ascontiguousarray(symbols, dtype=np.int32)
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        handle = ctypes.c_void_p()
+        check(lib.gt_build(symbols.ctypes.data, offsets.ctypes.data, int(n_tokens), ctypes.byref(handle)), "gt_build")
+        self._handle = handle
+        self.V = int(lib.gt_num_tokens(handle))
+        self.N = int(lib.gt_num_nodes(handle))
+        self.nnz = int(lib.gt_num_reach(handle))
+        self._uploaded = set()
+        self._workspaces = {}
+
+    def __del__(self):
+        h = getattr(self, "_handle", None)
+        if h:
+            try:
+                lib.gt_free(h)
+            except Exception:
+                pass
+            self._handle = None
+
+    # ---- host layout ---------------------------------------------------------------------------------
+    def layout(self):
+        V, N = self.V, self.N
+        out = {
+            "leaf_node": np.empty(V, np.int32), "parent": np.empty(N, np.int32), "edge_label": np.empty(N, np.int32),
+            "child_ptr": np.empty(N + 1, np.int32), "child_idx": np.empty(max(N - 1, 0), np.int32),
+            "perm": np.empty(V, np.int32), "lo": np.empty(N, np.int32), "hi": np.empty(N, np.int32),
+        }
+        check(lib.gt_export_layout(self._handle, *[a.ctypes.data for a in out.values()]), "gt_export_layout")
+        return out
+
+    def reachability(self):
+        rows = np.empty(self.nnz, np.int64)
+        cols = np.empty(self.nnz, np.int64)
+        check(lib.gt_export_reachability(self._handle, rows.ctypes.data, cols.ctypes.data), "gt_export_reachability")
+        return rows, cols
+
+    def plan(self, tile_leaves=0, seg_positions=0):
+        check(lib.gt_plan(self._handle, tile_leaves, seg_positions), "gt_plan")
+
+    def plan_info(self):
+        self.plan()
+        info = _lib.PlanInfo()
+        check(lib.gt_get_plan_info(self._handle, ctypes.byref(info)), "gt_get_plan_info")
+        return {name: getattr(info, name) for name, _ in info._fields_}
+
+    def plan_array(self, name):
+        self.plan()
+        es = ctypes.c_int32()
+        n = lib.gt_export_plan_array(self._handle, name.encode(), None, 0, ctypes.byref(es))
+        if n < 0:
+            check(1, "gt_export_plan_array")
+        arr = np.empty(n, np.uint16 if es.value == 2 else np.int32)
+        lib.gt_export_plan_array(self._handle, name.encode(), arr.ctypes.data, n, ctypes.byref(es))
+        return arr
+
+    # ---- device ----------------------------------------------------------------------------------------
+    def ensure_device(self, index):
+        if index not in self._uploaded:
+            check(lib.gt_upload(self._handle, int(index)), "gt_upload")
+            self._uploaded.add(index)
+
+    def _workspace(self, index, slot, rows):
+        need = int(lib.gt_workspace_bytes(self._handle, min(max(rows, 1), _WORKSPACE_ROWS)))
+        key = (index, slot)
+        buf = self._workspaces.get(key)
+        if buf is None or buf.numel() < need:
+            buf = torch.empty(max(need, 256), dtype=torch.uint8, device=torch.device("cuda", index))
+            self._workspaces[key] = buf
+        return buf
+
+    def reduce(self, ws, ops, out_dtype=torch.float32, log_input=False, out_sum=None, out_max=None, slot=0, phases=0):
+        """Launch the mass kernels for a ``[B, V]`` CUDA tensor on its device's current stream.
+
+        Returns ``(out_sum, out_max)`` device tensors of shape ``[B, N]`` (``None`` for an op not asked for).
+        Nothing is synchronised here.
+        """
+        require_cuda()
+        if not (isinstance(ws, torch.Tensor) and ws.is_cuda and ws.dim() == 2):
+            raise ValueError("reduce expects a 2-D CUDA tensor")
+        if ws.shape[1] != self.V:
+            raise AssertionError([ws.shape[1], self.V])
+        if ws.dtype not in _IN_TYPES:
+            ws = ws.to(torch.float32)
+        if ws.shape[0] > 1 and ws.shape[1] > 1 and ws.stride(1) != 1:
+            ws = ws.contiguous()
+        elif ws.shape[1] > 1 and ws.stride(1) != 1:
+            ws = ws.contiguous()
+        B = ws.shape[0]
+        index = ws.device.index
+        self.ensure_device(index)
+        opmask = 0
+        for op in ops:
+            opmask |= OPS[op]
+
+        def _out(t):
+            if t is None:
+                return torch.empty((B, self.N), dtype=out_dtype, device=ws.device)
+            if not (t.is_cuda and t.device == ws.device and t.dtype == out_dtype and t.shape == (B, self.N) and (t.stride(1) == 1 or self.N <= 1)):
+                raise ValueError("out tensor must be a [B, N] tensor of the output dtype on the input's device")
+            return t
+
+        out_sum = _out(out_sum) if opmask & _lib.GT_OP_SUM else None
+        out_max = _out(out_max) if opmask & _lib.GT_OP_MAX else None
+        if B == 0:
+            return out_sum, out_max
+        ld_out = (out_sum if out_sum is not None else out_max).stride(0) if B > 1 else self.N
+        if out_sum is not None and out_max is not None and B > 1 and out_sum.stride(0) != out_max.stride(0):
+            raise ValueError("out_sum and out_max must share a row stride")
+        ld_ws = ws.stride(0) if B > 1 else max(self.V, 1)
+        work = self._workspace(index, slot, B)
+        with torch.cuda.device(index):
+            stream = torch.cuda.current_stream(index).cuda_stream
+            check(
+                lib.gt_weight_reduce(
+                    self._handle, ws.data_ptr(), _IN_TYPES[ws.dtype], B, ld_ws,
+                    out_sum.data_ptr() if out_sum is not None else None,
+                    out_max.data_ptr() if out_max is not None else None,
+                    _OUT_TYPES[out_dtype], ld_out, opmask, (_lib.GT_FLAG_LOG_INPUT if log_input else 0) | int(phases),
+                    work.data_ptr(), work.numel(), stream,
+                ),
+                "gt_weight_reduce",
+            )
+        return out_sum, out_max

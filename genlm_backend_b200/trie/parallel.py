@@ -1,0 +1,181 @@
+"""``ParallelTokenCharacterTrie``: batched ``weight_sum`` / ``weight_max`` on the GPU.
+
+Drop-in for the reference's ``genlm/backend/trie/parallel.py``.  The reference computes
+``ws[:, positions] @ M`` with a sparse leaf x node reachability matrix (``parallel.py:92-103``) and a
+``scatter_reduce_(amax)`` over every (leaf, ancestor) pair (``parallel.py:120-145``).  Here both are one
+pass of the sm_100a kernels behind ``gt_weight_reduce``: rows are permuted into DFS leaf order through
+shared memory, and every node is a short subtraction-free reduction over aligned leaf blocks.
+
+Same signatures, same float32 numpy results in the reference's node order.  Additions (never changes
+of defaults): ``*_tensor`` methods that keep results on the device, ``log_input=True`` to fuse the
+``exp`` of log-probabilities, and ``devices=[...]`` to shard batch rows over several GPUs.
+"""
+import numpy as np
+import torch
+
+from .base import TokenCharacterTrie
+from ._engine import require_cuda
+
+# rows per pipelined slice of the host->device->host path
+_PIPE_ROWS = 32
+_PIPE_SLOTS = 3
+
+
+class ParallelTokenCharacterTrie(TokenCharacterTrie):
+    """A GPU version of ``TokenCharacterTrie`` that performs weight sum and max operations in parallel."""
+
+    def __init__(self, decode, device=None, devices=None, **kwargs):
+        """
+        Args:
+            decode (list): the token vocabulary.
+            device (str|None): ``"cuda"``, ``"cpu"`` or ``None`` as in the reference (``parallel.py:8-13``).  It
+                names where ``_preprocess_ws`` stages the rows; the reduction itself always runs on a GPU.
+            devices (list[int]|None): CUDA device indices to shard batch rows over (default: the current one).
+        """
+        super().__init__(decode, **kwargs)
+        self.device = device or ("cuda" if torch.cuda.is_available() else "cpu")
+        if self.device not in ["cpu", "cuda"]:
+            raise ValueError(f"Invalid device: {device}. Must be 'cpu', 'cuda' or None")
+        self._devices = None if devices is None else [int(d) for d in devices]
+        self._reach = None
+        self._streams = {}
+        # position of each leaf's weight in the input rows (the identity: idx_to_leaf[:, 0])
+        self.positions = torch.tensor(self.idx_to_leaf[:, 0], dtype=torch.long, device=self.device)
+
+    # ---- reference attributes kept for compatibility (not used by the kernels) ----------------------------
+    def _reachability(self):
+        if self._reach is None:
+            rows, cols = self._engine.reachability()
+            self._reach = (torch.from_numpy(rows).to(self.device), torch.from_numpy(cols).to(self.device))
+        return self._reach
+
+    @property
+    def src_indices(self):
+        return self._reachability()[0]
+
+    @property
+    def dst_indices(self):
+        return self._reachability()[1]
+
+    @property
+    def M(self):
+        """Sparse CSR leaf x node reachability matrix of the reference (``parallel.py:33-64``)."""
+        rows, cols = self._reachability()
+        values = torch.ones(len(rows), device=self.device)
+        return torch.sparse_coo_tensor(
+            torch.stack([rows, cols]), values, (len(self.decode), len(self))
+        ).to_sparse_csr()
+
+    def _build_parent_map(self):
+        parent = self._layout["parent"]
+        return {child: int(p) for child, p in enumerate(parent.tolist()) if p >= 0}
+
+    # ---- input handling ------------------------------------------------------------------------------------
+    def _preprocess_ws(self, batch_ws):
+        """Rows -> stacked float32 tensor on ``self.device`` (``parallel.py:66-75``)."""
+        processed = []
+        for ws in batch_ws:
+            if not isinstance(ws, torch.Tensor):
+                ws = torch.tensor(ws, device=self.device, dtype=torch.float32)
+            elif ws.device.type != self.device or ws.dtype != torch.float32:
+                ws = ws.to(device=self.device, dtype=torch.float32)
+            assert ws.shape[0] == len(self.decode), [ws.shape[0], len(self.decode)]
+            processed.append(ws)
+        return torch.stack(processed)
+
+    def _as_batch(self, ws):
+        """Anything the reference accepts -> one ``[B, V]`` tensor, without touching dtype or device when the
+        input already is a 2-D float tensor (so fp16 / bf16 rows are converted inside the kernel)."""
+        if isinstance(ws, torch.Tensor) and ws.dim() == 2 and ws.dtype in (torch.float16, torch.bfloat16, torch.float32):
+            assert ws.shape[1] == len(self.decode), [ws.shape[1], len(self.decode)]
+            return ws
+        return self._preprocess_ws(ws)
+
+    def _device_list(self):
+        require_cuda()
+        return self._devices if self._devices else [torch.cuda.current_device()]
+
+    # ---- device-resident API (additions) ---------------------------------------------------------------------
+    def batch_weight_tensor(self, ws, ops=("sum",), log_input=False, out_sum=None, out_max=None):
+        """Node masses for a ``[B, V]`` batch, kept on the GPU.  Returns ``(sum, max)`` float32 ``[B, N]`` tensors
+        (``None`` for an op not requested).  Launches on the current stream of the input's device; no sync."""
+        ws = self._as_batch(ws)
+        if not ws.is_cuda:
+            ws = ws.to(torch.device("cuda", self._device_list()[0]), non_blocking=True)
+        return self._engine.reduce(ws, ops, out_dtype=torch.float32, log_input=log_input, out_sum=out_sum, out_max=out_max)
+
+    def batch_weight_sum_tensor(self, ws, log_input=False, out=None):
+        return self.batch_weight_tensor(ws, ("sum",), log_input=log_input, out_sum=out)[0]
+
+    def batch_weight_max_tensor(self, ws, log_input=False, out=None):
+        return self.batch_weight_tensor(ws, ("max",), log_input=log_input, out_max=out)[1]
+
+    # ---- reference API: numpy results on the host --------------------------------------------------------------
+    def _pipe_streams(self, index):
+        if index not in self._streams:
+            with torch.cuda.device(index):
+                self._streams[index] = [torch.cuda.Stream(device=index) for _ in range(_PIPE_SLOTS)]
+        return self._streams[index]
+
+    def _batch_to_host(self, ws, ops, log_input=False):
+        """Run ``ops`` over the batch and return host arrays.  Rows are split contiguously over the configured
+        GPUs; on each GPU slices of ``_PIPE_ROWS`` rows flow H2D -> kernels -> D2H on rotating streams so the
+        copies overlap the kernels and each other.  Results land in pinned host memory that the returned
+        numpy arrays own."""
+        ws = self._as_batch(ws)
+        B, N = ws.shape[0], len(self)
+        devices = self._device_list()
+        outs = {op: torch.empty((B, N), dtype=torch.float32, pin_memory=True) for op in ops}
+        if B == 0:
+            return {op: o.numpy() for op, o in outs.items()}
+        per = (B + len(devices) - 1) // len(devices)
+        used = []
+        keep = []
+        for di, index in enumerate(devices):
+            lo, hi = di * per, min(B, (di + 1) * per)
+            if lo >= hi:
+                continue
+            dev = torch.device("cuda", index)
+            streams = self._pipe_streams(index)
+            start = torch.cuda.Event()
+            start.record(torch.cuda.current_stream(ws.device.index if ws.is_cuda else index))
+            for k, r0 in enumerate(range(lo, hi, _PIPE_ROWS)):
+                r1 = min(hi, r0 + _PIPE_ROWS)
+                st = streams[k % _PIPE_SLOTS]
+                st.wait_event(start)  # inputs produced on the caller's stream are ready
+                with torch.cuda.device(index), torch.cuda.stream(st):
+                    chunk = ws[r0:r1]
+                    if chunk.device != dev:
+                        chunk = chunk.to(dev, non_blocking=True)
+                    o_sum, o_max = self._engine.reduce(chunk, ops, log_input=log_input, slot=k % _PIPE_SLOTS)
+                    if o_sum is not None:
+                        outs["sum"][r0:r1].copy_(o_sum, non_blocking=True)
+                    if o_max is not None:
+                        outs["max"][r0:r1].copy_(o_max, non_blocking=True)
+                    keep.append((chunk, o_sum, o_max))
+            used.extend(streams)
+        for st in used:
+            st.synchronize()
+        del keep
+        return {op: o.numpy() for op, o in outs.items()}
+
+    def weight_sum(self, ws):
+        """Node sums for one weight vector -> ``float32[num_nodes]`` (``parallel.py:77-90``)."""
+        return self.batch_weight_sum(self._preprocess_ws([ws]))[0]
+
+    def batch_weight_sum(self, ws):
+        """Node sums for a batch -> ``float32[batch, num_nodes]`` numpy array (``parallel.py:92-103``)."""
+        return self._batch_to_host(ws, ("sum",))["sum"]
+
+    def weight_max(self, ws):
+        """Node maxima for one weight vector -> ``float32[num_nodes]`` (``parallel.py:105-118``)."""
+        return self.batch_weight_max(self._preprocess_ws([ws]))[0]
+
+    def batch_weight_max(self, ws):
+        """Node maxima for a batch -> ``float32[batch, num_nodes]`` numpy array (``parallel.py:120-145``)."""
+        return self._batch_to_host(ws, ("max",))["max"]
+
+    def batch_weight_sum_max(self, ws, log_input=False):
+        """Both reductions from one staging pass -> ``(sums, maxes)`` numpy arrays."""
+        out = self._batch_to_host(ws, ("sum", "max"), log_input=log_input)
+        return out["sum"], out["max"]

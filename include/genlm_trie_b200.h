@@ -1,0 +1,165 @@
+/*
+ * genlm_trie_b200.h -- C ABI of the B200-native token-character-trie mass path.
+ *
+ * This is the drop-in boundary for genlm-backend's trie hot path.  The reference
+ * has no FFI of its own (it is Python over numba / torch library kernels), so
+ * every entry point below names the reference Python code it replaces
+ * (paths relative to the genlm-backend repository root):
+ *
+ *   gt_build / gt_export_*      genlm/backend/trie/base.py:13-122   (TokenCharacterTrie.__init__, _rename,
+ *                                                                    _order, _order_full)
+ *   gt_export_reachability      genlm/backend/trie/parallel.py:21-64 (_build_parent_map,
+ *                                                                    _build_reachability_matrix)
+ *   gt_weight_sum_*             genlm/backend/trie/base.py:346-368   (_update_trie_numba_sum)
+ *                               genlm/backend/trie/parallel.py:92-103 (batch_weight_sum: sparse.mm)
+ *   gt_weight_max_*             genlm/backend/trie/base.py:371-393   (_update_trie_numba_max)
+ *                               genlm/backend/trie/parallel.py:120-145 (batch_weight_max: scatter_reduce amax)
+ *   gt_lse_sample               README.md:82-91 / genlm/backend/llm/base.py:131-146
+ *                               (masked logsumexp + multinomial of the SMC particle step)
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on failure; gt_last_error() returns a
+ *     thread-local message for the last failure on the calling thread;
+ *   - plain pointers and sizes only, no torch / numpy types;
+ *   - all device pointers are caller-owned; nothing is allocated per call; every launch goes to the
+ *     caller-supplied stream (a cudaStream_t passed as void*); no hidden synchronisation;
+ *   - node ids, leaf ids and row layout are exactly the reference's (post-order ids, root = N-1).
+ */
+#ifndef GENLM_TRIE_B200_H
+#define GENLM_TRIE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct gt_trie gt_trie; /* opaque: host layout + per-device resident metadata */
+typedef void* gt_stream;        /* cudaStream_t */
+
+/* ---- status ------------------------------------------------------------------------------- */
+#define GT_OK 0
+#define GT_ERR_ARG 1     /* bad argument (null pointer, negative size, row stride too small ...) */
+#define GT_ERR_CUDA 2    /* a CUDA runtime call failed; message has the cudaError string */
+#define GT_ERR_STATE 3   /* trie not uploaded to the current device, workspace too small ... */
+#define GT_ERR_LIMIT 4   /* vocabulary exceeds a compiled-in limit */
+
+const char* gt_last_error(void);
+int gt_version(void);
+
+/* ---- builder (host only; works without a GPU) --------------------------------------------- */
+
+/* Build the trie over n_tokens items.  Item i spells symbols[offsets[i] .. offsets[i+1]).
+ * Symbols 0..255 are bytes; symbols >= 256 stand for non-byte edge labels (the reference iterates
+ * arbitrary iterables, base.py:45-48).  Each item gets its own leaf (base.py:55-61), so duplicate
+ * byte strings are legal here; the (bytes, token_id) duplicate check of base.py:63-64 is the
+ * caller's job.  Node ids are the reference's post-order numbering (base.py:80-83, 236-247). */
+int gt_build(const int32_t* symbols, const int64_t* offsets, int64_t n_tokens, gt_trie** out);
+void gt_free(gt_trie* t);
+
+int64_t gt_num_tokens(const gt_trie* t); /* V = len(decode)                      */
+int64_t gt_num_nodes(const gt_trie* t);  /* N = len(children)                    */
+int64_t gt_root(const gt_trie* t);       /* == N-1                               */
+int64_t gt_num_reach(const gt_trie* t);  /* nnz of the leaf x node reachability  */
+int64_t gt_max_depth(const gt_trie* t);
+
+/* Copy layout arrays out (any pointer may be NULL to skip it).
+ *   leaf_node[V]     node id of the leaf of item i            (idx_to_leaf[:,1], base.py:115-117)
+ *   parent[N]        parent node id, -1 for the root          (parallel.py:21-31)
+ *   edge_label[N]    label of the edge into the node: symbol >= 0, or -1-i for the leaf of item i,
+ *                    INT32_MIN for the root                   (keys of children[..], base.py:50-58)
+ *   child_ptr[N+1], child_idx[N-1]   children CSR in insertion order (== ascending id order, which
+ *                    is what jump[] holds, base.py:120-122)
+ *   perm[V]          DFS leaf rank -> item position
+ *   lo[N], hi[N]     every node's leaves are DFS ranks [lo, hi) */
+int gt_export_layout(const gt_trie* t, int32_t* leaf_node, int32_t* parent, int32_t* edge_label,
+                     int32_t* child_ptr, int32_t* child_idx, int32_t* perm, int32_t* lo, int32_t* hi);
+
+/* (row, col) pairs of the reachability matrix in the reference's order: for item i its leaf, then
+ * each ancestor up to the root (parallel.py:42-54).  Arrays of gt_num_reach() entries. */
+int gt_export_reachability(const gt_trie* t, int64_t* rows, int64_t* cols);
+
+/* ---- device plan -------------------------------------------------------------------------- */
+
+/* Build the tile plan (once) and make its metadata resident on `device`.  Idempotent per device. */
+int gt_upload(gt_trie* t, int device);
+
+typedef struct gt_plan_info {
+    int64_t n_tokens, n_nodes;
+    int32_t tile_leaves;     /* T: DFS-ordered leaves per tile                       */
+    int32_t seg_positions;   /* Q: vocabulary positions per source segment           */
+    int32_t n_tiles, n_segs;
+    int32_t rows_per_item;   /* R: rows a CTA processes per metadata load            */
+    int32_t n_span;          /* nodes whose leaf range crosses a tile boundary       */
+    int64_t span_terms;      /* total frontier terms summed by the fix-up            */
+    int32_t max_levels;      /* deepest in-tile dependency chain of branching nodes  */
+    int32_t max_tile_values; /* largest per-tile value array (leaf + branching slots)*/
+    int64_t staged_row_elems;/* elements per row of the tile-major staging buffer    */
+    int64_t meta_bytes;      /* device-resident metadata                              */
+} gt_plan_info;
+int gt_get_plan_info(const gt_trie* t, gt_plan_info* info);
+
+/* Host-only: build the tile plan without touching a device (gt_upload calls this with its defaults when
+ * no plan exists yet).  tile_leaves: power of two in [1024, 8192]; seg_positions: multiple of 4, <= 32768;
+ * pass 0 for the defaults.  Fails if a plan already exists with different parameters. */
+int gt_plan(gt_trie* t, int32_t tile_leaves, int32_t seg_positions);
+
+/* Host-only introspection of the plan arrays, used by the CPU tests that emulate the kernels' data flow.
+ * `name` is one of: p1_chunk_ptr p1_zoff p1_src z_tile_off p2_slot br_ptr br_child_ptr br_child
+ * tile_node_lo node_slot span_node span_ptr span_term.  Returns the element count (or -1), and copies
+ * min(count, capacity) elements into dst when dst != NULL.  elem_size receives 2 or 4. */
+int64_t gt_export_plan_array(const gt_trie* t, const char* name, void* dst, int64_t capacity, int32_t* elem_size);
+
+/* Caller-owned scratch needed for a batch of up to max_rows rows on the current device. */
+size_t gt_workspace_bytes(const gt_trie* t, int64_t max_rows);
+
+/* ---- trie mass kernels -------------------------------------------------------------------- */
+
+#define GT_FLAG_LOG_INPUT 1u /* rows hold log-weights: exp() is fused into the load (-inf -> 0) */
+/* Profiling aids: restrict a call to some phases (default: all).  Used by bench.py to time one kernel in
+ * isolation with CUDA events; results are only complete when all three phases have run in order. */
+#define GT_FLAG_PHASE_PERMUTE 0x100u
+#define GT_FLAG_PHASE_TILE 0x200u
+#define GT_FLAG_PHASE_SPAN 0x400u
+#define GT_FLAG_PHASE_MASK 0x700u
+
+/* Input / output element types. */
+#define GT_F32 0
+#define GT_F64 1
+#define GT_F16 2
+#define GT_BF16 3
+
+#define GT_OP_SUM 1
+#define GT_OP_MAX 2
+
+/* out[b, n] = sum (or max) over the leaves under node n of ws[b, item(leaf)],  b < n_rows, n < N.
+ *   ws       device pointer, row b starts at ws + b*ld_ws elements, V elements per row, type in_type
+ *   out_sum / out_max   device pointers (one may be NULL when the op is not requested), row stride
+ *            ld_out elements, type out_type (GT_F32 or GT_F64)
+ *   ops      GT_OP_SUM | GT_OP_MAX
+ *   workspace  device scratch of at least gt_workspace_bytes(t, n_rows) bytes
+ * Sums are accumulated in fp64 and rounded once; max is exact. */
+int gt_weight_reduce(const gt_trie* t, const void* ws, int in_type, int64_t n_rows, int64_t ld_ws,
+                     void* out_sum, void* out_max, int out_type, int64_t ld_out, unsigned ops,
+                     unsigned flags, void* workspace, size_t workspace_bytes, gt_stream stream);
+
+/* ---- SMC row op: masked logsumexp + one categorical draw per row ------------------------- */
+
+#define GT_MASK_NONE 0
+#define GT_MASK_ADD_F32 1 /* additive float mask ({0,-inf} in the reference idiom, README.md:59-70) */
+#define GT_MASK_BOOL_U8 2 /* one byte per token, 0 = masked out                                   */
+#define GT_MASK_BITS_U32 3/* bit i%32 of word i/32, 0 = masked out                                */
+
+/* For each row b: masked = logp[b]/temperature + mask;  logZ[b] = logsumexp(masked);
+ * tok[b] ~ Categorical(exp(masked - logZ[b])) by inverse CDF with one Philox uniform per row,
+ * counter = (seed, offset + b).  Rows with no mass get logZ = -inf, tok = -1.
+ *   mask_ld   elements (floats / bytes / words) between consecutive rows' masks; 0 = shared mask */
+int gt_lse_sample(const void* logp, int in_type, int64_t n_rows, int64_t n_vocab, int64_t ld_logp,
+                  const void* mask, int mask_kind, int64_t mask_ld, float temperature,
+                  uint64_t seed, uint64_t offset, float* logZ_out, int32_t* tok_out, gt_stream stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GENLM_TRIE_B200_H */

@@ -1,0 +1,237 @@
+"""GPU parity tests for the trie mass path (run with -m gpu on the B200 box).
+
+Oracle: the C restatement of the reference's numba loops (oracle/trie_oracle.c, base.py:346-393) and golden
+outputs of the reference itself (tests/golden).  Bars: weight_max and all indexing bit-exact; weight_sum within
+fp32 relative 1e-5 of the fp64 path (north star) -- we assert the much tighter 2e-6 the design guarantees, and
+exact zeros.
+"""
+import hashlib
+import warnings
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from genlm_backend_b200 import Token, TokenCharacterTrie, ParallelTokenCharacterTrie
+from genlm_backend_b200.synthetic import synth_vocab, dirichlet_rows
+from helpers import load_golden, unflat, tokens, rel_err, EOS
+
+pytestmark = pytest.mark.gpu
+
+SUM_RTOL = 2e-6  # design bound (fp32 pyramid + short fp32 term sums); the contract is 1e-5
+
+
+def oracle_for(trie):
+    lay = trie._layout
+    return oracle.OracleLayout(trie.idx_to_leaf, lay["child_ptr"], lay["child_idx"])
+
+
+def check_against(trie, ws, want_sum, want_max, f64=False):
+    """ws: numpy [B, V]; wants: float64 [B, N] from the oracle / reference."""
+    have_sum = trie.batch_weight_sum(torch.tensor(ws))
+    have_max = trie.batch_weight_max(torch.tensor(ws))
+    assert have_sum.shape == want_sum.shape and have_max.shape == want_max.shape
+    assert have_sum.dtype == (np.float64 if f64 else np.float32)
+    r, z = rel_err(have_sum, want_sum)
+    assert r <= (1e-12 if f64 else SUM_RTOL), r
+    assert z == 0.0
+    want_max = want_max if f64 else want_max.astype(np.float32)
+    assert np.array_equal(have_max, want_max)
+
+
+@pytest.mark.parametrize("name", ["toy", "edge", "synth3000"])
+@pytest.mark.parametrize("cls", [ParallelTokenCharacterTrie, TokenCharacterTrie])
+def test_golden_reference_outputs(name, cls):
+    g = load_golden(name)
+    trie = cls(tokens(unflat(g["blob"], g["lens"])))
+    f64 = cls is TokenCharacterTrie
+    check_against(trie, g["ws"], g["seq_sum"], g["seq_max"], f64=f64)
+    if not f64:  # the reference's own fp32 torch path, to its own tolerance (tests/test_trie.py:108)
+        np.testing.assert_allclose(trie.batch_weight_sum(torch.tensor(g["ws"])), g["par_sum"], rtol=1e-5, atol=1e-8)
+        assert np.array_equal(trie.batch_weight_max(torch.tensor(g["ws"])), g["par_max"])
+
+
+def test_golden_sentinel_and_plain_bytes():
+    g = load_golden("sentinel")
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        dec = [Token(0, b"ab"), Token(1, b""), Token(2, b"ab"), Token(3, b"a"), EOS(), b"plain"]
+        trie = ParallelTokenCharacterTrie(dec)
+    check_against(trie, g["ws"], g["seq_sum"], g["seq_max"])
+
+
+@pytest.mark.parametrize("V", [50257, 128256])
+def test_golden_baseline_sizes(V):
+    """BASELINE.json configs 1 and 2: sampled node values, probe dot products and the max digest of the reference."""
+    g = load_golden(f"synth{V}")
+    trie = ParallelTokenCharacterTrie(synth_vocab(V))
+    assert len(trie) == int(g["n_nodes"]) and trie.root == int(g["root"])
+    ws = dirichlet_rows(2, V, alpha=0.1, seed=1)
+    hs = trie.batch_weight_sum(torch.tensor(ws))
+    hm = trie.batch_weight_max(torch.tensor(ws))
+    pick = g["pick"]
+    r, z = rel_err(hs[:, pick], g["seq_sum_pick"])
+    assert r <= SUM_RTOL and z == 0.0
+    assert np.array_equal(hm[:, pick], g["seq_max_pick"].astype(np.float32))
+    probe = np.random.default_rng(4).standard_normal(len(trie))
+    np.testing.assert_allclose(hs.astype(np.float64) @ probe, g["seq_sum_probe"], rtol=1e-5)
+    digest = np.frombuffer(hashlib.sha256(np.ascontiguousarray(hm).tobytes()).digest(), dtype=np.uint8)
+    assert np.array_equal(digest, g["seq_max_digest"])  # weight_max bit-exact over all 2 x N values
+    # sequential class at full size: float64 end to end
+    seq = TokenCharacterTrie(synth_vocab(V))
+    h64 = seq.batch_weight_sum(torch.tensor(ws))
+    r, z = rel_err(h64[:, pick], g["seq_sum_pick"])
+    assert r <= 1e-12 and z == 0.0
+
+
+@pytest.mark.parametrize("V,T,Q", [(300, 1024, 64), (5000, 1024, 512), (5000, 2048, 8192), (20011, 4096, 8192),
+                                   (20011, 8192, 4096), (20011, 1024, 32768)])
+def test_plan_shapes_against_oracle(V, T, Q):
+    """Different tile / segment sizes (more spanning nodes, partial tiles, odd V so rows are 16-byte unaligned)."""
+    trie = ParallelTokenCharacterTrie(synth_vocab(V, seed=3))
+    trie._engine.plan(T, Q)
+    o = oracle_for(trie)
+    ws = dirichlet_rows(5, V, alpha=0.1, seed=2)
+    check_against(trie, ws, o.weight_sum(ws), o.weight_max(ws))
+
+
+@pytest.mark.parametrize("B", [0, 1, 2, 3, 7, 64, 131])
+def test_batch_sizes(B):
+    V = 4099
+    trie = ParallelTokenCharacterTrie(synth_vocab(V, seed=5))
+    o = oracle_for(trie)
+    ws = dirichlet_rows(max(B, 1), V, alpha=0.3, seed=B)[:B]
+    hs = trie.batch_weight_sum(torch.tensor(ws))
+    hm = trie.batch_weight_max(torch.tensor(ws))
+    assert hs.shape == (B, len(trie)) and hm.shape == (B, len(trie))
+    if B:
+        r, z = rel_err(hs, o.weight_sum(ws))
+        assert r <= SUM_RTOL and z == 0.0
+        assert np.array_equal(hm, o.weight_max(ws).astype(np.float32))
+
+
+def test_small_workspace_chunks_the_batch():
+    """The C side chunks a batch that does not fit the caller's scratch."""
+    from genlm_backend_b200 import _lib
+
+    V, B = 3001, 37
+    trie = ParallelTokenCharacterTrie(synth_vocab(V, seed=6))
+    eng = trie._engine
+    ws = torch.tensor(dirichlet_rows(B, V, alpha=0.2, seed=9), device="cuda")
+    eng.ensure_device(0)
+    out = torch.empty((B, len(trie)), dtype=torch.float32, device="cuda")
+    need_one = int(_lib.lib.gt_workspace_bytes(eng._handle, 1))
+    work = torch.empty(need_one // 2 * 5 // 2, dtype=torch.uint8, device="cuda")  # ~5 float rows
+    _lib.check(_lib.lib.gt_weight_reduce(eng._handle, ws.data_ptr(), _lib.GT_F32, B, ws.stride(0), out.data_ptr(), None,
+                                         _lib.GT_F32, out.stride(0), _lib.GT_OP_SUM, 0, work.data_ptr(), work.numel(),
+                                         torch.cuda.current_stream().cuda_stream), "gt_weight_reduce")
+    torch.cuda.synchronize()
+    r, z = rel_err(out.cpu().numpy(), oracle_for(trie).weight_sum(ws.cpu().numpy()))
+    assert r <= SUM_RTOL and z == 0.0
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16, torch.float64])
+def test_input_dtypes(dtype):
+    V = 6007
+    trie = ParallelTokenCharacterTrie(synth_vocab(V, seed=8))
+    o = oracle_for(trie)
+    ws = torch.tensor(dirichlet_rows(3, V, alpha=0.5, seed=4)).to(dtype)
+    as32 = ws.to(torch.float32).numpy()  # the kernel converts each element to fp32 first
+    hs, hm = trie.batch_weight_tensor(ws.cuda(), ops=("sum", "max"))
+    r, z = rel_err(hs.cpu().numpy(), o.weight_sum(as32))
+    assert r <= SUM_RTOL and z == 0.0
+    assert np.array_equal(hm.cpu().numpy(), o.weight_max(as32).astype(np.float32))
+    # the sequential class keeps fp64 inputs in fp64
+    if dtype == torch.float64:
+        seq = TokenCharacterTrie(synth_vocab(V, seed=8))
+        w64 = np.random.default_rng(0).dirichlet(np.full(V, 0.5), size=2)
+        r, z = rel_err(seq.batch_weight_sum(w64), o.weight_sum(w64))
+        assert r <= 1e-12 and z == 0.0
+        assert np.array_equal(seq.batch_weight_max(w64), o.weight_max(w64))
+
+
+def test_log_input_fuses_exp():
+    V = 5003
+    trie = ParallelTokenCharacterTrie(synth_vocab(V, seed=10))
+    ws = dirichlet_rows(3, V, alpha=0.1, seed=11)
+    with np.errstate(divide="ignore"):
+        logw = np.log(ws)  # -inf for exact zeros
+    hs, hm = trie.batch_weight_tensor(torch.tensor(logw).cuda(), ops=("sum", "max"), log_input=True)
+    back = np.exp(logw.astype(np.float64))
+    o = oracle_for(trie)
+    r, z = rel_err(hs.cpu().numpy(), o.weight_sum(back))
+    assert r <= 1e-5 and z == 0.0  # expf adds ~1e-7 per leaf on top of the reduction error
+    r, z = rel_err(hm.cpu().numpy(), o.weight_max(back))
+    assert r <= 1e-6 and z == 0.0
+
+
+def test_reference_input_forms_and_errors():
+    """tests/test_trie.py:210-264 (lists, numpy, tuples of rows) and parallel.py:73 (length assert)."""
+    dec = [Token(0, b"a"), Token(1, b"b"), Token(2, b"ab"), Token(3, b"<eos>")]
+    par = ParallelTokenCharacterTrie(dec)
+    seq = TokenCharacterTrie(dec)
+    want = [0.1, 0.2, 0.2, 0.3, 0.2, 0.2, 0.5, 0.5, 0.5, 0.5, 0.5, 0.5, 1.0]
+    for ws in ([0.1, 0.2, 0.2, 0.5], np.array([0.1, 0.2, 0.2, 0.5]), torch.tensor([0.1, 0.2, 0.2, 0.5]),
+               torch.tensor([0.1, 0.2, 0.2, 0.5], device="cuda")):
+        np.testing.assert_allclose(par.weight_sum(ws), want, rtol=1e-6)
+        np.testing.assert_allclose(seq.weight_sum(ws), want, rtol=1e-6)
+        assert par.weight_sum(ws).dtype == np.float32 and seq.weight_sum(ws).dtype == np.float64
+    rows = (torch.tensor([0.1, 0.2, 0.2, 0.5]), torch.tensor([0.0, 0.3, 0.6, 0.1]))  # what the async wrapper passes
+    assert par.batch_weight_max(rows).shape == (2, 13)
+    assert seq.batch_weight_max(rows).shape == (2, 13)
+    with pytest.raises(AssertionError):
+        par.weight_sum(torch.tensor([0.1, 0.2, 0.2]))
+    with pytest.raises(AssertionError):
+        seq.weight_sum(torch.tensor([0.1, 0.2, 0.2]))
+    processed = par._preprocess_ws(np.array([[0.5] * 4, [0.1] * 4]))
+    assert isinstance(processed, torch.Tensor) and processed.device.type == par.device and processed.dtype == torch.float32
+
+
+def test_properties_at_full_size():
+    """Size-independent properties at BASELINE config 5's vocabulary (151,665 tokens, rows not 16-byte aligned)."""
+    V, B = 151665, 6
+    trie = ParallelTokenCharacterTrie(synth_vocab(V))
+    assert len(trie) == 407861
+    lay = trie._layout
+    a = torch.tensor(dirichlet_rows(B, V, alpha=1.0, seed=21), device="cuda")
+    b = torch.tensor(dirichlet_rows(B, V, alpha=0.1, seed=22), device="cuda")
+    sa, ma = trie.batch_weight_tensor(a, ops=("sum", "max"))
+    sb, mb = trie.batch_weight_tensor(b, ops=("sum", "max"))
+    sab = trie.batch_weight_sum_tensor(a + b)
+    torch.cuda.synchronize()
+    # leaves carry their token's weight bit-exactly, for both ops
+    leaf = torch.tensor(lay["leaf_node"].astype(np.int64), device="cuda")
+    assert torch.equal(sa[:, leaf], a) and torch.equal(ma[:, leaf], a) and torch.equal(mb[:, leaf], b)
+    # root: total mass / global max
+    np.testing.assert_allclose(sa[:, trie.root].cpu().numpy(), a.double().sum(1).cpu().numpy(), rtol=1e-6)
+    assert torch.equal(mb[:, trie.root], b.max(1).values)
+    # linearity of the sum
+    np.testing.assert_allclose(sab.cpu().numpy(), (sa + sb).cpu().numpy(), rtol=1e-5, atol=1e-30)
+    # every internal node: sum == sum of children (fp64 check), max == max of children (exact)
+    ptr = torch.tensor(lay["child_ptr"].astype(np.int64), device="cuda")
+    idx = torch.tensor(lay["child_idx"].astype(np.int64), device="cuda")
+    owner = torch.repeat_interleave(torch.arange(len(trie), device="cuda"), ptr[1:] - ptr[:-1])
+    internal = (ptr[1:] - ptr[:-1]) > 0
+    for s, m in ((sa, ma), (sb, mb)):
+        tot = torch.zeros((B, len(trie)), dtype=torch.float64, device="cuda").index_add_(1, owner, s[:, idx].double())
+        err = ((tot - s.double()).abs() / tot.clamp_min(1e-300))[:, internal]
+        assert float(err.max()) <= 4e-6
+        assert bool(((tot == 0) == (s == 0))[:, internal].all())
+        mx = torch.full((B, len(trie)), -1.0, device="cuda").scatter_reduce_(1, owner.expand(B, -1), m[:, idx], reduce="amax")
+        assert torch.equal(mx[:, internal], m[:, internal])
+    # idempotence: max over the max-leaves again
+    assert torch.equal(trie.batch_weight_max_tensor(ma[:, leaf]), ma)
+
+
+def test_multi_device_row_sharding_matches_single():
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    V, B = 9001, 13
+    dec = synth_vocab(V, seed=12)
+    ws = torch.tensor(dirichlet_rows(B, V, alpha=0.2, seed=13))
+    one = ParallelTokenCharacterTrie(dec, devices=[0])
+    many = ParallelTokenCharacterTrie(dec, devices=list(range(n)))
+    assert np.array_equal(one.batch_weight_sum(ws), many.batch_weight_sum(ws))
+    assert np.array_equal(one.batch_weight_max(ws), many.batch_weight_max(ws))
