@@ -23,6 +23,9 @@
 #include <limits>
 #include <type_traits>
 #include <algorithm>
+#include <map>
+#include <mutex>
+#include <utility>
 
 #include "trie_internal.h"
 
@@ -63,12 +66,14 @@ void free_device_plan(DevicePlan* d) {
         cudaError_t e_ = (call);                                                          \
         if (e_ != cudaSuccess) {                                                          \
             gt::set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+            (void)cudaGetLastError(); /* do not leave the error for the next, unrelated call */        \
             return GT_ERR_CUDA;                                                           \
         }                                                                                 \
     } while (0)
 
 constexpr int kThreads = 512;
 constexpr int OP_SUM = 1, OP_MAX = 2;
+constexpr size_t kMaxSmem = 200 * 1024;  // dynamic shared memory we are willing to ask for per CTA
 constexpr int kSegPad = 8;  // slack so a row segment can be stored at its global 16-byte phase
 
 // ---- small device helpers -----------------------------------------------------------------------
@@ -413,17 +418,25 @@ constexpr int R_F64 = 1;  // rows per CTA, double pipeline
 template <typename VT, int R> static size_t permute_smem(const PlanView& v) { return (size_t)R * (v.Q + kSegPad) * sizeof(VT); }
 template <typename VT, int R> static size_t tile_smem(const PlanView& v) { return (size_t)R * v.SV * sizeof(VT); }
 
-// Opt in to > 48 KB dynamic shared memory once per (kernel instantiation, device, size): the attribute call is
-// kept off the steady-state launch path (and out of CUDA graph captures).
-template <typename K> static cudaError_t allow_smem(K kernel, size_t bytes) {
-    static size_t granted[64] = {0};  // one static per instantiation of this template
+// Opt in to > 48 KB dynamic shared memory once per (kernel, device, size): the attribute call is kept off the
+// steady-state launch path (and out of CUDA graph captures).  Keyed by the kernel's address: instantiations
+// with the same signature share a function type.
+static cudaError_t allow_smem_impl(const void* kernel, size_t bytes) {
+    static std::mutex mu;
+    static std::map<std::pair<const void*, int>, size_t> granted;
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
-    if (dev >= 0 && dev < 64 && granted[dev] >= bytes) return cudaSuccess;
+    std::lock_guard<std::mutex> lock(mu);
+    auto key = std::make_pair(kernel, dev);
+    auto it = granted.find(key);
+    if (it != granted.end() && it->second >= bytes) return cudaSuccess;
     e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-    if (e == cudaSuccess && dev >= 0 && dev < 64) granted[dev] = bytes;
+    if (e == cudaSuccess) granted[key] = bytes;
     return e;
+}
+template <typename K> static cudaError_t allow_smem(K kernel, size_t bytes) {
+    return allow_smem_impl(reinterpret_cast<const void*>(kernel), bytes);
 }
 
 template <typename VT, typename IN_T, int R>
@@ -472,13 +485,18 @@ static int reduce_typed(const PlanView& v, const void* ws, int in_type, int64_t 
         const void* wsr = static_cast<const char*>(ws) + (size_t)r0 * ld_ws * in_size;
         int rc = GT_OK;
         if (v.NT > 0 && (phases & GT_FLAG_PHASE_PERMUTE)) {
+            // rows per CTA in the permute phase: R unless the segment buffer would not fit in shared memory
+            const bool wide = permute_smem<VT, R>(v) <= kMaxSmem;
+#define GT_PERMUTE(IN_T) (wide ? launch_permute<VT, IN_T, R>(v, wsr, ld_ws, z, rows, log_input, st) \
+                               : launch_permute<VT, IN_T, 1>(v, wsr, ld_ws, z, rows, log_input, st))
             switch (in_type) {
-                case GT_F32: rc = launch_permute<VT, float, R>(v, wsr, ld_ws, z, rows, log_input, st); break;
-                case GT_F64: rc = launch_permute<VT, double, R>(v, wsr, ld_ws, z, rows, log_input, st); break;
-                case GT_F16: rc = launch_permute<VT, __half, R>(v, wsr, ld_ws, z, rows, log_input, st); break;
-                case GT_BF16: rc = launch_permute<VT, __nv_bfloat16, R>(v, wsr, ld_ws, z, rows, log_input, st); break;
+                case GT_F32: rc = GT_PERMUTE(float); break;
+                case GT_F64: rc = GT_PERMUTE(double); break;
+                case GT_F16: rc = GT_PERMUTE(__half); break;
+                case GT_BF16: rc = GT_PERMUTE(__nv_bfloat16); break;
                 default: set_error("unknown input type %d", in_type); return GT_ERR_ARG;
             }
+#undef GT_PERMUTE
             if (rc != GT_OK) return rc;
         }
         if (ops & GT_OP_SUM) {

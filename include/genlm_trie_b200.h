@@ -101,7 +101,7 @@ typedef struct gt_plan_info {
 int gt_get_plan_info(const gt_trie* t, gt_plan_info* info);
 
 /* Host-only: build the tile plan without touching a device (gt_upload calls this with its defaults when
- * no plan exists yet).  tile_leaves: power of two in [1024, 8192]; seg_positions: multiple of 4, <= 32768;
+ * no plan exists yet).  tile_leaves: power of two in [1024, 8192]; seg_positions: multiple of 4, <= 16384;
  * pass 0 for the defaults.  Fails if a plan already exists with different parameters. */
 int gt_plan(gt_trie* t, int32_t tile_leaves, int32_t seg_positions);
 

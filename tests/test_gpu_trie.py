@@ -86,7 +86,7 @@ def test_golden_baseline_sizes(V):
 
 
 @pytest.mark.parametrize("V,T,Q", [(300, 1024, 64), (5000, 1024, 512), (5000, 2048, 8192), (20011, 4096, 8192),
-                                   (20011, 8192, 4096), (20011, 1024, 32768)])
+                                   (20011, 8192, 4096), (20011, 1024, 16384)])
 def test_plan_shapes_against_oracle(V, T, Q):
     """Different tile / segment sizes (more spanning nodes, partial tiles, odd V so rows are 16-byte unaligned)."""
     trie = ParallelTokenCharacterTrie(synth_vocab(V, seed=3))
@@ -162,8 +162,9 @@ def test_log_input_fuses_exp():
     o = oracle_for(trie)
     r, z = rel_err(hs.cpu().numpy(), o.weight_sum(back))
     assert r <= 1e-5 and z == 0.0  # expf adds ~1e-7 per leaf on top of the reduction error
-    r, z = rel_err(hm.cpu().numpy(), o.weight_max(back))
-    assert r <= 1e-6 and z == 0.0
+    # expf results below the smallest normal fp32 are denormals with few mantissa bits: absolute bound there
+    np.testing.assert_allclose(hm.cpu().numpy(), o.weight_max(back), rtol=1e-6, atol=1e-37)
+    assert (hm.cpu().numpy()[o.weight_max(back) == 0] == 0).all()
 
 
 def test_reference_input_forms_and_errors():

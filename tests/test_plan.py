@@ -1,0 +1,76 @@
+"""Host-side tests of the tile planner (csrc/trie_plan.cpp): the kernels' data flow is emulated in numpy from the
+real plan arrays (tests/plan_emulator.py) and compared with the oracle.  No GPU needed."""
+import numpy as np
+import pytest
+
+import oracle
+from genlm_backend_b200 import TokenCharacterTrie, Token
+from genlm_backend_b200.synthetic import synth_vocab, dirichlet_rows
+from helpers import rel_err
+from plan_emulator import emulate
+
+
+def oracle_for(trie):
+    lay = trie._layout
+    return oracle.OracleLayout(trie.idx_to_leaf, lay["child_ptr"], lay["child_idx"])
+
+
+@pytest.mark.parametrize("V,T,Q", [(1, 1024, 4), (5, 1024, 4), (700, 1024, 128), (3000, 1024, 512), (3000, 2048, 8192),
+                                   (20011, 4096, 8192), (20011, 1024, 1000), (20011, 8192, 16384), (50257, 4096, 8192)])
+def test_emulated_kernels_match_oracle(V, T, Q):
+    trie = TokenCharacterTrie(synth_vocab(max(V, 256), seed=2)[-V:])
+    trie._engine.plan(T, Q)
+    ws = dirichlet_rows(3, V, alpha=0.1, seed=1)
+    o = oracle_for(trie)
+    have = emulate(trie._engine, ws, "sum")
+    assert not np.isnan(have).any()  # every node written exactly through one of the three phases
+    r, z = rel_err(have, o.weight_sum(ws))
+    assert r <= 2e-6 and z == 0.0
+    assert np.array_equal(emulate(trie._engine, ws, "max"), o.weight_max(ws).astype(np.float32))
+
+
+def test_plan_invariants():
+    V, T, Q = 20011, 1024, 1000
+    trie = TokenCharacterTrie(synth_vocab(V, seed=4))
+    eng = trie._engine
+    eng.plan(T, Q)
+    info = eng.plan_info()
+    lay = trie._layout
+    assert info["n_tiles"] == -(-V // T) and info["n_segs"] == -(-V // Q)
+    assert info["staged_row_elems"] % 4 == 0 and info["staged_row_elems"] >= V
+    # staging is a permutation of the row (plus padding)
+    src, zoff, cptr = eng.plan_array("p1_src"), eng.plan_array("p1_zoff"), eng.plan_array("p1_chunk_ptr")
+    seen = np.zeros(V, dtype=np.int64)
+    for s in range(info["n_segs"]):
+        e = src[4 * cptr[s]:4 * cptr[s + 1]]
+        e = e[e != 0xFFFF].astype(np.int64) + s * Q
+        np.add.at(seen, e, 1)
+    assert (seen == 1).all()
+    assert len(np.unique(zoff)) == len(zoff) and (zoff % 4 == 0).all()
+    # node intervals partition the id space; spanning nodes are exactly those without a slot
+    lo = eng.plan_array("tile_node_lo")
+    assert lo[0] == 0 and lo[-1] == len(trie) and (np.diff(lo) > 0).all()
+    slot = eng.plan_array("node_slot")
+    spanning = (lay["lo"] // T) != ((lay["hi"] - 1) // T)
+    assert np.array_equal(slot == 0xFFFF, spanning)
+    assert np.array_equal(np.sort(eng.plan_array("span_node")), np.flatnonzero(spanning))
+    # frontier terms are in-tile nodes covering the spanning node's range exactly once
+    sp, st, sn = eng.plan_array("span_ptr"), eng.plan_array("span_term"), eng.plan_array("span_node")
+    for i, n in enumerate(sn):
+        terms = st[sp[i]:sp[i + 1]]
+        assert not spanning[terms].any()
+        assert (lay["hi"][terms] - lay["lo"][terms]).sum() == lay["hi"][n] - lay["lo"][n]
+    assert info["n_span"] == int(spanning.sum())
+
+
+def test_plan_parameter_validation():
+    trie = TokenCharacterTrie([Token(0, b"a")])
+    from genlm_backend_b200._lib import GtError
+
+    for T, Q in [(1000, 8192), (512, 8192), (16384, 8192), (4096, 6), (4096, 32768)]:
+        with pytest.raises(GtError):
+            trie._engine.plan(T, Q)
+    trie._engine.plan(2048, 4096)
+    trie._engine.plan()  # defaults resolve to the existing plan
+    with pytest.raises(GtError):
+        trie._engine.plan(4096, 4096)
