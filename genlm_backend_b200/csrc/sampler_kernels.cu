@@ -164,12 +164,24 @@ __global__ void __launch_bounds__(kSThreads) lse_sample_kernel(SampleArgs A) {
 
         // ---- pass 1: online (max, sum exp) per thread ------------------------------------------------
         float m = -INFINITY, s = 0.f;
-        for (int g = tid; g < ng; g += kSThreads) {
-            float x[EPV];
-            rv.fetch(g, x);
-            float gm = x[0];
+        constexpr int U = EPV >= 8 ? 2 : 4;  // independent 16-byte groups in flight per thread
+        for (int gb = tid; gb < ng; gb += U * kSThreads) {
+            float x[U][EPV];
 #pragma unroll
-            for (int k = 1; k < EPV; ++k) gm = fmaxf(gm, x[k]);
+            for (int u = 0; u < U; ++u) {
+                const int g = gb + u * kSThreads;
+                if (g < ng) {
+                    rv.fetch(g, x[u]);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < EPV; ++k) x[u][k] = -INFINITY;
+                }
+            }
+            float gm = x[0][0];
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+#pragma unroll
+                for (int k = 0; k < EPV; ++k) gm = fmaxf(gm, x[u][k]);
             if (gm > m) {  // rare once the running max has settled
                 s *= exp2f((m - gm) * kLog2e);  // m = -inf: s is still 0
                 m = gm;
@@ -177,7 +189,9 @@ __global__ void __launch_bounds__(kSThreads) lse_sample_kernel(SampleArgs A) {
             if (m > -INFINITY) {
                 const float ml = m * kLog2e;
 #pragma unroll
-                for (int k = 0; k < EPV; ++k) s += exp2f(fmaf(x[k], kLog2e, -ml));
+                for (int u = 0; u < U; ++u)
+#pragma unroll
+                    for (int k = 0; k < EPV; ++k) s += exp2f(fmaf(x[u][k], kLog2e, -ml));
             }
         }
         // A NaN element poisons s (fmaxf ignores it, so m stays finite): logZ becomes NaN, tok = -1.

@@ -36,40 +36,44 @@ struct Plan {
     int32_t T = 0, Q = 0, NT = 0, NS = 0;
     int64_t Zrow = 0;  // floats per staged row (multiple of 4)
 
-    // phase 1 (permute): per segment s, chunks of 4 staged elements.
-    //   p1_chunk_ptr[s] .. p1_chunk_ptr[s+1]  : chunk index range of segment s
-    //   p1_zoff[c]     : offset (in floats, multiple of 4) of chunk c inside a staged row
-    //   p1_src[4*c+k]  : position inside the segment (uint16) feeding element k, 0xFFFF = padding
+    // phase 1 (permute): per segment s, records of 4 staged elements.
+    //   p1_chunk_ptr[s] .. p1_chunk_ptr[s+1] : record index range of segment s
+    //   p1_rec[c] = {zoff, src01, src23, 0}: zoff = offset (floats, multiple of 4) inside a staged row,
+    //   src* = two uint16 positions inside the segment each (0xFFFF = padding)
     std::vector<int32_t> p1_chunk_ptr;  // [NS+1]
-    std::vector<int32_t> p1_zoff;       // [n_chunks]
-    std::vector<uint16_t> p1_src;       // [4*n_chunks]
+    std::vector<int32_t> p1_rec;        // [4 * n_records]
 
     // phase 2 (tile): staged element i of tile t goes to value slot p2_slot[z_tile_off[t] + i]
     // (uint16; 0xFFFF = padding).
     std::vector<int32_t> z_tile_off;    // [NT+1]
     std::vector<uint16_t> p2_slot;      // [Zrow]
 
-    // per-tile value array: slots [0, tile_nleaf) are the tile's leaves in DFS order, then the
-    // tile's branching nodes ordered by dependency level.
-    std::vector<int32_t> tile_nleaf;    // [NT]
-    std::vector<int32_t> tile_nbranch;  // [NT]
-    // branching nodes, CSR over all tiles:
-    std::vector<int32_t> br_ptr;        // [NT+1]  branching-node index range per tile
-    std::vector<int32_t> br_child_ptr;  // [n_br+1] range into br_child (global offsets)
-    std::vector<uint16_t> br_child;     // child value slots (tile-local)
-    std::vector<int32_t> lvl_ptr;       // [NT+1]  range into lvl_end
-    std::vector<int32_t> lvl_end;       // per tile: cumulative end (tile-local branching index) of each level
+    // per-tile value array: slots [0,T) leaves in DFS order, [T,2T-1) pyramid of aligned blocks,
+    // 2T-1 the identity element, [2T, ..) multi-term ranges.
+    // Multi-term ranges in ELL form: per tile chunks of 32 ranges (sorted by descending term count);
+    // chunk c holds ell_k[c] rows of 32 uint16 slots starting at ell_terms[32 * ell_off[c]], padded with
+    // the identity slot.  Range j of the tile (j = 32*(c - ell_chunk_ptr[t]) + lane) lands in slot 2T + j.
+    std::vector<int32_t> ell_chunk_ptr;  // [NT+1]
+    std::vector<int32_t> ell_desc;       // [2 * n_chunks]  (off32, k)
+    std::vector<uint16_t> ell_terms;
     int32_t max_levels = 0, max_tile_values = 0;
+    int64_t n_multi = 0, n_terms = 0;
 
     // emit: node ids [tile_node_lo[t], tile_node_lo[t+1]) belong to tile t; node_slot[n] is the
-    // tile-local value slot, 0xFFFF for spanning nodes (written by the fix-up).
+    // tile-local value slot, 0xFFFF for spanning nodes.
     std::vector<int32_t> tile_node_lo;  // [NT+1]
     std::vector<uint16_t> node_slot;    // [N]
 
-    // spanning nodes (leaf range crosses a tile boundary): value = reduce over frontier node ids.
-    std::vector<int32_t> span_node;     // [n_span] node id
-    std::vector<int32_t> span_ptr;      // [n_span+1] into span_term
-    std::vector<int32_t> span_term;     // frontier node ids (in-tile nodes)
+    // spanning nodes (leaf range crosses a tile boundary, or is empty): one "piece" per overlapped tile
+    // (a leaf range inside that tile, resolved to a value slot like any node).  Tile t writes pieces
+    // piece_ptr[t]..piece_ptr[t+1] (slot piece_slot[i] -> part[piece_idx[i]]); node span_node[i] is the
+    // reduction of parts span_pp[i] .. span_pp[i+1].
+    std::vector<int32_t> piece_ptr;     // [NT+1]
+    std::vector<uint16_t> piece_slot;   // [n_piece_emits]
+    std::vector<int32_t> piece_idx;     // [n_piece_emits]
+    std::vector<int32_t> span_node;     // [n_span]
+    std::vector<int32_t> span_pp;       // [n_span+1]
+    int32_t n_pieces = 0;
 };
 
 struct DevicePlan;  // defined in the CUDA translation unit

@@ -9,10 +9,10 @@
 //                             -> shared memory -> tile-major staging rows z (coalesced 128-bit stores,
 //                             L2-resident scratch).  All scattered accesses hit shared memory only.
 //   phase 2  tile_kernel    : staged tile -> DFS-ordered leaf values in shared memory -> aligned-block
-//                             pyramid (warp shuffles) -> multi-term nodes -> coalesced emit of the
-//                             tile's node-id interval.
-//   phase 3  span_kernel    : the few nodes whose leaf range crosses a tile boundary, reduced from the
-//                             already written values of their maximal in-tile descendants (fp64 for sums).
+//                             pyramid (warp shuffles) -> multi-term ranges (ELL-packed term lists) ->
+//                             coalesced 128-bit emit of the tile's node-id interval.  Nodes whose leaf
+//                             range crosses tiles are written as per-tile pieces; the last CTA of a row
+//                             group to finish (atomic ticket) reduces them in fp64.
 #include <cuda_runtime.h>
 #include <cuda_fp16.h>
 #include <cuda_bf16.h>
@@ -34,11 +34,12 @@ namespace gt {
 struct PlanView {
     int32_t T, logT, Q, NT, NS, SV;  // SV = per-row value-array length in shared memory
     int64_t V, N, Zrow;
-    const int32_t* p1_chunk_ptr; const int32_t* p1_zoff; const uint16_t* p1_src;
+    const int32_t* p1_chunk_ptr; const int4* p1_rec;
     const int32_t* z_tile_off; const uint16_t* p2_slot;
-    const int32_t* br_ptr; const int32_t* br_child_ptr; const uint16_t* br_child;
+    const int32_t* ell_chunk_ptr; const int2* ell_desc; const uint16_t* ell_terms;
     const int32_t* tile_node_lo; const uint16_t* node_slot;
-    int32_t n_span; const int32_t* span_node; const int32_t* span_ptr; const int32_t* span_term;
+    const int32_t* piece_ptr; const uint16_t* piece_slot; const int32_t* piece_idx;
+    int32_t n_span, n_pieces; const int32_t* span_node; const int32_t* span_pp;
 };
 
 struct DevicePlan {
@@ -106,6 +107,14 @@ template <> __device__ __forceinline__ void store4<double>(double* p, double a, 
     reinterpret_cast<double2*>(p)[0] = make_double2(a, b);
     reinterpret_cast<double2*>(p)[1] = make_double2(c, d);
 }
+template <typename VT> __device__ __forceinline__ void store4_stream(VT* p, VT a, VT b, VT c, VT d);
+template <> __device__ __forceinline__ void store4_stream<float>(float* p, float a, float b, float c, float d) {
+    __stcs(reinterpret_cast<float4*>(p), make_float4(a, b, c, d));
+}
+template <> __device__ __forceinline__ void store4_stream<double>(double* p, double a, double b, double c, double d) {
+    __stcs(reinterpret_cast<double2*>(p), make_double2(a, b));
+    __stcs(reinterpret_cast<double2*>(p) + 1, make_double2(c, d));
+}
 template <typename VT> __device__ __forceinline__ void load4(const VT* p, VT& a, VT& b, VT& c, VT& d);
 template <> __device__ __forceinline__ void load4<float>(const float* p, float& a, float& b, float& c, float& d) {
     const float4 v = *reinterpret_cast<const float4*>(p);
@@ -168,7 +177,8 @@ __device__ __forceinline__ void load_segment_f64(const double* __restrict__ row,
 
 template <typename VT, typename IN_T, int R>
 __global__ void __launch_bounds__(kThreads) permute_kernel(PlanView P, const IN_T* __restrict__ ws, int64_t ld_ws,
-                                                           VT* __restrict__ z, int n_rows, int log_input) {
+                                                           VT* __restrict__ z, int* __restrict__ counters, int n_rows,
+                                                           int log_input) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     VT* seg = reinterpret_cast<VT*>(smem_raw);  // [R][Q + kSegPad]
     const int pitch = P.Q + kSegPad;
@@ -177,6 +187,8 @@ __global__ void __launch_bounds__(kThreads) permute_kernel(PlanView P, const IN_
     const int nrows = min(R, n_rows - b0);
     const int seg_lo = s * P.Q;
     const int seg_n = (int)min((int64_t)P.Q, P.V - seg_lo);
+    // tickets of the tile kernels' row groups (indexed by row group of any size <= rows): zero one per row
+    if (s == 0 && threadIdx.x < R && b0 + (int)threadIdx.x < n_rows) counters[b0 + threadIdx.x] = 0;
 
     int phase[R];
 #pragma unroll
@@ -192,31 +204,43 @@ __global__ void __launch_bounds__(kThreads) permute_kernel(PlanView P, const IN_
     __syncthreads();
 
     const int c0 = P.p1_chunk_ptr[s], c1 = P.p1_chunk_ptr[s + 1];
-    const ushort4* src4 = reinterpret_cast<const ushort4*>(P.p1_src);
-    for (int c = c0 + threadIdx.x; c < c1; c += kThreads) {
-        const int zo = P.p1_zoff[c];
-        const ushort4 src = src4[c];
+    constexpr int U = 4;  // records in flight per thread
+    for (int cb = c0 + threadIdx.x; cb < c1; cb += U * kThreads) {
+        int4 rec[U];
 #pragma unroll
-        for (int r = 0; r < R; ++r) {
-            if (r < nrows) {
-                const VT* sr = seg + r * pitch + phase[r];
-                const VT a = src.x != 0xFFFF ? sr[src.x] : VT(0);
-                const VT b = src.y != 0xFFFF ? sr[src.y] : VT(0);
-                const VT cc = src.z != 0xFFFF ? sr[src.z] : VT(0);
-                const VT d = src.w != 0xFFFF ? sr[src.w] : VT(0);
-                store4<VT>(z + (size_t)(b0 + r) * P.Zrow + zo, a, b, cc, d);
+        for (int u = 0; u < U; ++u) {
+            const int c = cb + u * kThreads;
+            rec[u] = c < c1 ? __ldg(P.p1_rec + c) : make_int4(-1, -1, -1, 0);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (rec[u].x < 0) continue;
+            const unsigned s0 = (unsigned)rec[u].y & 0xFFFFu, s1 = (unsigned)rec[u].y >> 16;
+            const unsigned s2 = (unsigned)rec[u].z & 0xFFFFu, s3 = (unsigned)rec[u].z >> 16;
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                if (r < nrows) {
+                    const VT* sr = seg + r * pitch + phase[r];
+                    const VT a = s0 != 0xFFFFu ? sr[s0] : VT(0);
+                    const VT b = s1 != 0xFFFFu ? sr[s1] : VT(0);
+                    const VT c = s2 != 0xFFFFu ? sr[s2] : VT(0);
+                    const VT d = s3 != 0xFFFFu ? sr[s3] : VT(0);
+                    store4<VT>(z + (size_t)(b0 + r) * P.Zrow + rec[u].x, a, b, c, d);
+                }
             }
         }
     }
 }
 
-// ---- phase 2: per-tile pyramid, multi-term nodes, emit -----------------------------------------------
+// ---- phase 2: per-tile pyramid, multi-term ranges, emit, spanning pieces -------------------------------------
 
-template <typename VT, int R, int OP>
-__global__ void __launch_bounds__(kThreads) tile_kernel(PlanView P, const VT* __restrict__ z, VT* __restrict__ out,
-                                                        int64_t ld_out, int n_rows) {
+template <typename VT, int R, int OP, bool VEC>
+__global__ void __launch_bounds__(kThreads, 2) tile_kernel(PlanView P, const VT* __restrict__ z, VT* __restrict__ out,
+                                                           int64_t ld_out, VT* __restrict__ part,
+                                                           int* __restrict__ counters, int n_rows) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     VT* vals = reinterpret_cast<VT*>(smem_raw);  // [R][SV]
+    __shared__ int s_last;
     const int T = P.T, SV = P.SV;
     const int t = blockIdx.x;
     const int b0 = blockIdx.y * R;
@@ -224,23 +248,36 @@ __global__ void __launch_bounds__(kThreads) tile_kernel(PlanView P, const VT* __
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int kWarps = kThreads / 32;
 
-    // 1. staged tile -> DFS-ordered leaf slots
+    // 1. staged tile -> DFS-ordered leaf slots (two groups of 4 in flight per thread and row)
     {
         const int zlo = P.z_tile_off[t];
         const int zn4 = (P.z_tile_off[t + 1] - zlo) >> 2;
-        const ushort4* slot4 = reinterpret_cast<const ushort4*>(P.p2_slot + zlo);
-        for (int i = tid; i < zn4; i += kThreads) {
-            const ushort4 sl = slot4[i];
+        const uint2* slot4 = reinterpret_cast<const uint2*>(P.p2_slot + zlo);
+        constexpr int U = 2;
+        for (int ib = tid; ib < zn4; ib += U * kThreads) {
+            uint2 sl[U];
+            VT v[U][R][4];
 #pragma unroll
-            for (int r = 0; r < R; ++r) {
-                if (r < nrows) {
-                    VT a, b, c, d;
-                    load4<VT>(z + (size_t)(b0 + r) * P.Zrow + zlo + 4 * i, a, b, c, d);
-                    VT* lv = vals + r * SV;
-                    if (sl.x != 0xFFFF) lv[sl.x] = a;
-                    if (sl.y != 0xFFFF) lv[sl.y] = b;
-                    if (sl.z != 0xFFFF) lv[sl.z] = c;
-                    if (sl.w != 0xFFFF) lv[sl.w] = d;
+            for (int u = 0; u < U; ++u) {
+                const int i = ib + u * kThreads;
+                sl[u] = i < zn4 ? __ldg(slot4 + i) : make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu);
+#pragma unroll
+                for (int r = 0; r < R; ++r)
+                    if (r < nrows && i < zn4)
+                        load4<VT>(z + (size_t)(b0 + r) * P.Zrow + zlo + 4 * i, v[u][r][0], v[u][r][1], v[u][r][2], v[u][r][3]);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const unsigned s0 = sl[u].x & 0xFFFFu, s1 = sl[u].x >> 16, s2 = sl[u].y & 0xFFFFu, s3 = sl[u].y >> 16;
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    if (r < nrows) {
+                        VT* lv = vals + r * SV;
+                        if (s0 != 0xFFFFu) lv[s0] = v[u][r][0];
+                        if (s1 != 0xFFFFu) lv[s1] = v[u][r][1];
+                        if (s2 != 0xFFFFu) lv[s2] = v[u][r][2];
+                        if (s3 != 0xFFFFu) lv[s3] = v[u][r][3];
+                    }
                 }
             }
         }
@@ -248,6 +285,7 @@ __global__ void __launch_bounds__(kThreads) tile_kernel(PlanView P, const VT* __
         for (int i = nleaf + tid; i < T; i += kThreads)
 #pragma unroll
             for (int r = 0; r < R; ++r) vals[r * SV + i] = op_ident<OP, VT>();
+        if (tid < R) vals[tid * SV + 2 * T - 1] = op_ident<OP, VT>();  // identity slot used as ELL padding
     }
     __syncthreads();
 
@@ -293,20 +331,22 @@ __global__ void __launch_bounds__(kThreads) tile_kernel(PlanView P, const VT* __
     }
     __syncthreads();
 
-    // 3. nodes that need more than one block: short reductions over leaf / pyramid slots
+    // 3. ranges that need more than one block: ELL chunks of 32 ranges, one warp per chunk, terms coalesced
     {
-        const int j0 = P.br_ptr[t];
-        const int nb = P.br_ptr[t + 1] - j0;
-        for (int j = tid; j < nb; j += kThreads) {
-            const int p0 = P.br_child_ptr[j0 + j], p1 = P.br_child_ptr[j0 + j + 1];
+        const int c0 = P.ell_chunk_ptr[t], c1 = P.ell_chunk_ptr[t + 1];
+        for (int c = c0 + warp; c < c1; c += kWarps) {
+            const int2 d = __ldg(P.ell_desc + c);
+            const uint16_t* tp = P.ell_terms + (size_t)d.x * 32 + lane;
             VT acc[R];
 #pragma unroll
             for (int r = 0; r < R; ++r) acc[r] = op_ident<OP, VT>();
-            for (int p = p0; p < p1; ++p) {
-                const int sl = P.br_child[p];
+#pragma unroll 4
+            for (int kk = 0; kk < d.y; ++kk) {
+                const int sl = __ldg(tp + kk * 32);
 #pragma unroll
                 for (int r = 0; r < R; ++r) acc[r] = op_apply<OP>(acc[r], vals[r * SV + sl]);
             }
+            const int j = (c - c0) * 32 + lane;
 #pragma unroll
             for (int r = 0; r < R; ++r) vals[r * SV + 2 * T + j] = acc[r];
         }
@@ -316,34 +356,97 @@ __global__ void __launch_bounds__(kThreads) tile_kernel(PlanView P, const VT* __
     // 4. emit the tile's node-id interval, coalesced
     {
         const int n0 = P.tile_node_lo[t], n1 = P.tile_node_lo[t + 1];
-        for (int n = n0 + tid; n < n1; n += kThreads) {
-            const int sl = P.node_slot[n];
-            if (sl != 0xFFFF) {
+        if constexpr (VEC) {
+            // rows are 16-byte aligned and ld_out % 4 == 0: one 128-bit store per 4 consecutive node ids
+            const int q0 = n0 >> 2, q1 = (n1 + 3) >> 2;
+            const uint2* slot4 = reinterpret_cast<const uint2*>(P.node_slot);
+            constexpr int U = 4;
+            for (int qb = q0 + tid; qb < q1; qb += U * kThreads) {
+                uint2 sl[U];
 #pragma unroll
-                for (int r = 0; r < R; ++r)
-                    if (r < nrows) __stcs(out + (size_t)(b0 + r) * ld_out + n, vals[r * SV + sl]);
+                for (int u = 0; u < U; ++u) {
+                    const int q = qb + u * kThreads;
+                    sl[u] = q < q1 ? __ldg(slot4 + q) : make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu);
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int q = qb + u * kThreads;
+                    const unsigned s0 = sl[u].x & 0xFFFFu, s1 = sl[u].x >> 16, s2 = sl[u].y & 0xFFFFu, s3 = sl[u].y >> 16;
+                    const int n = 4 * q;
+                    const bool in0 = n >= n0 && n < n1 && s0 != 0xFFFFu, in1 = n + 1 >= n0 && n + 1 < n1 && s1 != 0xFFFFu;
+                    const bool in2 = n + 2 >= n0 && n + 2 < n1 && s2 != 0xFFFFu, in3 = n + 3 >= n0 && n + 3 < n1 && s3 != 0xFFFFu;
+                    if (in0 && in1 && in2 && in3) {
+#pragma unroll
+                        for (int r = 0; r < R; ++r) {
+                            if (r < nrows) {
+                                const VT* lv = vals + r * SV;
+                                store4_stream<VT>(out + (size_t)(b0 + r) * ld_out + n, lv[s0], lv[s1], lv[s2], lv[s3]);
+                            }
+                        }
+                    } else if (in0 || in1 || in2 || in3) {
+#pragma unroll
+                        for (int r = 0; r < R; ++r) {
+                            if (r < nrows) {
+                                const VT* lv = vals + r * SV;
+                                VT* o = out + (size_t)(b0 + r) * ld_out + n;
+                                if (in0) __stcs(o, lv[s0]);
+                                if (in1) __stcs(o + 1, lv[s1]);
+                                if (in2) __stcs(o + 2, lv[s2]);
+                                if (in3) __stcs(o + 3, lv[s3]);
+                            }
+                        }
+                    }
+                }
+            }
+        } else {
+            constexpr int U = 4;
+            for (int nb = n0 + tid; nb < n1; nb += U * kThreads) {
+                unsigned sl[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int n = nb + u * kThreads;
+                    sl[u] = n < n1 ? (unsigned)__ldg(P.node_slot + n) : 0xFFFFu;
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    if (sl[u] == 0xFFFFu) continue;
+                    const int n = nb + u * kThreads;
+#pragma unroll
+                    for (int r = 0; r < R; ++r)
+                        if (r < nrows) __stcs(out + (size_t)(b0 + r) * ld_out + n, vals[r * SV + sl[u]]);
+                }
             }
         }
     }
-}
 
-// ---- phase 3: nodes spanning tiles -------------------------------------------------------------------
-
-template <typename VT, int OP>
-__global__ void __launch_bounds__(256) span_kernel(PlanView P, VT* __restrict__ out, int64_t ld_out, int n_rows) {
-    const int lane = threadIdx.x & 31;
-    const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (i >= P.n_span) return;
-    const int node = P.span_node[i];
-    const int p0 = P.span_ptr[i], p1 = P.span_ptr[i + 1];
-    using AT = typename std::conditional<OP == OP_SUM, double, VT>::type;
-    for (int b = blockIdx.y; b < n_rows; b += gridDim.y) {
-        const VT* row = out + (size_t)b * ld_out;
-        AT acc = op_ident<OP, AT>();
-        for (int p = p0 + lane; p < p1; p += 32) acc = op_apply<OP, AT>(acc, (AT)row[P.span_term[p]]);
+    // 5. pieces of spanning nodes that overlap this tile; the last tile of the row group reduces them
+    if (P.n_span > 0) {
+        const int p0 = P.piece_ptr[t], p1 = P.piece_ptr[t + 1];
+        for (int i = p0 + tid; i < p1; i += kThreads) {
+            const int sl = P.piece_slot[i], idx = P.piece_idx[i];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) acc = op_apply<OP, AT>(acc, __shfl_xor_sync(0xffffffffu, acc, o));
-        if (lane == 0) out[(size_t)b * ld_out + node] = p1 > p0 ? (VT)acc : VT(0);
+            for (int r = 0; r < R; ++r)
+                if (r < nrows) part[(size_t)(b0 + r) * P.n_pieces + idx] = vals[r * SV + sl];
+        }
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) s_last = atomicAdd(counters + blockIdx.y, 1) == P.NT - 1;
+        __syncthreads();
+        if (s_last) {
+            __threadfence();
+            using AT = typename std::conditional<OP == OP_SUM, double, VT>::type;
+            for (int i = tid; i < P.n_span * R; i += kThreads) {
+                const int r = i / P.n_span, k = i - r * P.n_span;
+                if (r >= nrows) break;
+                const int q0 = P.span_pp[k], q1 = P.span_pp[k + 1];
+                const VT* pr = part + (size_t)(b0 + r) * P.n_pieces;
+                AT acc = op_ident<OP, AT>();
+#pragma unroll 4
+                for (int q = q0; q < q1; ++q) acc = op_apply<OP, AT>(acc, (AT)__ldcg(pr + q));
+                out[(size_t)(b0 + r) * ld_out + P.span_node[k]] = q1 > q0 ? (VT)acc : VT(0);
+            }
+            if (tid == 0) counters[blockIdx.y] = 0;  // ready for the next tile launch over the same row groups
+        }
     }
 }
 
@@ -360,11 +463,12 @@ static DevicePlan* upload_plan(const Layout& L, const Plan& P, int device) {
         return off;
     };
 #define ADDV(v) add((v).data(), (v).size() * sizeof((v)[0]))
-    const size_t o_p1_chunk_ptr = ADDV(P.p1_chunk_ptr), o_p1_zoff = ADDV(P.p1_zoff), o_p1_src = ADDV(P.p1_src);
+    const size_t o_p1_chunk_ptr = ADDV(P.p1_chunk_ptr), o_p1_rec = ADDV(P.p1_rec);
     const size_t o_z_tile_off = ADDV(P.z_tile_off), o_p2_slot = ADDV(P.p2_slot);
-    const size_t o_br_ptr = ADDV(P.br_ptr), o_br_child_ptr = ADDV(P.br_child_ptr), o_br_child = ADDV(P.br_child);
+    const size_t o_ell_chunk_ptr = ADDV(P.ell_chunk_ptr), o_ell_desc = ADDV(P.ell_desc), o_ell_terms = ADDV(P.ell_terms);
     const size_t o_tile_node_lo = ADDV(P.tile_node_lo), o_node_slot = ADDV(P.node_slot);
-    const size_t o_span_node = ADDV(P.span_node), o_span_ptr = ADDV(P.span_ptr), o_span_term = ADDV(P.span_term);
+    const size_t o_piece_ptr = ADDV(P.piece_ptr), o_piece_slot = ADDV(P.piece_slot), o_piece_idx = ADDV(P.piece_idx);
+    const size_t o_span_node = ADDV(P.span_node), o_span_pp = ADDV(P.span_pp);
 #undef ADDV
     total += 256;
 
@@ -400,15 +504,15 @@ static DevicePlan* upload_plan(const Layout& L, const Plan& P, int device) {
     v.Q = P.Q; v.NT = P.NT; v.NS = P.NS;
     v.SV = (P.max_tile_values + 3) & ~3;
     v.V = L.V; v.N = L.N; v.Zrow = P.Zrow;
-    v.p1_chunk_ptr = (const int32_t*)(base + o_p1_chunk_ptr); v.p1_zoff = (const int32_t*)(base + o_p1_zoff);
-    v.p1_src = (const uint16_t*)(base + o_p1_src);
+    v.p1_chunk_ptr = (const int32_t*)(base + o_p1_chunk_ptr); v.p1_rec = (const int4*)(base + o_p1_rec);
     v.z_tile_off = (const int32_t*)(base + o_z_tile_off); v.p2_slot = (const uint16_t*)(base + o_p2_slot);
-    v.br_ptr = (const int32_t*)(base + o_br_ptr); v.br_child_ptr = (const int32_t*)(base + o_br_child_ptr);
-    v.br_child = (const uint16_t*)(base + o_br_child);
+    v.ell_chunk_ptr = (const int32_t*)(base + o_ell_chunk_ptr); v.ell_desc = (const int2*)(base + o_ell_desc);
+    v.ell_terms = (const uint16_t*)(base + o_ell_terms);
     v.tile_node_lo = (const int32_t*)(base + o_tile_node_lo); v.node_slot = (const uint16_t*)(base + o_node_slot);
-    v.n_span = (int32_t)P.span_node.size();
-    v.span_node = (const int32_t*)(base + o_span_node); v.span_ptr = (const int32_t*)(base + o_span_ptr);
-    v.span_term = (const int32_t*)(base + o_span_term);
+    v.piece_ptr = (const int32_t*)(base + o_piece_ptr); v.piece_slot = (const uint16_t*)(base + o_piece_slot);
+    v.piece_idx = (const int32_t*)(base + o_piece_idx);
+    v.n_span = (int32_t)P.span_node.size(); v.n_pieces = P.n_pieces;
+    v.span_node = (const int32_t*)(base + o_span_node); v.span_pp = (const int32_t*)(base + o_span_pp);
     return d;
 }
 
@@ -439,31 +543,55 @@ template <typename K> static cudaError_t allow_smem(K kernel, size_t bytes) {
     return allow_smem_impl(reinterpret_cast<const void*>(kernel), bytes);
 }
 
+// Scratch layout for one chunk of `rows` rows: z [rows][Zrow] VT | part [rows][n_pieces] VT | counters [rows] int
+template <typename VT> struct Scratch {
+    VT* z; VT* part; int* counters;
+    static size_t bytes_per_row(const PlanView& v) {
+        return (size_t)v.Zrow * sizeof(VT) + (size_t)((v.n_pieces + 3) & ~3) * sizeof(VT) + 16;
+    }
+    Scratch(const PlanView& v, void* base, int64_t rows) {
+        char* p = static_cast<char*>(base);
+        z = reinterpret_cast<VT*>(p);
+        p += (((size_t)rows * v.Zrow * sizeof(VT)) + 255) & ~size_t(255);
+        part = reinterpret_cast<VT*>(p);
+        p += (((size_t)rows * v.n_pieces * sizeof(VT)) + 255) & ~size_t(255);
+        counters = reinterpret_cast<int*>(p);
+    }
+    static size_t total(const PlanView& v, int64_t rows) {
+        return ((((size_t)rows * v.Zrow * sizeof(VT)) + 255) & ~size_t(255)) +
+               ((((size_t)rows * v.n_pieces * sizeof(VT)) + 255) & ~size_t(255)) + (((size_t)rows * sizeof(int)) + 255 & ~size_t(255));
+    }
+};
+
 template <typename VT, typename IN_T, int R>
-static int launch_permute(const PlanView& v, const void* ws, int64_t ld_ws, VT* z, int rows, bool log_input, cudaStream_t st) {
+static int launch_permute(const PlanView& v, const void* ws, int64_t ld_ws, const Scratch<VT>& sc, int rows,
+                          bool log_input, cudaStream_t st) {
     const size_t smem = permute_smem<VT, R>(v);
     GT_CUDA(allow_smem(permute_kernel<VT, IN_T, R>, smem));
     dim3 grid((unsigned)v.NS, (unsigned)((rows + R - 1) / R));
-    permute_kernel<VT, IN_T, R><<<grid, kThreads, smem, st>>>(v, static_cast<const IN_T*>(ws), ld_ws, z, rows, log_input ? 1 : 0);
+    permute_kernel<VT, IN_T, R><<<grid, kThreads, smem, st>>>(v, static_cast<const IN_T*>(ws), ld_ws, sc.z, sc.counters, rows,
+                                                             log_input ? 1 : 0);
     GT_CUDA(cudaGetLastError());
     return GT_OK;
 }
 
 template <typename VT, int R, int OP>
-static int launch_tile_and_span(const PlanView& v, const VT* z, VT* out, int64_t ld_out, int rows, unsigned phases,
-                                cudaStream_t st) {
-    if (v.NT > 0 && (phases & GT_FLAG_PHASE_TILE)) {
-        const size_t smem = tile_smem<VT, R>(v);
-        GT_CUDA(allow_smem(tile_kernel<VT, R, OP>, smem));
-        dim3 grid((unsigned)v.NT, (unsigned)((rows + R - 1) / R));
-        tile_kernel<VT, R, OP><<<grid, kThreads, smem, st>>>(v, z, out, ld_out, rows);
-        GT_CUDA(cudaGetLastError());
+static int launch_tile(const PlanView& v, const Scratch<VT>& sc, VT* out, int64_t ld_out, int rows, cudaStream_t st) {
+    if (v.NT == 0) {  // empty vocabulary: the root is the only node and has no mass
+        GT_CUDA(cudaMemset2DAsync(out, (size_t)ld_out * sizeof(VT), 0, (size_t)v.N * sizeof(VT), (size_t)rows, st));
+        return GT_OK;
     }
-    if (v.n_span > 0 && (phases & GT_FLAG_PHASE_SPAN)) {
-        dim3 grid((unsigned)((v.n_span + 7) / 8), (unsigned)std::min(rows, 1024));
-        span_kernel<VT, OP><<<grid, 256, 0, st>>>(v, out, ld_out, rows);
-        GT_CUDA(cudaGetLastError());
+    const size_t smem = tile_smem<VT, R>(v);
+    dim3 grid((unsigned)v.NT, (unsigned)((rows + R - 1) / R));
+    const bool vec = (ld_out % 4 == 0) && (reinterpret_cast<uintptr_t>(out) % (4 * sizeof(VT)) == 0);
+    if (vec) {
+        GT_CUDA(allow_smem(tile_kernel<VT, R, OP, true>, smem));
+        tile_kernel<VT, R, OP, true><<<grid, kThreads, smem, st>>>(v, sc.z, out, ld_out, sc.part, sc.counters, rows);
+    } else {
+        GT_CUDA(allow_smem(tile_kernel<VT, R, OP, false>, smem));
+        tile_kernel<VT, R, OP, false><<<grid, kThreads, smem, st>>>(v, sc.z, out, ld_out, sc.part, sc.counters, rows);
     }
+    GT_CUDA(cudaGetLastError());
     return GT_OK;
 }
 
@@ -471,24 +599,31 @@ template <typename VT, int R>
 static int reduce_typed(const PlanView& v, const void* ws, int in_type, int64_t n_rows, int64_t ld_ws, void* out_sum,
                         void* out_max, int64_t ld_out, unsigned ops, unsigned flags, void* workspace,
                         size_t workspace_bytes, cudaStream_t st) {
-    const size_t row_bytes = (size_t)v.Zrow * sizeof(VT);
-    int64_t chunk = row_bytes ? (int64_t)(workspace_bytes / row_bytes) : n_rows;
-    if (v.Zrow > 0 && chunk < 1) { set_error("workspace too small: need at least %zu bytes", row_bytes); return GT_ERR_STATE; }
-    chunk = std::min<int64_t>(chunk, 32768);
-    if (v.Zrow == 0) chunk = 32768;
+    // rows per chunk: what the caller's scratch can stage (multiple of R so row groups never straddle chunks)
+    int64_t chunk = std::min<int64_t>(n_rows, 32768);
+    while (chunk > 0 && Scratch<VT>::total(v, chunk) > workspace_bytes) chunk = chunk > 2 * R ? (chunk / 2 / R) * R : chunk - 1;
+    if (chunk < 1) {
+        set_error("workspace too small: %zu bytes given, one row needs %zu", workspace_bytes, Scratch<VT>::total(v, 1));
+        return GT_ERR_STATE;
+    }
+    if (chunk < n_rows) chunk = std::max<int64_t>(R, (chunk / R) * R);
+    if (Scratch<VT>::total(v, std::min(chunk, n_rows)) > workspace_bytes) {
+        set_error("workspace too small: %zu bytes given, %d rows need %zu", workspace_bytes, R, Scratch<VT>::total(v, R));
+        return GT_ERR_STATE;
+    }
     const bool log_input = (flags & GT_FLAG_LOG_INPUT) != 0;
     const unsigned phases = (flags & GT_FLAG_PHASE_MASK) ? (flags & GT_FLAG_PHASE_MASK) : GT_FLAG_PHASE_MASK;
-    VT* z = static_cast<VT*>(workspace);
     const size_t in_size = in_type == GT_F64 ? 8 : in_type == GT_F32 ? 4 : 2;
     for (int64_t r0 = 0; r0 < n_rows; r0 += chunk) {
         const int rows = (int)std::min<int64_t>(chunk, n_rows - r0);
+        const Scratch<VT> sc(v, workspace, rows);
         const void* wsr = static_cast<const char*>(ws) + (size_t)r0 * ld_ws * in_size;
         int rc = GT_OK;
         if (v.NT > 0 && (phases & GT_FLAG_PHASE_PERMUTE)) {
             // rows per CTA in the permute phase: R unless the segment buffer would not fit in shared memory
             const bool wide = permute_smem<VT, R>(v) <= kMaxSmem;
-#define GT_PERMUTE(IN_T) (wide ? launch_permute<VT, IN_T, R>(v, wsr, ld_ws, z, rows, log_input, st) \
-                               : launch_permute<VT, IN_T, 1>(v, wsr, ld_ws, z, rows, log_input, st))
+#define GT_PERMUTE(IN_T) (wide ? launch_permute<VT, IN_T, R>(v, wsr, ld_ws, sc, rows, log_input, st) \
+                               : launch_permute<VT, IN_T, 1>(v, wsr, ld_ws, sc, rows, log_input, st))
             switch (in_type) {
                 case GT_F32: rc = GT_PERMUTE(float); break;
                 case GT_F64: rc = GT_PERMUTE(double); break;
@@ -499,12 +634,12 @@ static int reduce_typed(const PlanView& v, const void* ws, int in_type, int64_t 
 #undef GT_PERMUTE
             if (rc != GT_OK) return rc;
         }
-        if (ops & GT_OP_SUM) {
-            rc = launch_tile_and_span<VT, R, OP_SUM>(v, z, static_cast<VT*>(out_sum) + (size_t)r0 * ld_out, ld_out, rows, phases, st);
+        if ((ops & GT_OP_SUM) && (phases & GT_FLAG_PHASE_TILE)) {
+            rc = launch_tile<VT, R, OP_SUM>(v, sc, static_cast<VT*>(out_sum) + (size_t)r0 * ld_out, ld_out, rows, st);
             if (rc != GT_OK) return rc;
         }
-        if (ops & GT_OP_MAX) {
-            rc = launch_tile_and_span<VT, R, OP_MAX>(v, z, static_cast<VT*>(out_max) + (size_t)r0 * ld_out, ld_out, rows, phases, st);
+        if ((ops & GT_OP_MAX) && (phases & GT_FLAG_PHASE_TILE)) {
+            rc = launch_tile<VT, R, OP_MAX>(v, sc, static_cast<VT*>(out_max) + (size_t)r0 * ld_out, ld_out, rows, st);
             if (rc != GT_OK) return rc;
         }
     }
@@ -536,7 +671,7 @@ int gt_get_plan_info(const gt_trie* t, gt_plan_info* info) {
     info->n_tokens = t->layout.V; info->n_nodes = t->layout.N;
     info->tile_leaves = P.T; info->seg_positions = P.Q; info->n_tiles = P.NT; info->n_segs = P.NS;
     info->rows_per_item = gt::R_F32;
-    info->n_span = (int32_t)P.span_node.size(); info->span_terms = (int64_t)P.span_term.size();
+    info->n_span = (int32_t)P.span_node.size(); info->span_terms = (int64_t)P.n_pieces;
     info->max_levels = P.max_levels; info->max_tile_values = P.max_tile_values;
     info->staged_row_elems = P.Zrow;
     size_t meta = 0;
@@ -547,7 +682,9 @@ int gt_get_plan_info(const gt_trie* t, gt_plan_info* info) {
 
 size_t gt_workspace_bytes(const gt_trie* t, int64_t max_rows) {
     if (!t || !t->plan || max_rows <= 0) return 0;
-    return (size_t)max_rows * (size_t)t->plan->Zrow * sizeof(double) + 256;
+    gt::PlanView v{};
+    v.Zrow = t->plan->Zrow; v.n_pieces = t->plan->n_pieces;
+    return gt::Scratch<double>::total(v, max_rows) + 256;
 }
 
 int gt_weight_reduce(const gt_trie* t, const void* ws, int in_type, int64_t n_rows, int64_t ld_ws, void* out_sum,
@@ -571,7 +708,7 @@ int gt_weight_reduce(const gt_trie* t, const void* ws, int in_type, int64_t n_ro
     auto it = t->dev.find(device);
     if (it == t->dev.end()) { gt::set_error("trie metadata is not resident on device %d (call gt_upload)", device); return GT_ERR_STATE; }
     const gt::PlanView& v = it->second->view;
-    if (v.Zrow > 0 && !workspace) { gt::set_error("gt_weight_reduce: null workspace"); return GT_ERR_ARG; }
+    if (!workspace) { gt::set_error("gt_weight_reduce: null workspace"); return GT_ERR_ARG; }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (out_type == GT_F32)
         return gt::reduce_typed<float, gt::R_F32>(v, ws, in_type, n_rows, ld_ws, out_sum, out_max, ld_out, ops, flags,

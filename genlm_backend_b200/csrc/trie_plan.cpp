@@ -15,7 +15,7 @@
 
 #include <algorithm>
 #include <numeric>
-#include <unordered_map>
+#include <map>
 #include <cstring>
 #include <cstdlib>
 
@@ -63,22 +63,26 @@ int build_plan(const Layout& L, int32_t T, int32_t Q, Plan& P) {
             z_src[(size_t)at] = (uint16_t)(pos - s * Q);
         }
     }
-    // phase-1 chunk lists: segment-major
+    // phase-1 records: segment-major
     P.p1_chunk_ptr.assign((size_t)NS + 1, 0);
-    P.p1_zoff.clear(); P.p1_src.clear();
-    P.p1_zoff.reserve((size_t)z / 4); P.p1_src.reserve((size_t)z);
+    P.p1_rec.clear();
+    P.p1_rec.reserve((size_t)z);
     for (int32_t s = 0; s < NS; ++s) {
-        P.p1_chunk_ptr[s] = (int32_t)P.p1_zoff.size();
+        P.p1_chunk_ptr[s] = (int32_t)(P.p1_rec.size() / 4);
         for (int32_t t = 0; t < NT; ++t) {
             const int64_t a = run_off[(size_t)t * NS + s];
             const int64_t n = (cnt[(size_t)t * NS + s] + 3) & ~3;
             for (int64_t k = 0; k < n; k += 4) {
-                P.p1_zoff.push_back((int32_t)(a + k));
-                for (int e = 0; e < 4; ++e) P.p1_src.push_back(z_src[(size_t)(a + k + e)]);
+                const uint32_t s0 = z_src[(size_t)(a + k)], s1 = z_src[(size_t)(a + k + 1)];
+                const uint32_t s2 = z_src[(size_t)(a + k + 2)], s3 = z_src[(size_t)(a + k + 3)];
+                P.p1_rec.push_back((int32_t)(a + k));
+                P.p1_rec.push_back((int32_t)(s0 | (s1 << 16)));
+                P.p1_rec.push_back((int32_t)(s2 | (s3 << 16)));
+                P.p1_rec.push_back(0);
             }
         }
     }
-    P.p1_chunk_ptr[NS] = (int32_t)P.p1_zoff.size();
+    P.p1_chunk_ptr[NS] = (int32_t)(P.p1_rec.size() / 4);
 
     // ---- node intervals per tile -------------------------------------------------------------------
     P.tile_node_lo.assign((size_t)NT + 1, (int32_t)N);
@@ -86,50 +90,70 @@ int build_plan(const Layout& L, int32_t T, int32_t Q, Plan& P) {
     if (NT > 0 && P.tile_node_lo[0] != 0) { set_error("internal: first DFS leaf is not node 0"); return GT_ERR_STATE; }
 
     // ---- value slots ------------------------------------------------------------------------------
-    // tile-local slots: [0,T) leaves, [T,2T) pyramid (level k>=1 block i at 2T-(T>>(k-1))+i), [2T,..) multi-term nodes
-    P.node_slot.assign((size_t)N, 0xFFFF);
-    P.tile_nleaf.assign((size_t)NT, 0); P.tile_nbranch.assign((size_t)NT, 0);
-    for (int32_t t = 0; t < NT; ++t) P.tile_nleaf[t] = (int32_t)std::min<int64_t>(T, V - (int64_t)t * T);
-
-    struct Multi { int32_t node; std::vector<uint16_t> terms; };
-    std::vector<std::vector<Multi>> multi((size_t)NT);
-    std::vector<uint8_t> spanning((size_t)N, 0);
+    // A leaf range [a,b) inside tile t resolves to a slot: a leaf, one aligned pyramid block, or a
+    // multi-term range (deduplicated per tile) whose slot is known after sorting by term count.
+    const uint16_t IDENT = (uint16_t)(2 * T - 1);
     auto block_slot = [&](int k, int32_t i) -> uint16_t {
         return (uint16_t)(k == 0 ? i : 2 * T - (T >> (k - 1)) + i);
     };
-    std::vector<int32_t> pending_multi_index((size_t)N, -1);  // node -> index in multi[t] (before sorting)
+    struct Multi { std::vector<uint16_t> terms; };
+    std::vector<std::vector<Multi>> multi((size_t)NT);
+    std::vector<std::map<std::pair<int32_t, int32_t>, int32_t>> multi_index((size_t)NT);
+    // returns slot >= 0, or -(1 + index into multi[t])
+    auto resolve = [&](int32_t t, int32_t a, int32_t b) -> int32_t {
+        std::vector<uint16_t> terms;
+        int32_t x = a;
+        while (x < b) {
+            int k = x == 0 ? logT : std::min(logT, __builtin_ctz((unsigned)x));
+            while (x + (1 << k) > b) --k;
+            terms.push_back(block_slot(k, x >> k));
+            x += 1 << k;
+        }
+        if (terms.size() == 1) return terms[0];
+        auto key = std::make_pair(a, b);
+        auto it = multi_index[t].find(key);
+        if (it != multi_index[t].end()) return -(1 + it->second);
+        const int32_t idx = (int32_t)multi[t].size();
+        multi_index[t][key] = idx;
+        multi[t].push_back(Multi{std::move(terms)});
+        return -(1 + idx);
+    };
+
+    std::vector<int32_t> node_res((size_t)N, INT32_MIN);  // resolve() result per in-tile node
+    std::vector<uint8_t> spanning((size_t)N, 0);
     for (int64_t n = 0; n < N; ++n) {
         const int32_t lo = L.lo[(size_t)n], hi = L.hi[(size_t)n];
         if (hi <= lo) { spanning[(size_t)n] = 1; continue; }  // empty range (root of an empty vocabulary)
         const int32_t t = lo / T;
         if ((hi - 1) / T != t) { spanning[(size_t)n] = 1; continue; }
-        if (L.is_leaf[(size_t)n]) { P.node_slot[(size_t)n] = (uint16_t)(lo - t * T); continue; }
-        const int32_t deg = L.child_ptr[(size_t)n + 1] - L.child_ptr[(size_t)n];
-        if (deg == 1) {  // same range as its child n-1: share the slot (possibly a pending multi-term slot)
-            P.node_slot[(size_t)n] = P.node_slot[(size_t)n - 1];
-            pending_multi_index[(size_t)n] = pending_multi_index[(size_t)n - 1];
-            continue;
-        }
-        int32_t a = lo - t * T;
-        const int32_t b = hi - t * T;
-        std::vector<uint16_t> terms;
-        while (a < b) {
-            int k = a == 0 ? logT : std::min(logT, __builtin_ctz((unsigned)a));
-            while (a + (1 << k) > b) --k;
-            terms.push_back(block_slot(k, a >> k));
-            a += 1 << k;
-        }
-        if (terms.size() == 1) { P.node_slot[(size_t)n] = terms[0]; continue; }
-        pending_multi_index[(size_t)n] = (int32_t)multi[t].size();
-        multi[t].push_back(Multi{(int32_t)n, std::move(terms)});
+        node_res[(size_t)n] = resolve(t, lo - t * T, hi - t * T);
     }
 
-    // order each tile's multi-term nodes by descending term count (lanes of a warp then run the same
-    // trip count), assign slots 2T + j
-    P.br_ptr.assign((size_t)NT + 1, 0);
-    P.br_child_ptr.clear(); P.br_child.clear();
-    P.br_child_ptr.push_back(0);
+    // spanning nodes -> pieces
+    struct PieceEmit { int32_t res; int32_t idx; };
+    std::vector<std::vector<PieceEmit>> piece_emit((size_t)NT);
+    P.span_node.clear(); P.span_pp.assign(1, 0);
+    int32_t n_pieces = 0;
+    for (int64_t n = 0; n < N; ++n) {
+        if (!spanning[(size_t)n]) continue;
+        P.span_node.push_back((int32_t)n);
+        const int32_t lo = L.lo[(size_t)n], hi = L.hi[(size_t)n];
+        if (hi > lo) {
+            for (int32_t t = lo / T; t <= (hi - 1) / T; ++t) {
+                const int32_t a = std::max(lo, t * T) - t * T, b = std::min<int64_t>(hi, (int64_t)(t + 1) * T) - t * T;
+                piece_emit[t].push_back(PieceEmit{resolve(t, a, b), n_pieces++});
+            }
+        }
+        P.span_pp.push_back(n_pieces);
+    }
+    P.n_pieces = n_pieces;
+
+    // order each tile's multi-term ranges by descending term count (a warp's 32 lanes then share a trip
+    // count), pack them as ELL chunks, assign slots 2T + j
+    P.ell_chunk_ptr.assign((size_t)NT + 1, 0);
+    P.ell_desc.clear(); P.ell_terms.clear();
     P.max_tile_values = 2 * T;
+    P.n_multi = 0; P.n_terms = 0;
     std::vector<std::vector<int32_t>> rank_of((size_t)NT);  // original index -> sorted position
     for (int32_t t = 0; t < NT; ++t) {
         auto& m = multi[t];
@@ -138,48 +162,45 @@ int build_plan(const Layout& L, int32_t T, int32_t Q, Plan& P) {
         std::stable_sort(order.begin(), order.end(),
                          [&](int32_t x, int32_t y) { return m[x].terms.size() > m[y].terms.size(); });
         rank_of[t].assign(m.size(), 0);
-        P.br_ptr[t] = (int32_t)(P.br_child_ptr.size() - 1);
-        for (size_t j = 0; j < order.size(); ++j) {
-            rank_of[t][order[j]] = (int32_t)j;
-            for (uint16_t s : m[order[j]].terms) P.br_child.push_back(s);
-            P.br_child_ptr.push_back((int32_t)P.br_child.size());
+        for (size_t j = 0; j < order.size(); ++j) rank_of[t][order[j]] = (int32_t)j;
+        P.ell_chunk_ptr[t] = (int32_t)(P.ell_desc.size() / 2);
+        for (size_t j0 = 0; j0 < order.size(); j0 += 32) {
+            const size_t cn = std::min<size_t>(32, order.size() - j0);
+            const int32_t k = (int32_t)m[order[j0]].terms.size();
+            P.ell_desc.push_back((int32_t)(P.ell_terms.size() / 32));
+            P.ell_desc.push_back(k);
+            for (int32_t kk = 0; kk < k; ++kk)
+                for (size_t lane = 0; lane < 32; ++lane) {
+                    uint16_t sl = IDENT;
+                    if (lane < cn && kk < (int32_t)m[order[j0 + lane]].terms.size()) sl = m[order[j0 + lane]].terms[kk];
+                    P.ell_terms.push_back(sl);
+                }
         }
-        P.tile_nbranch[t] = (int32_t)m.size();
-        if (2 * T + (int64_t)m.size() >= 0xFFFF) { set_error("tile value array exceeds 16-bit slots"); return GT_ERR_LIMIT; }
-        P.max_tile_values = std::max<int32_t>(P.max_tile_values, 2 * T + (int32_t)m.size());
+        P.n_multi += (int64_t)m.size();
+        for (auto& e : m) P.n_terms += (int64_t)e.terms.size();
+        const int64_t values = 2 * (int64_t)T + (int64_t)((m.size() + 31) / 32) * 32;
+        if (values >= 0xFFFF) { set_error("tile value array exceeds 16-bit slots"); return GT_ERR_LIMIT; }
+        P.max_tile_values = std::max<int32_t>(P.max_tile_values, (int32_t)values);
     }
-    P.br_ptr[NT] = (int32_t)(P.br_child_ptr.size() - 1);
-    for (int64_t n = 0; n < N; ++n) {
-        const int32_t idx = pending_multi_index[(size_t)n];
-        if (idx >= 0) {
-            const int32_t t = L.lo[(size_t)n] / T;
-            P.node_slot[(size_t)n] = (uint16_t)(2 * T + rank_of[t][idx]);
-        }
-    }
+    P.ell_chunk_ptr[NT] = (int32_t)(P.ell_desc.size() / 2);
     P.max_levels = logT;
 
-    // ---- spanning nodes: value = reduction over the maximal in-tile nodes below them ---------------
-    P.span_node.clear(); P.span_ptr.assign(1, 0); P.span_term.clear();
-    std::vector<int32_t> span_index((size_t)N, -1);
-    for (int64_t n = 0; n < N; ++n) {  // ascending ids: children before parents
-        if (!spanning[(size_t)n]) continue;
-        span_index[(size_t)n] = (int32_t)P.span_node.size();
-        P.span_node.push_back((int32_t)n);
-        for (int32_t p = L.child_ptr[(size_t)n]; p < L.child_ptr[(size_t)n + 1]; ++p) {
-            const int32_t c = L.child_idx[(size_t)p];
-            if (spanning[(size_t)c]) {
-                const int32_t ci = span_index[(size_t)c];
-                // copy by index: span_term may reallocate while we append
-                for (int32_t q = P.span_ptr[(size_t)ci]; q < P.span_ptr[(size_t)ci + 1]; ++q) {
-                    const int32_t term = P.span_term[(size_t)q];
-                    P.span_term.push_back(term);
-                }
-            } else {
-                P.span_term.push_back(c);
-            }
+    auto final_slot = [&](int32_t t, int32_t res) -> uint16_t {
+        return res >= 0 ? (uint16_t)res : (uint16_t)(2 * T + rank_of[t][-(res + 1)]);
+    };
+    P.node_slot.assign((size_t)N, 0xFFFF);
+    for (int64_t n = 0; n < N; ++n)
+        if (!spanning[(size_t)n]) P.node_slot[(size_t)n] = final_slot(L.lo[(size_t)n] / T, node_res[(size_t)n]);
+    P.piece_ptr.assign((size_t)NT + 1, 0);
+    P.piece_slot.clear(); P.piece_idx.clear();
+    for (int32_t t = 0; t < NT; ++t) {
+        P.piece_ptr[t] = (int32_t)P.piece_slot.size();
+        for (const PieceEmit& e : piece_emit[t]) {
+            P.piece_slot.push_back(final_slot(t, e.res));
+            P.piece_idx.push_back(e.idx);
         }
-        P.span_ptr.push_back((int32_t)P.span_term.size());
     }
+    P.piece_ptr[NT] = (int32_t)P.piece_slot.size();
     return GT_OK;
 }
 
@@ -211,9 +232,9 @@ int64_t gt_export_plan_array(const gt_trie* t, const char* name, void* dst, int6
     const gt::Plan& P = *t->plan;
     const void* src = nullptr; int64_t n = -1; int32_t es = 4;
 #define GT_ARR(field) if (!strcmp(name, #field)) { src = P.field.data(); n = (int64_t)P.field.size(); es = (int32_t)sizeof(P.field[0]); }
-    GT_ARR(p1_chunk_ptr) GT_ARR(p1_zoff) GT_ARR(p1_src) GT_ARR(z_tile_off) GT_ARR(p2_slot) GT_ARR(br_ptr)
-    GT_ARR(br_child_ptr) GT_ARR(br_child) GT_ARR(tile_node_lo) GT_ARR(node_slot) GT_ARR(span_node) GT_ARR(span_ptr)
-    GT_ARR(span_term)
+    GT_ARR(p1_chunk_ptr) GT_ARR(p1_rec) GT_ARR(z_tile_off) GT_ARR(p2_slot) GT_ARR(ell_chunk_ptr) GT_ARR(ell_desc)
+    GT_ARR(ell_terms) GT_ARR(tile_node_lo) GT_ARR(node_slot) GT_ARR(piece_ptr) GT_ARR(piece_slot) GT_ARR(piece_idx)
+    GT_ARR(span_node) GT_ARR(span_pp)
 #undef GT_ARR
     if (n < 0) { gt::set_error("gt_export_plan_array: unknown array '%s'", name); return -1; }
     if (elem_size) *elem_size = es;

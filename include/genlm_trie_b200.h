@@ -92,7 +92,7 @@ typedef struct gt_plan_info {
     int32_t n_tiles, n_segs;
     int32_t rows_per_item;   /* R: rows a CTA processes per metadata load            */
     int32_t n_span;          /* nodes whose leaf range crosses a tile boundary       */
-    int64_t span_terms;      /* total frontier terms summed by the fix-up            */
+    int64_t span_terms;      /* per-tile pieces the spanning nodes are reduced from  */
     int32_t max_levels;      /* deepest in-tile dependency chain of branching nodes  */
     int32_t max_tile_values; /* largest per-tile value array (leaf + branching slots)*/
     int64_t staged_row_elems;/* elements per row of the tile-major staging buffer    */
@@ -106,8 +106,8 @@ int gt_get_plan_info(const gt_trie* t, gt_plan_info* info);
 int gt_plan(gt_trie* t, int32_t tile_leaves, int32_t seg_positions);
 
 /* Host-only introspection of the plan arrays, used by the CPU tests that emulate the kernels' data flow.
- * `name` is one of: p1_chunk_ptr p1_zoff p1_src z_tile_off p2_slot br_ptr br_child_ptr br_child
- * tile_node_lo node_slot span_node span_ptr span_term.  Returns the element count (or -1), and copies
+ * `name` is one of: p1_chunk_ptr p1_rec z_tile_off p2_slot ell_chunk_ptr ell_desc ell_terms tile_node_lo
+ * node_slot piece_ptr piece_slot piece_idx span_node span_pp.  Returns the element count (or -1), and copies
  * min(count, capacity) elements into dst when dst != NULL.  elem_size receives 2 or 4. */
 int64_t gt_export_plan_array(const gt_trie* t, const char* name, void* dst, int64_t capacity, int32_t* elem_size);
 
@@ -118,11 +118,10 @@ size_t gt_workspace_bytes(const gt_trie* t, int64_t max_rows);
 
 #define GT_FLAG_LOG_INPUT 1u /* rows hold log-weights: exp() is fused into the load (-inf -> 0) */
 /* Profiling aids: restrict a call to some phases (default: all).  Used by bench.py to time one kernel in
- * isolation with CUDA events; results are only complete when all three phases have run in order. */
+ * isolation with CUDA events; results are only complete when both phases have run in order. */
 #define GT_FLAG_PHASE_PERMUTE 0x100u
 #define GT_FLAG_PHASE_TILE 0x200u
-#define GT_FLAG_PHASE_SPAN 0x400u
-#define GT_FLAG_PHASE_MASK 0x700u
+#define GT_FLAG_PHASE_MASK 0x300u
 
 /* Input / output element types. */
 #define GT_F32 0

@@ -10,8 +10,8 @@ def emulate(engine, ws, op="sum"):
     """ws: float32 [B, V].  Returns float32 [B, N] computed the way permute/tile/span kernels do."""
     info = engine.plan_info()
     A = {name: engine.plan_array(name) for name in (
-        "p1_chunk_ptr", "p1_zoff", "p1_src", "z_tile_off", "p2_slot", "br_ptr", "br_child_ptr", "br_child",
-        "tile_node_lo", "node_slot", "span_node", "span_ptr", "span_term")}
+        "p1_chunk_ptr", "p1_rec", "z_tile_off", "p2_slot", "ell_chunk_ptr", "ell_desc", "ell_terms",
+        "tile_node_lo", "node_slot", "piece_ptr", "piece_slot", "piece_idx", "span_node", "span_pp")}
     T, Q, NT, NS = info["tile_leaves"], info["seg_positions"], info["n_tiles"], info["n_segs"]
     V, N, Zrow = info["n_tokens"], info["n_nodes"], info["staged_row_elems"]
     logT = T.bit_length() - 1
@@ -20,13 +20,16 @@ def emulate(engine, ws, op="sum"):
     red = np.add if op == "sum" else np.fmax
     ident = np.float32(0.0) if op == "sum" else np.float32(-np.inf)
 
-    # phase 1: permute_kernel
+    # phase 1: permute_kernel (records of {zoff, src0|src1<<16, src2|src3<<16, 0})
     z = np.full((B, Zrow), np.nan, dtype=np.float32)
+    rec = A["p1_rec"].reshape(-1, 4)
     for s in range(NS):
         seg = ws[:, s * Q:min(V, (s + 1) * Q)]
         c0, c1 = A["p1_chunk_ptr"][s], A["p1_chunk_ptr"][s + 1]
-        zoff = A["p1_zoff"][c0:c1].astype(np.int64)
-        src = A["p1_src"][4 * c0:4 * c1].reshape(-1, 4)
+        r = rec[c0:c1]
+        zoff = r[:, 0].astype(np.int64)
+        lohi = r[:, 1:3].astype(np.int64) & 0xFFFFFFFF
+        src = np.stack([lohi[:, 0] & 0xFFFF, lohi[:, 0] >> 16, lohi[:, 1] & 0xFFFF, lohi[:, 1] >> 16], axis=1)
         dst = (zoff[:, None] + np.arange(4)[None, :]).reshape(-1)
         srcf = src.reshape(-1)
         pad = srcf == 0xFFFF
@@ -36,6 +39,9 @@ def emulate(engine, ws, op="sum"):
     assert not np.isnan(z).any() or np.isnan(ws).any(), "staging row has unwritten elements"
 
     out = np.full((B, N), np.nan, dtype=np.float32)
+    part = np.full((B, max(int(A["span_pp"][-1]) if len(A["span_pp"]) else 0, 1)), np.nan, dtype=np.float32)
+    if len(A["span_pp"]) == 0 or A["span_pp"][-1] == 0:
+        part[:] = 0
     SV = info["max_tile_values"]
     for t in range(NT):
         # phase 2.1: leaves
@@ -54,27 +60,33 @@ def emulate(engine, ws, op="sum"):
             off = 2 * T - (T >> (k - 1))
             vals[:, off:off + cur.shape[1]] = cur
             prev = cur
-        # phase 2.3: multi-term nodes
-        j0, j1 = A["br_ptr"][t], A["br_ptr"][t + 1]
-        for j in range(j0, j1):
-            p0, p1 = A["br_child_ptr"][j], A["br_child_ptr"][j + 1]
-            acc = np.full(B, ident, dtype=np.float32)
-            for p in range(p0, p1):
-                acc = red(acc, vals[:, A["br_child"][p]]).astype(np.float32)
-            vals[:, 2 * T + (j - j0)] = acc
+        # phase 2.3: multi-term ranges, ELL chunks of 32 (padding = identity slot 2T-1)
+        vals[:, 2 * T - 1] = ident
+        c0, c1 = A["ell_chunk_ptr"][t], A["ell_chunk_ptr"][t + 1]
+        desc = A["ell_desc"].reshape(-1, 2)
+        for c in range(c0, c1):
+            off32, k = desc[c]
+            terms = A["ell_terms"][32 * off32:32 * (off32 + k)].reshape(k, 32)
+            acc = np.full((B, 32), ident, dtype=np.float32)
+            for kk in range(k):
+                acc = red(acc, vals[:, terms[kk]]).astype(np.float32)
+            vals[:, 2 * T + 32 * (c - c0):2 * T + 32 * (c - c0 + 1)] = acc
         # phase 2.4: emit
         n0, n1 = A["tile_node_lo"][t], A["tile_node_lo"][t + 1]
         sl = A["node_slot"][n0:n1]
         keep = sl != 0xFFFF
         out[:, n0 + np.flatnonzero(keep)] = vals[:, sl[keep]]
-    # phase 3: spanning nodes
+        # phase 2.5: pieces of spanning nodes
+        p0, p1 = A["piece_ptr"][t], A["piece_ptr"][t + 1]
+        part[:, A["piece_idx"][p0:p1]] = vals[:, A["piece_slot"][p0:p1]]
+    # last CTA of the row group: spanning nodes from their pieces (fp64 for sums)
+    assert not np.isnan(part).any() or np.isnan(ws).any()
     for i, node in enumerate(A["span_node"]):
-        p0, p1 = A["span_ptr"][i], A["span_ptr"][i + 1]
-        terms = A["span_term"][p0:p1]
-        if p1 == p0:
+        q0, q1 = A["span_pp"][i], A["span_pp"][i + 1]
+        if q1 == q0:
             out[:, node] = 0.0
         elif op == "sum":
-            out[:, node] = out[:, terms].astype(np.float64).sum(axis=1).astype(np.float32)
+            out[:, node] = part[:, q0:q1].astype(np.float64).sum(axis=1).astype(np.float32)
         else:
-            out[:, node] = np.fmax.reduce(out[:, terms], axis=1)
+            out[:, node] = np.fmax.reduce(part[:, q0:q1], axis=1)
     return out

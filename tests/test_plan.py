@@ -39,11 +39,13 @@ def test_plan_invariants():
     assert info["n_tiles"] == -(-V // T) and info["n_segs"] == -(-V // Q)
     assert info["staged_row_elems"] % 4 == 0 and info["staged_row_elems"] >= V
     # staging is a permutation of the row (plus padding)
-    src, zoff, cptr = eng.plan_array("p1_src"), eng.plan_array("p1_zoff"), eng.plan_array("p1_chunk_ptr")
+    rec, cptr = eng.plan_array("p1_rec").reshape(-1, 4), eng.plan_array("p1_chunk_ptr")
+    zoff = rec[:, 0]
     seen = np.zeros(V, dtype=np.int64)
     for s in range(info["n_segs"]):
-        e = src[4 * cptr[s]:4 * cptr[s + 1]]
-        e = e[e != 0xFFFF].astype(np.int64) + s * Q
+        lohi = rec[cptr[s]:cptr[s + 1], 1:3].astype(np.int64) & 0xFFFFFFFF
+        e = np.stack([lohi[:, 0] & 0xFFFF, lohi[:, 0] >> 16, lohi[:, 1] & 0xFFFF, lohi[:, 1] >> 16], axis=1).reshape(-1)
+        e = e[e != 0xFFFF] + s * Q
         np.add.at(seen, e, 1)
     assert (seen == 1).all()
     assert len(np.unique(zoff)) == len(zoff) and (zoff % 4 == 0).all()
@@ -54,13 +56,16 @@ def test_plan_invariants():
     spanning = (lay["lo"] // T) != ((lay["hi"] - 1) // T)
     assert np.array_equal(slot == 0xFFFF, spanning)
     assert np.array_equal(np.sort(eng.plan_array("span_node")), np.flatnonzero(spanning))
-    # frontier terms are in-tile nodes covering the spanning node's range exactly once
-    sp, st, sn = eng.plan_array("span_ptr"), eng.plan_array("span_term"), eng.plan_array("span_node")
+    # every spanning node has one piece per tile it overlaps, each written by exactly one tile
+    pp, sn = eng.plan_array("span_pp"), eng.plan_array("span_node")
     for i, n in enumerate(sn):
-        terms = st[sp[i]:sp[i + 1]]
-        assert not spanning[terms].any()
-        assert (lay["hi"][terms] - lay["lo"][terms]).sum() == lay["hi"][n] - lay["lo"][n]
-    assert info["n_span"] == int(spanning.sum())
+        assert pp[i + 1] - pp[i] == (lay["hi"][n] - 1) // T - lay["lo"][n] // T + 1
+    pidx = eng.plan_array("piece_idx")
+    assert np.array_equal(np.sort(pidx), np.arange(pp[-1]))
+    assert info["n_span"] == int(spanning.sum()) and info["span_terms"] == pp[-1]
+    # ELL padding uses the identity slot; real terms never point at it or past the tile's value array
+    terms = eng.plan_array("ell_terms")
+    assert terms.max() <= 2 * T - 1 and (terms != 2 * T - 1).sum() > 0
 
 
 def test_plan_parameter_validation():
