@@ -234,24 +234,80 @@ __global__ void __launch_bounds__(kThreads) permute_kernel(PlanView P, const IN_
 
 // ---- phase 2: per-tile pyramid, multi-term ranges, emit, spanning pieces -------------------------------------
 
+// R consecutive rows share a CTA and live interleaved in shared memory: vals[slot * R + r].  One vector
+// shared-memory access then serves all R rows of a slot.
+template <typename VT, int R> struct RowVec {
+    VT v[R];
+    __device__ __forceinline__ static RowVec load(const VT* p) {
+        RowVec x;
+        if constexpr (sizeof(VT) * R == 8) { const float2 t = *reinterpret_cast<const float2*>(p); memcpy(x.v, &t, 8); }
+        else if constexpr (sizeof(VT) * R == 16) { const float4 t = *reinterpret_cast<const float4*>(p); memcpy(x.v, &t, 16); }
+        else {
+#pragma unroll
+            for (int r = 0; r < R; ++r) x.v[r] = p[r];
+        }
+        return x;
+    }
+    __device__ __forceinline__ void store(VT* p) const {
+        if constexpr (sizeof(VT) * R == 8) { float2 t; memcpy(&t, v, 8); *reinterpret_cast<float2*>(p) = t; }
+        else if constexpr (sizeof(VT) * R == 16) { float4 t; memcpy(&t, v, 16); *reinterpret_cast<float4*>(p) = t; }
+        else {
+#pragma unroll
+            for (int r = 0; r < R; ++r) p[r] = v[r];
+        }
+    }
+    template <int OP> __device__ __forceinline__ static RowVec combine(const RowVec& a, const RowVec& b) {
+        RowVec x;
+#pragma unroll
+        for (int r = 0; r < R; ++r) x.v[r] = op_apply<OP>(a.v[r], b.v[r]);
+        return x;
+    }
+    template <int OP> __device__ __forceinline__ static RowVec ident() {
+        RowVec x;
+#pragma unroll
+        for (int r = 0; r < R; ++r) x.v[r] = op_ident<OP, VT>();
+        return x;
+    }
+    __device__ __forceinline__ RowVec shfl_down(int delta) const {
+        RowVec x;
+#pragma unroll
+        for (int r = 0; r < R; ++r) x.v[r] = __shfl_down_sync(0xffffffffu, v[r], delta);
+        return x;
+    }
+};
+
 template <typename VT, int R, int OP, bool VEC>
 __global__ void __launch_bounds__(kThreads, 2) tile_kernel(PlanView P, const VT* __restrict__ z, VT* __restrict__ out,
                                                            int64_t ld_out, VT* __restrict__ part,
                                                            int* __restrict__ counters, int n_rows) {
+    using RV = RowVec<VT, R>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    VT* vals = reinterpret_cast<VT*>(smem_raw);  // [R][SV]
+    VT* vals = reinterpret_cast<VT*>(smem_raw);  // [SV + 1][R]; slot SV is the trash slot for padding elements
     __shared__ int s_last;
-    const int T = P.T, SV = P.SV;
+    const int T = P.T;
     const int t = blockIdx.x;
     const int b0 = blockIdx.y * R;
     const int nrows = min(R, n_rows - b0);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int kWarps = kThreads / 32;
 
-    // 1. staged tile -> DFS-ordered leaf slots (two groups of 4 in flight per thread and row)
+    // per-tile scalars, fetched once up front (each is an L2 round trip if loaded where it is first needed)
+    const int zlo = __ldg(P.z_tile_off + t), zhi = __ldg(P.z_tile_off + t + 1);
+    const int ec0 = __ldg(P.ell_chunk_ptr + t), ec1 = __ldg(P.ell_chunk_ptr + t + 1);
+    const int n0 = __ldg(P.tile_node_lo + t), n1 = __ldg(P.tile_node_lo + t + 1);
+    const int pc0 = __ldg(P.piece_ptr + t), pc1 = __ldg(P.piece_ptr + t + 1);
+    // ELL descriptors of the chunks this warp will process: lane i holds the i-th one (<= 32 per warp)
+    int2 my_desc = make_int2(0, 0);
+    if (ec0 + warp + kWarps * lane < ec1) my_desc = __ldg(P.ell_desc + ec0 + warp + kWarps * lane);
+
+    // row pointers; rows past the batch are clamped for loads (their results are never stored)
+    const VT* zrow[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) zrow[r] = z + (size_t)min(b0 + r, n_rows - 1) * P.Zrow + zlo;
+
+    // 1. staged tile -> DFS-ordered leaf slots
     {
-        const int zlo = P.z_tile_off[t];
-        const int zn4 = (P.z_tile_off[t + 1] - zlo) >> 2;
+        const int zn4 = (zhi - zlo) >> 2;
         const uint2* slot4 = reinterpret_cast<const uint2*>(P.p2_slot + zlo);
         constexpr int U = 2;
         for (int ib = tid; ib < zn4; ib += U * kThreads) {
@@ -259,178 +315,160 @@ __global__ void __launch_bounds__(kThreads, 2) tile_kernel(PlanView P, const VT*
             VT v[U][R][4];
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                const int i = ib + u * kThreads;
-                sl[u] = i < zn4 ? __ldg(slot4 + i) : make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu);
+                const int i = min(ib + u * kThreads, zn4 - 1);  // clamped duplicate instead of a predicate
+                sl[u] = __ldg(slot4 + i);
 #pragma unroll
-                for (int r = 0; r < R; ++r)
-                    if (r < nrows && i < zn4)
-                        load4<VT>(z + (size_t)(b0 + r) * P.Zrow + zlo + 4 * i, v[u][r][0], v[u][r][1], v[u][r][2], v[u][r][3]);
+                for (int r = 0; r < R; ++r) load4<VT>(zrow[r] + 4 * i, v[u][r][0], v[u][r][1], v[u][r][2], v[u][r][3]);
             }
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                const unsigned s0 = sl[u].x & 0xFFFFu, s1 = sl[u].x >> 16, s2 = sl[u].y & 0xFFFFu, s3 = sl[u].y >> 16;
+                const unsigned s4[4] = {sl[u].x & 0xFFFFu, sl[u].x >> 16, sl[u].y & 0xFFFFu, sl[u].y >> 16};
 #pragma unroll
-                for (int r = 0; r < R; ++r) {
-                    if (r < nrows) {
-                        VT* lv = vals + r * SV;
-                        if (s0 != 0xFFFFu) lv[s0] = v[u][r][0];
-                        if (s1 != 0xFFFFu) lv[s1] = v[u][r][1];
-                        if (s2 != 0xFFFFu) lv[s2] = v[u][r][2];
-                        if (s3 != 0xFFFFu) lv[s3] = v[u][r][3];
-                    }
+                for (int e = 0; e < 4; ++e) {
+                    RV x;
+#pragma unroll
+                    for (int r = 0; r < R; ++r) x.v[r] = v[u][r][e];
+                    x.store(vals + s4[e] * R);
                 }
             }
         }
         const int nleaf = (int)min((int64_t)T, P.V - (int64_t)t * T);
-        for (int i = nleaf + tid; i < T; i += kThreads)
-#pragma unroll
-            for (int r = 0; r < R; ++r) vals[r * SV + i] = op_ident<OP, VT>();
-        if (tid < R) vals[tid * SV + 2 * T - 1] = op_ident<OP, VT>();  // identity slot used as ELL padding
+        for (int i = nleaf + tid; i < T; i += kThreads) RV::template ident<OP>().store(vals + i * R);
+        if (tid == 0) RV::template ident<OP>().store(vals + (2 * T - 1) * R);  // identity slot (ELL padding)
     }
     __syncthreads();
 
-    // 2. pyramid of aligned blocks: level k block i at 2T - (T >> (k-1)) + i.
+    // 2. pyramid of aligned blocks: level k block i at slot 2T - (T >> (k-1)) + i.
     //    Levels 1..3 inside a thread (8 consecutive leaves), 4..8 by warp shuffles (256 leaves per warp).
     for (int ub = warp * 32; ub < (T >> 3); ub += kWarps * 32) {
         const int u = ub + lane;
+        RV x[8];
 #pragma unroll
-        for (int r = 0; r < R; ++r) {
-            if (r < nrows) {
-                VT* lv = vals + r * SV;
-                VT x0, x1, x2, x3, x4, x5, x6, x7;
-                load4<VT>(lv + 8 * u, x0, x1, x2, x3);
-                load4<VT>(lv + 8 * u + 4, x4, x5, x6, x7);
-                const VT a0 = op_apply<OP>(x0, x1), a1 = op_apply<OP>(x2, x3);
-                const VT a2 = op_apply<OP>(x4, x5), a3 = op_apply<OP>(x6, x7);
-                store4<VT>(lv + T + 4 * u, a0, a1, a2, a3);
-                const VT c0 = op_apply<OP>(a0, a1), c1 = op_apply<OP>(a2, a3);
-                lv[2 * T - (T >> 1) + 2 * u] = c0;
-                lv[2 * T - (T >> 1) + 2 * u + 1] = c1;
-                VT x = op_apply<OP>(c0, c1);
-                lv[2 * T - (T >> 2) + u] = x;
+        for (int e = 0; e < 8; ++e) x[e] = RV::load(vals + (8 * u + e) * R);
+        RV a[4];
 #pragma unroll
-                for (int j = 1; j <= 5; ++j) {
-                    const VT y = __shfl_down_sync(0xffffffffu, x, 1 << (j - 1));
-                    x = op_apply<OP>(x, y);
-                    if ((lane & ((1 << j) - 1)) == 0) lv[2 * T - (T >> (2 + j)) + (u >> j)] = x;
-                }
-            }
+        for (int e = 0; e < 4; ++e) {
+            a[e] = RV::template combine<OP>(x[2 * e], x[2 * e + 1]);
+            a[e].store(vals + (T + 4 * u + e) * R);
+        }
+        const RV c0 = RV::template combine<OP>(a[0], a[1]), c1 = RV::template combine<OP>(a[2], a[3]);
+        c0.store(vals + (2 * T - (T >> 1) + 2 * u) * R);
+        c1.store(vals + (2 * T - (T >> 1) + 2 * u + 1) * R);
+        RV y = RV::template combine<OP>(c0, c1);
+        y.store(vals + (2 * T - (T >> 2) + u) * R);
+#pragma unroll
+        for (int j = 1; j <= 5; ++j) {
+            y = RV::template combine<OP>(y, y.shfl_down(1 << (j - 1)));
+            if ((lane & ((1 << j) - 1)) == 0) y.store(vals + (2 * T - (T >> (2 + j)) + (u >> j)) * R);
         }
     }
     __syncthreads();
-    //    Levels 9..logT: T/256 <= 32 level-8 blocks, one warp per row.
-    if (warp < nrows && P.logT > 8) {
-        VT* lv = vals + warp * SV;
+    //    Levels 9..logT: T/256 <= 32 level-8 blocks, one warp.
+    if (warp == 0 && P.logT > 8) {
         const int n8 = T >> 8;
-        VT x = lane < n8 ? lv[2 * T - (T >> 7) + lane] : op_ident<OP, VT>();
+        RV y = lane < n8 ? RV::load(vals + (2 * T - (T >> 7) + lane) * R) : RV::template ident<OP>();
         for (int j = 1; j <= P.logT - 8; ++j) {
-            const VT y = __shfl_down_sync(0xffffffffu, x, 1 << (j - 1));
-            x = op_apply<OP>(x, y);
-            if ((lane & ((1 << j) - 1)) == 0 && lane < n8) lv[2 * T - (T >> (7 + j)) + (lane >> j)] = x;
+            y = RV::template combine<OP>(y, y.shfl_down(1 << (j - 1)));
+            if ((lane & ((1 << j) - 1)) == 0 && lane < n8) y.store(vals + (2 * T - (T >> (7 + j)) + (lane >> j)) * R);
         }
     }
     __syncthreads();
 
-    // 3. ranges that need more than one block: ELL chunks of 32 ranges, one warp per chunk, terms coalesced
+    // 3. ranges that need more than one block: ELL chunks of 32 ranges, one warp per chunk; the chunk's terms
+    //    are fetched 8 rows (8 independent coalesced loads) at a time
     {
-        const int c0 = P.ell_chunk_ptr[t], c1 = P.ell_chunk_ptr[t + 1];
-        for (int c = c0 + warp; c < c1; c += kWarps) {
-            const int2 d = __ldg(P.ell_desc + c);
-            const uint16_t* tp = P.ell_terms + (size_t)d.x * 32 + lane;
-            VT acc[R];
+        int it = 0;
+        for (int c = ec0 + warp; c < ec1; c += kWarps, ++it) {
+            const int off32 = __shfl_sync(0xffffffffu, my_desc.x, it), k = __shfl_sync(0xffffffffu, my_desc.y, it);
+            const uint16_t* tp = P.ell_terms + (size_t)off32 * 32 + lane;
+            RV acc = RV::template ident<OP>();
+            for (int kb = 0; kb < k; kb += 8) {
+                int sl[8];
 #pragma unroll
-            for (int r = 0; r < R; ++r) acc[r] = op_ident<OP, VT>();
-#pragma unroll 4
-            for (int kk = 0; kk < d.y; ++kk) {
-                const int sl = __ldg(tp + kk * 32);
+                for (int e = 0; e < 8; ++e) sl[e] = __ldg(tp + min(kb + e, k - 1) * 32);
 #pragma unroll
-                for (int r = 0; r < R; ++r) acc[r] = op_apply<OP>(acc[r], vals[r * SV + sl]);
+                for (int e = 0; e < 8; ++e)
+                    if (kb + e < k) acc = RV::template combine<OP>(acc, RV::load(vals + sl[e] * R));
             }
-            const int j = (c - c0) * 32 + lane;
-#pragma unroll
-            for (int r = 0; r < R; ++r) vals[r * SV + 2 * T + j] = acc[r];
+            acc.store(vals + (2 * T + (c - ec0) * 32 + lane) * R);
         }
     }
     __syncthreads();
 
-    // 4. emit the tile's node-id interval, coalesced
+    // 4. pieces of spanning nodes that overlap this tile (reduced by the last tile of the row group, below)
+    for (int i = pc0 + tid; i < pc1; i += kThreads) {
+        const RV x = RV::load(vals + (int)__ldg(P.piece_slot + i) * R);
+        const int idx = __ldg(P.piece_idx + i);
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+            if (r < nrows) part[(size_t)(b0 + r) * P.n_pieces + idx] = x.v[r];
+    }
+
+    // 5. emit the tile's node-id interval, coalesced.  Spanning nodes inside the interval carry the identity
+    //    slot: what is written for them here is overwritten by the reduction of their pieces.
     {
-        const int n0 = P.tile_node_lo[t], n1 = P.tile_node_lo[t + 1];
+        VT* orow[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) orow[r] = out + (size_t)min(b0 + r, n_rows - 1) * ld_out;
         if constexpr (VEC) {
             // rows are 16-byte aligned and ld_out % 4 == 0: one 128-bit store per 4 consecutive node ids
-            const int q0 = n0 >> 2, q1 = (n1 + 3) >> 2;
+            const int q0 = (n0 + 3) >> 2, q1 = n1 >> 2;  // interior quads
             const uint2* slot4 = reinterpret_cast<const uint2*>(P.node_slot);
             constexpr int U = 4;
             for (int qb = q0 + tid; qb < q1; qb += U * kThreads) {
                 uint2 sl[U];
 #pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    const int q = qb + u * kThreads;
-                    sl[u] = q < q1 ? __ldg(slot4 + q) : make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu);
-                }
+                for (int u = 0; u < U; ++u) sl[u] = __ldg(slot4 + min(qb + u * kThreads, q1 - 1));
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
                     const int q = qb + u * kThreads;
-                    const unsigned s0 = sl[u].x & 0xFFFFu, s1 = sl[u].x >> 16, s2 = sl[u].y & 0xFFFFu, s3 = sl[u].y >> 16;
-                    const int n = 4 * q;
-                    const bool in0 = n >= n0 && n < n1 && s0 != 0xFFFFu, in1 = n + 1 >= n0 && n + 1 < n1 && s1 != 0xFFFFu;
-                    const bool in2 = n + 2 >= n0 && n + 2 < n1 && s2 != 0xFFFFu, in3 = n + 3 >= n0 && n + 3 < n1 && s3 != 0xFFFFu;
-                    if (in0 && in1 && in2 && in3) {
+                    if (q < q1) {
+                        const RV x0 = RV::load(vals + (sl[u].x & 0xFFFFu) * R), x1 = RV::load(vals + (sl[u].x >> 16) * R);
+                        const RV x2 = RV::load(vals + (sl[u].y & 0xFFFFu) * R), x3 = RV::load(vals + (sl[u].y >> 16) * R);
 #pragma unroll
-                        for (int r = 0; r < R; ++r) {
-                            if (r < nrows) {
-                                const VT* lv = vals + r * SV;
-                                store4_stream<VT>(out + (size_t)(b0 + r) * ld_out + n, lv[s0], lv[s1], lv[s2], lv[s3]);
-                            }
-                        }
-                    } else if (in0 || in1 || in2 || in3) {
-#pragma unroll
-                        for (int r = 0; r < R; ++r) {
-                            if (r < nrows) {
-                                const VT* lv = vals + r * SV;
-                                VT* o = out + (size_t)(b0 + r) * ld_out + n;
-                                if (in0) __stcs(o, lv[s0]);
-                                if (in1) __stcs(o + 1, lv[s1]);
-                                if (in2) __stcs(o + 2, lv[s2]);
-                                if (in3) __stcs(o + 3, lv[s3]);
-                            }
-                        }
+                        for (int r = 0; r < R; ++r)
+                            if (r < nrows) store4_stream<VT>(orow[r] + 4 * q, x0.v[r], x1.v[r], x2.v[r], x3.v[r]);
                     }
+                }
+            }
+            // the (at most 6) nodes of the interval outside the interior quads
+            if (tid < 8) {
+                const int n = tid < 4 ? n0 + tid : (q1 << 2) + (tid - 4);
+                const bool head = tid < 4 && n < min(q0 << 2, n1), tail = tid >= 4 && n >= max(q0 << 2, n0) && n < n1 && q1 >= q0;
+                if (head || tail) {
+                    const RV x = RV::load(vals + (int)__ldg(P.node_slot + n) * R);
+#pragma unroll
+                    for (int r = 0; r < R; ++r)
+                        if (r < nrows) orow[r][n] = x.v[r];
                 }
             }
         } else {
             constexpr int U = 4;
             for (int nb = n0 + tid; nb < n1; nb += U * kThreads) {
-                unsigned sl[U];
+                int sl[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) sl[u] = __ldg(P.node_slot + min(nb + u * kThreads, n1 - 1));
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
                     const int n = nb + u * kThreads;
-                    sl[u] = n < n1 ? (unsigned)__ldg(P.node_slot + n) : 0xFFFFu;
-                }
+                    if (n < n1) {
+                        const RV x = RV::load(vals + sl[u] * R);
 #pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    if (sl[u] == 0xFFFFu) continue;
-                    const int n = nb + u * kThreads;
-#pragma unroll
-                    for (int r = 0; r < R; ++r)
-                        if (r < nrows) __stcs(out + (size_t)(b0 + r) * ld_out + n, vals[r * SV + sl[u]]);
+                        for (int r = 0; r < R; ++r)
+                            if (r < nrows) __stcs(orow[r] + n, x.v[r]);
+                    }
                 }
             }
         }
     }
 
-    // 5. pieces of spanning nodes that overlap this tile; the last tile of the row group reduces them
+    // 6. the last CTA of the row group to get here reduces the spanning nodes from their pieces (fp64 for sums)
     if (P.n_span > 0) {
-        const int p0 = P.piece_ptr[t], p1 = P.piece_ptr[t + 1];
-        for (int i = p0 + tid; i < p1; i += kThreads) {
-            const int sl = P.piece_slot[i], idx = P.piece_idx[i];
-#pragma unroll
-            for (int r = 0; r < R; ++r)
-                if (r < nrows) part[(size_t)(b0 + r) * P.n_pieces + idx] = vals[r * SV + sl];
-        }
-        __threadfence();
         __syncthreads();
-        if (tid == 0) s_last = atomicAdd(counters + blockIdx.y, 1) == P.NT - 1;
+        if (tid == 0) {
+            __threadfence();  // cumulative: publishes the whole CTA's stores (ordered before it by the barrier)
+            s_last = atomicAdd(counters + blockIdx.y, 1) == P.NT - 1;
+        }
         __syncthreads();
         if (s_last) {
             __threadfence();
@@ -520,7 +558,7 @@ constexpr int R_F32 = 2;  // rows per CTA, float pipeline
 constexpr int R_F64 = 1;  // rows per CTA, double pipeline
 
 template <typename VT, int R> static size_t permute_smem(const PlanView& v) { return (size_t)R * (v.Q + kSegPad) * sizeof(VT); }
-template <typename VT, int R> static size_t tile_smem(const PlanView& v) { return (size_t)R * v.SV * sizeof(VT); }
+template <typename VT, int R> static size_t tile_smem(const PlanView& v) { return (size_t)R * (v.SV + 4) * sizeof(VT); }
 
 // Opt in to > 48 KB dynamic shared memory once per (kernel, device, size): the attribute call is kept off the
 // steady-state launch path (and out of CUDA graph captures).  Keyed by the kernel's address: instantiations

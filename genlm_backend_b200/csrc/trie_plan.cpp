@@ -188,7 +188,7 @@ int build_plan(const Layout& L, int32_t T, int32_t Q, Plan& P) {
     auto final_slot = [&](int32_t t, int32_t res) -> uint16_t {
         return res >= 0 ? (uint16_t)res : (uint16_t)(2 * T + rank_of[t][-(res + 1)]);
     };
-    P.node_slot.assign((size_t)N, 0xFFFF);
+    P.node_slot.assign((size_t)N, IDENT);  // spanning nodes: identity slot (their emit is overwritten by the piece reduction)
     for (int64_t n = 0; n < N; ++n)
         if (!spanning[(size_t)n]) P.node_slot[(size_t)n] = final_slot(L.lo[(size_t)n] / T, node_res[(size_t)n]);
     P.piece_ptr.assign((size_t)NT + 1, 0);
@@ -201,6 +201,9 @@ int build_plan(const Layout& L, int32_t T, int32_t Q, Plan& P) {
         }
     }
     P.piece_ptr[NT] = (int32_t)P.piece_slot.size();
+    // staged padding elements land in the trash slot one past the value array (same for every tile)
+    P.max_tile_values = (P.max_tile_values + 3) & ~3;
+    for (auto& sl : P.p2_slot) if (sl == 0xFFFF) sl = (uint16_t)P.max_tile_values;
     return GT_OK;
 }
 

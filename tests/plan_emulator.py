@@ -45,11 +45,11 @@ def emulate(engine, ws, op="sum"):
     SV = info["max_tile_values"]
     for t in range(NT):
         # phase 2.1: leaves
-        vals = np.full((B, SV), np.nan, dtype=np.float32)
+        vals = np.full((B, SV + 1), np.nan, dtype=np.float32)  # slot SV = trash slot for staged padding
         zlo, zhi = A["z_tile_off"][t], A["z_tile_off"][t + 1]
         slot = A["p2_slot"][zlo:zhi]
-        keep = slot != 0xFFFF
-        vals[:, slot[keep]] = z[:, zlo:zhi][:, keep]
+        assert slot.max() <= SV and np.array_equal(np.sort(slot[slot < SV]), np.arange((slot < SV).sum()))
+        vals[:, slot] = z[:, zlo:zhi]
         nleaf = min(T, V - t * T)
         vals[:, nleaf:T] = ident
         assert not np.isnan(vals[:, :nleaf]).any() or np.isnan(ws).any()
@@ -73,9 +73,8 @@ def emulate(engine, ws, op="sum"):
             vals[:, 2 * T + 32 * (c - c0):2 * T + 32 * (c - c0 + 1)] = acc
         # phase 2.4: emit
         n0, n1 = A["tile_node_lo"][t], A["tile_node_lo"][t + 1]
-        sl = A["node_slot"][n0:n1]
-        keep = sl != 0xFFFF
-        out[:, n0 + np.flatnonzero(keep)] = vals[:, sl[keep]]
+        sl = A["node_slot"][n0:n1]  # spanning nodes carry the identity slot here and are overwritten below
+        out[:, n0:n1] = vals[:, sl]
         # phase 2.5: pieces of spanning nodes
         p0, p1 = A["piece_ptr"][t], A["piece_ptr"][t + 1]
         part[:, A["piece_idx"][p0:p1]] = vals[:, A["piece_slot"][p0:p1]]

@@ -54,7 +54,7 @@ def test_plan_invariants():
     assert lo[0] == 0 and lo[-1] == len(trie) and (np.diff(lo) > 0).all()
     slot = eng.plan_array("node_slot")
     spanning = (lay["lo"] // T) != ((lay["hi"] - 1) // T)
-    assert np.array_equal(slot == 0xFFFF, spanning)
+    assert np.array_equal(slot == 2 * T - 1, spanning)  # spanning nodes point at the identity slot
     assert np.array_equal(np.sort(eng.plan_array("span_node")), np.flatnonzero(spanning))
     # every spanning node has one piece per tile it overlaps, each written by exactly one tile
     pp, sn = eng.plan_array("span_pp"), eng.plan_array("span_node")

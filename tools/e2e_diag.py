@@ -44,3 +44,30 @@ def duplex():
     with torch.cuda.stream(s1):
         pin_out.copy_(dev_out, non_blocking=True)
 print("duplex H2D 33MB + D2H 88MB ms", t(duplex))
+
+# ---- bench-like loop: results retained, inputs alternate; with and without an NVML sampling thread -------------
+import threading
+host2 = [host, torch.tensor(dirichlet_rows(B, V, alpha=1.0, seed=2)).pin_memory()]
+def loop(n=10):
+    keep = None
+    for i in range(4):
+        keep = trie.batch_weight_sum_max(host2[i % 2])
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(n):
+        sums, maxes = trie.batch_weight_sum_max(host2[i % 2])
+        _ = float(sums[0, N - 1]) + float(maxes[B - 1, N - 1])
+    return (time.perf_counter() - t0) / n * 1e3
+print("bench-like e2e loop, no sampler ms/step", loop())
+import pynvml
+pynvml.nvmlInit(); h = pynvml.nvmlDeviceGetHandleByIndex(0)
+stop = threading.Event()
+def sampler(period):
+    while not stop.is_set():
+        pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM); pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+        time.sleep(period)
+t0 = time.perf_counter(); pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM); print("one nvml clock query ms", (time.perf_counter() - t0) * 1e3)
+for period in (0.02, 0.2):
+    stop.clear(); th = threading.Thread(target=sampler, args=(period,), daemon=True); th.start()
+    print(f"bench-like e2e loop, nvml sampler every {period}s ms/step", loop())
+    stop.set(); th.join()
