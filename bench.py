@@ -225,7 +225,7 @@ def run_ours(args):
     def step(k, phases=0, ops=("sum", "max")):
         eng.reduce(ws_sets[k], ops, out_sum=sum_sets[k], out_max=max_sets[k], phases=phases)
 
-    launches_per_step = 3  # permute + tile<sum> + tile<max>
+    launches_per_step = 1 + 2 * (1 + (1 if info["n_span"] > 0 else 0))  # permute + 2 x (tile + span)
 
     # warm-up (also sets kernel attributes, allocates the scratch) ------------------------------------------------
     for i in range(W):
@@ -341,7 +341,7 @@ def run_ours(args):
         },
         "path_roofline": {
             "achieved": path_achieved, "peak": peak, "unit": "GB/s", "frac": path_achieved / peak,
-            "note": "whole step (permute + tile<sum> + tile<max>) against 2 x (4V + 4N) bytes per distribution",
+            "note": "whole step (permute + 2 x (tile + span)) against 2 x (4V + 4N) bytes per distribution",
         },
         "kernel_ms": {"permute": ms_permute, "tile_sum": ms_tile, "tile_max": ms_tile_max,
                       "sum_op_all_phases": ms_sum_op},

@@ -8,11 +8,11 @@
 //   phase 1  permute_kernel : row segment (vocabulary order, coalesced 128-bit loads, exp/cast fused)
 //                             -> shared memory -> tile-major staging rows z (coalesced 128-bit stores,
 //                             L2-resident scratch).  All scattered accesses hit shared memory only.
-//   phase 2  tile_kernel    : staged tile -> DFS-ordered leaf values in shared memory -> aligned-block
-//                             pyramid (warp shuffles) -> multi-term ranges (ELL-packed term lists) ->
-//                             coalesced 128-bit emit of the tile's node-id interval.  Nodes whose leaf
-//                             range crosses tiles are written as per-tile pieces; the last CTA of a row
-//                             group to finish (atomic ticket) reduces them in fp64.
+//   phase 2  tile_kernel    : staged tile -> DFS-ordered leaf values in shared memory (rows of a row group
+//                             interleaved per slot) -> aligned-block pyramid (warp shuffles) -> multi-term
+//                             ranges (ELL-packed term lists) -> coalesced 128-bit emit of the tile's node-id
+//                             interval.  Nodes whose leaf range crosses tiles are written as per-tile pieces.
+//   phase 3  span_kernel    : those few nodes, reduced from their pieces (fp64 for sums).
 #include <cuda_runtime.h>
 #include <cuda_fp16.h>
 #include <cuda_bf16.h>
@@ -177,8 +177,7 @@ __device__ __forceinline__ void load_segment_f64(const double* __restrict__ row,
 
 template <typename VT, typename IN_T, int R>
 __global__ void __launch_bounds__(kThreads) permute_kernel(PlanView P, const IN_T* __restrict__ ws, int64_t ld_ws,
-                                                           VT* __restrict__ z, int* __restrict__ counters, int n_rows,
-                                                           int log_input) {
+                                                           VT* __restrict__ z, int n_rows, int log_input) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     VT* seg = reinterpret_cast<VT*>(smem_raw);  // [R][Q + kSegPad]
     const int pitch = P.Q + kSegPad;
@@ -187,8 +186,6 @@ __global__ void __launch_bounds__(kThreads) permute_kernel(PlanView P, const IN_
     const int nrows = min(R, n_rows - b0);
     const int seg_lo = s * P.Q;
     const int seg_n = (int)min((int64_t)P.Q, P.V - seg_lo);
-    // tickets of the tile kernels' row groups (indexed by row group of any size <= rows): zero one per row
-    if (s == 0 && threadIdx.x < R && b0 + (int)threadIdx.x < n_rows) counters[b0 + threadIdx.x] = 0;
 
     int phase[R];
 #pragma unroll
@@ -234,6 +231,17 @@ __global__ void __launch_bounds__(kThreads) permute_kernel(PlanView P, const IN_
 
 // ---- phase 2: per-tile pyramid, multi-term ranges, emit, spanning pieces -------------------------------------
 
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+// first / one-past-last ELL term row (in units of 32 terms) of a tile's chunk range
+__device__ __forceinline__ int my_first_off(const PlanView& P, int ec0, int ec1) {
+    return ec1 > ec0 ? __ldg(P.ell_desc + ec0).x : 0;
+}
+__device__ __forceinline__ int my_last_off(const PlanView& P, int ec0, int ec1) {
+    if (ec1 <= ec0) return 0;
+    const int2 d = __ldg(P.ell_desc + ec1 - 1);
+    return d.x + d.y;
+}
+
 // R consecutive rows share a CTA and live interleaved in shared memory: vals[slot * R + r].  One vector
 // shared-memory access then serves all R rows of a slot.
 template <typename VT, int R> struct RowVec {
@@ -278,12 +286,10 @@ template <typename VT, int R> struct RowVec {
 
 template <typename VT, int R, int OP, bool VEC>
 __global__ void __launch_bounds__(kThreads, 2) tile_kernel(PlanView P, const VT* __restrict__ z, VT* __restrict__ out,
-                                                           int64_t ld_out, VT* __restrict__ part,
-                                                           int* __restrict__ counters, int n_rows) {
+                                                           int64_t ld_out, VT* __restrict__ part, int n_rows) {
     using RV = RowVec<VT, R>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     VT* vals = reinterpret_cast<VT*>(smem_raw);  // [SV + 1][R]; slot SV is the trash slot for padding elements
-    __shared__ int s_last;
     const int T = P.T;
     const int t = blockIdx.x;
     const int b0 = blockIdx.y * R;
@@ -299,6 +305,17 @@ __global__ void __launch_bounds__(kThreads, 2) tile_kernel(PlanView P, const VT*
     // ELL descriptors of the chunks this warp will process: lane i holds the i-th one (<= 32 per warp)
     int2 my_desc = make_int2(0, 0);
     if (ec0 + warp + kWarps * lane < ec1) my_desc = __ldg(P.ell_desc + ec0 + warp + kWarps * lane);
+
+    // the ELL term rows and the emit slots are read once, late in the kernel: start pulling their lines into L1
+    // now so those phases do not pay an L2 round trip per batch
+    {
+        const char* e0 = reinterpret_cast<const char*>(P.ell_terms + (size_t)my_first_off(P, ec0, ec1) * 32);
+        const char* e1 = reinterpret_cast<const char*>(P.ell_terms + (size_t)my_last_off(P, ec0, ec1) * 32);
+        for (const char* p = e0 + (size_t)tid * 128; p < e1; p += (size_t)kThreads * 128) prefetch_l1(p);
+        const char* s0 = reinterpret_cast<const char*>(P.node_slot + n0);
+        const char* s1 = reinterpret_cast<const char*>(P.node_slot + n1);
+        for (const char* p = s0 + (size_t)tid * 128; p < s1; p += (size_t)kThreads * 128) prefetch_l1(p);
+    }
 
     // row pointers; rows past the batch are clamped for loads (their results are never stored)
     const VT* zrow[R];
@@ -382,12 +399,12 @@ __global__ void __launch_bounds__(kThreads, 2) tile_kernel(PlanView P, const VT*
             const int off32 = __shfl_sync(0xffffffffu, my_desc.x, it), k = __shfl_sync(0xffffffffu, my_desc.y, it);
             const uint16_t* tp = P.ell_terms + (size_t)off32 * 32 + lane;
             RV acc = RV::template ident<OP>();
-            for (int kb = 0; kb < k; kb += 8) {
-                int sl[8];
+            for (int kb = 0; kb < k; kb += 4) {  // k >= 2; rows past k are clamped re-reads that are not accumulated
+                int sl[4];
 #pragma unroll
-                for (int e = 0; e < 8; ++e) sl[e] = __ldg(tp + min(kb + e, k - 1) * 32);
+                for (int e = 0; e < 4; ++e) sl[e] = __ldg(tp + min(kb + e, k - 1) * 32);
 #pragma unroll
-                for (int e = 0; e < 8; ++e)
+                for (int e = 0; e < 4; ++e)
                     if (kb + e < k) acc = RV::template combine<OP>(acc, RV::load(vals + sl[e] * R));
             }
             acc.store(vals + (2 * T + (c - ec0) * 32 + lane) * R);
@@ -395,7 +412,7 @@ __global__ void __launch_bounds__(kThreads, 2) tile_kernel(PlanView P, const VT*
     }
     __syncthreads();
 
-    // 4. pieces of spanning nodes that overlap this tile (reduced by the last tile of the row group, below)
+    // 4. pieces of spanning nodes that overlap this tile (reduced by span_kernel, which runs next on the stream)
     for (int i = pc0 + tid; i < pc1; i += kThreads) {
         const RV x = RV::load(vals + (int)__ldg(P.piece_slot + i) * R);
         const int idx = __ldg(P.piece_idx + i);
@@ -414,7 +431,7 @@ __global__ void __launch_bounds__(kThreads, 2) tile_kernel(PlanView P, const VT*
             // rows are 16-byte aligned and ld_out % 4 == 0: one 128-bit store per 4 consecutive node ids
             const int q0 = (n0 + 3) >> 2, q1 = n1 >> 2;  // interior quads
             const uint2* slot4 = reinterpret_cast<const uint2*>(P.node_slot);
-            constexpr int U = 4;
+            constexpr int U = 2;
             for (int qb = q0 + tid; qb < q1; qb += U * kThreads) {
                 uint2 sl[U];
 #pragma unroll
@@ -462,29 +479,24 @@ __global__ void __launch_bounds__(kThreads, 2) tile_kernel(PlanView P, const VT*
         }
     }
 
-    // 6. the last CTA of the row group to get here reduces the spanning nodes from their pieces (fp64 for sums)
-    if (P.n_span > 0) {
-        __syncthreads();
-        if (tid == 0) {
-            __threadfence();  // cumulative: publishes the whole CTA's stores (ordered before it by the barrier)
-            s_last = atomicAdd(counters + blockIdx.y, 1) == P.NT - 1;
-        }
-        __syncthreads();
-        if (s_last) {
-            __threadfence();
-            using AT = typename std::conditional<OP == OP_SUM, double, VT>::type;
-            for (int i = tid; i < P.n_span * R; i += kThreads) {
-                const int r = i / P.n_span, k = i - r * P.n_span;
-                if (r >= nrows) break;
-                const int q0 = P.span_pp[k], q1 = P.span_pp[k + 1];
-                const VT* pr = part + (size_t)(b0 + r) * P.n_pieces;
-                AT acc = op_ident<OP, AT>();
-#pragma unroll 4
-                for (int q = q0; q < q1; ++q) acc = op_apply<OP, AT>(acc, (AT)__ldcg(pr + q));
-                out[(size_t)(b0 + r) * ld_out + P.span_node[k]] = q1 > q0 ? (VT)acc : VT(0);
-            }
-            if (tid == 0) counters[blockIdx.y] = 0;  // ready for the next tile launch over the same row groups
-        }
+}
+
+// ---- phase 3: nodes whose leaf range crosses tiles, reduced from their per-tile pieces (fp64 for sums) ------------
+// One thread per (spanning node, row); consecutive lanes take consecutive spanning nodes of one row, whose pieces
+// are adjacent in `part`.  Runs after tile_kernel in stream order and overwrites the placeholder it emitted.
+template <typename VT, int OP>
+__global__ void __launch_bounds__(256) span_kernel(PlanView P, const VT* __restrict__ part, VT* __restrict__ out,
+                                                   int64_t ld_out, int n_rows) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= P.n_span) return;
+    const int q0 = __ldg(P.span_pp + k), q1 = __ldg(P.span_pp + k + 1), node = __ldg(P.span_node + k);
+    using AT = typename std::conditional<OP == OP_SUM, double, VT>::type;
+    for (int b = blockIdx.y; b < n_rows; b += gridDim.y) {
+        const VT* pr = part + (size_t)b * P.n_pieces;
+        AT acc = op_ident<OP, AT>();
+#pragma unroll 8
+        for (int q = q0; q < q1; ++q) acc = op_apply<OP, AT>(acc, (AT)pr[q]);
+        out[(size_t)b * ld_out + node] = q1 > q0 ? (VT)acc : VT(0);
     }
 }
 
@@ -581,23 +593,18 @@ template <typename K> static cudaError_t allow_smem(K kernel, size_t bytes) {
     return allow_smem_impl(reinterpret_cast<const void*>(kernel), bytes);
 }
 
-// Scratch layout for one chunk of `rows` rows: z [rows][Zrow] VT | part [rows][n_pieces] VT | counters [rows] int
+// Scratch layout for one chunk of `rows` rows: z [rows][Zrow] VT | part [rows][n_pieces] VT
 template <typename VT> struct Scratch {
-    VT* z; VT* part; int* counters;
-    static size_t bytes_per_row(const PlanView& v) {
-        return (size_t)v.Zrow * sizeof(VT) + (size_t)((v.n_pieces + 3) & ~3) * sizeof(VT) + 16;
-    }
+    VT* z; VT* part;
     Scratch(const PlanView& v, void* base, int64_t rows) {
         char* p = static_cast<char*>(base);
         z = reinterpret_cast<VT*>(p);
         p += (((size_t)rows * v.Zrow * sizeof(VT)) + 255) & ~size_t(255);
         part = reinterpret_cast<VT*>(p);
-        p += (((size_t)rows * v.n_pieces * sizeof(VT)) + 255) & ~size_t(255);
-        counters = reinterpret_cast<int*>(p);
     }
     static size_t total(const PlanView& v, int64_t rows) {
         return ((((size_t)rows * v.Zrow * sizeof(VT)) + 255) & ~size_t(255)) +
-               ((((size_t)rows * v.n_pieces * sizeof(VT)) + 255) & ~size_t(255)) + (((size_t)rows * sizeof(int)) + 255 & ~size_t(255));
+               ((((size_t)rows * v.n_pieces * sizeof(VT)) + 255) & ~size_t(255));
     }
 };
 
@@ -607,7 +614,7 @@ static int launch_permute(const PlanView& v, const void* ws, int64_t ld_ws, cons
     const size_t smem = permute_smem<VT, R>(v);
     GT_CUDA(allow_smem(permute_kernel<VT, IN_T, R>, smem));
     dim3 grid((unsigned)v.NS, (unsigned)((rows + R - 1) / R));
-    permute_kernel<VT, IN_T, R><<<grid, kThreads, smem, st>>>(v, static_cast<const IN_T*>(ws), ld_ws, sc.z, sc.counters, rows,
+    permute_kernel<VT, IN_T, R><<<grid, kThreads, smem, st>>>(v, static_cast<const IN_T*>(ws), ld_ws, sc.z, rows,
                                                              log_input ? 1 : 0);
     GT_CUDA(cudaGetLastError());
     return GT_OK;
@@ -624,12 +631,17 @@ static int launch_tile(const PlanView& v, const Scratch<VT>& sc, VT* out, int64_
     const bool vec = (ld_out % 4 == 0) && (reinterpret_cast<uintptr_t>(out) % (4 * sizeof(VT)) == 0);
     if (vec) {
         GT_CUDA(allow_smem(tile_kernel<VT, R, OP, true>, smem));
-        tile_kernel<VT, R, OP, true><<<grid, kThreads, smem, st>>>(v, sc.z, out, ld_out, sc.part, sc.counters, rows);
+        tile_kernel<VT, R, OP, true><<<grid, kThreads, smem, st>>>(v, sc.z, out, ld_out, sc.part, rows);
     } else {
         GT_CUDA(allow_smem(tile_kernel<VT, R, OP, false>, smem));
-        tile_kernel<VT, R, OP, false><<<grid, kThreads, smem, st>>>(v, sc.z, out, ld_out, sc.part, sc.counters, rows);
+        tile_kernel<VT, R, OP, false><<<grid, kThreads, smem, st>>>(v, sc.z, out, ld_out, sc.part, rows);
     }
     GT_CUDA(cudaGetLastError());
+    if (v.n_span > 0) {
+        dim3 sgrid((unsigned)((v.n_span + 255) / 256), (unsigned)std::min(rows, 4096));
+        span_kernel<VT, OP><<<sgrid, 256, 0, st>>>(v, sc.part, out, ld_out, rows);
+        GT_CUDA(cudaGetLastError());
+    }
     return GT_OK;
 }
 

@@ -120,7 +120,7 @@ size_t gt_workspace_bytes(const gt_trie* t, int64_t max_rows);
 /* Profiling aids: restrict a call to some phases (default: all).  Used by bench.py to time one kernel in
  * isolation with CUDA events; results are only complete when both phases have run in order. */
 #define GT_FLAG_PHASE_PERMUTE 0x100u
-#define GT_FLAG_PHASE_TILE 0x200u
+#define GT_FLAG_PHASE_TILE 0x200u /* tile kernel + the small spanning-node kernel that follows it */
 #define GT_FLAG_PHASE_MASK 0x300u
 
 /* Input / output element types. */
