@@ -284,7 +284,7 @@ template <typename VT, int R> struct RowVec {
     }
 };
 
-template <typename VT, int R, int OP, bool VEC>
+template <typename VT, int R, int OP>
 __global__ void __launch_bounds__(kThreads, 2) tile_kernel(PlanView P, const VT* __restrict__ z, VT* __restrict__ out,
                                                            int64_t ld_out, VT* __restrict__ part, int n_rows) {
     using RV = RowVec<VT, R>;
@@ -355,28 +355,54 @@ __global__ void __launch_bounds__(kThreads, 2) tile_kernel(PlanView P, const VT*
     }
     __syncthreads();
 
-    // 2. pyramid of aligned blocks: level k block i at slot 2T - (T >> (k-1)) + i.
-    //    Levels 1..3 inside a thread (8 consecutive leaves), 4..8 by warp shuffles (256 leaves per warp).
-    for (int ub = warp * 32; ub < (T >> 3); ub += kWarps * 32) {
-        const int u = ub + lane;
-        RV x[8];
+    // 2. pyramid of aligned blocks: level k block i at slot 2T - (T >> (k-1)) + i.  One warp builds levels 1..8
+    //    of a 256-leaf block.  Lane l loads the 16-byte chunks j*32 + l (conflict-free), reduces inside the
+    //    chunk, then across lanes by shuffles, then across its J chunks.
+    {
+        constexpr int E = (16 / (int)(sizeof(VT) * R)) > 0 ? (16 / (int)(sizeof(VT) * R)) : 1;  // slots per chunk
+        constexpr int LE = E == 4 ? 2 : (E == 2 ? 1 : 0);
+        constexpr int J = 8 / E;  // chunks per lane: J * 32 * E = 256 leaves
+        auto level_slot = [&](int k, int i) { return 2 * T - (T >> (k - 1)) + i; };
+        for (int blk = warp; blk < (T >> 8); blk += kWarps) {
+            const int base = blk << 8;
+            RV top[J];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) x[e] = RV::load(vals + (8 * u + e) * R);
-        RV a[4];
+            for (int j = 0; j < J; ++j) {
+                const int c = j * 32 + lane;       // chunk inside the block
+                const int s0 = base + c * E;       // its first leaf slot
+                RV y;
+                if constexpr (E == 1) {
+                    y = RV::load(vals + s0 * R);
+                } else if constexpr (E == 2) {
+                    const RV x0 = RV::load(vals + s0 * R), x1 = RV::load(vals + (s0 + 1) * R);
+                    y = RV::template combine<OP>(x0, x1);
+                    y.store(vals + level_slot(1, s0 >> 1) * R);
+                } else {
+                    const RV x0 = RV::load(vals + s0 * R), x1 = RV::load(vals + (s0 + 1) * R);
+                    const RV x2 = RV::load(vals + (s0 + 2) * R), x3 = RV::load(vals + (s0 + 3) * R);
+                    const RV a0 = RV::template combine<OP>(x0, x1), a1 = RV::template combine<OP>(x2, x3);
+                    a0.store(vals + level_slot(1, s0 >> 1) * R);
+                    a1.store(vals + level_slot(1, (s0 >> 1) + 1) * R);
+                    y = RV::template combine<OP>(a0, a1);
+                    y.store(vals + level_slot(2, s0 >> 2) * R);
+                }
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            a[e] = RV::template combine<OP>(x[2 * e], x[2 * e + 1]);
-            a[e].store(vals + (T + 4 * u + e) * R);
-        }
-        const RV c0 = RV::template combine<OP>(a[0], a[1]), c1 = RV::template combine<OP>(a[2], a[3]);
-        c0.store(vals + (2 * T - (T >> 1) + 2 * u) * R);
-        c1.store(vals + (2 * T - (T >> 1) + 2 * u + 1) * R);
-        RV y = RV::template combine<OP>(c0, c1);
-        y.store(vals + (2 * T - (T >> 2) + u) * R);
+                for (int st = 1; st <= 5; ++st) {
+                    y = RV::template combine<OP>(y, y.shfl_down(1 << (st - 1)));
+                    if ((lane & ((1 << st) - 1)) == 0) y.store(vals + level_slot(LE + st, s0 >> (LE + st)) * R);
+                }
+                top[j] = y;  // lane 0: the level LE+5 block j of this 256-leaf block
+            }
+            if (lane == 0) {
 #pragma unroll
-        for (int j = 1; j <= 5; ++j) {
-            y = RV::template combine<OP>(y, y.shfl_down(1 << (j - 1)));
-            if ((lane & ((1 << j) - 1)) == 0) y.store(vals + (2 * T - (T >> (2 + j)) + (u >> j)) * R);
+                for (int w = J, k = LE + 6; w > 1; w >>= 1, ++k) {
+#pragma unroll
+                    for (int j = 0; j < w / 2; ++j) {
+                        top[j] = RV::template combine<OP>(top[2 * j], top[2 * j + 1]);
+                        top[j].store(vals + level_slot(k, (base >> k) + j) * R);
+                    }
+                }
+            }
         }
     }
     __syncthreads();
@@ -421,64 +447,31 @@ __global__ void __launch_bounds__(kThreads, 2) tile_kernel(PlanView P, const VT*
             if (r < nrows) part[(size_t)(b0 + r) * P.n_pieces + idx] = x.v[r];
     }
 
-    // 5. emit the tile's node-id interval, coalesced.  Spanning nodes inside the interval carry the identity
-    //    slot: what is written for them here is overwritten by the reduction of their pieces.
+    // 5. emit the tile's node-id interval: lane = consecutive node id, so the slot reads of a warp cluster on a few
+    //    neighbouring slots (unary chains broadcast) and every store instruction writes one full 128-byte line per
+    //    row.  Spanning nodes inside the interval carry the identity slot: what is written for them here is
+    //    overwritten by span_kernel.
     {
         VT* orow[R];
 #pragma unroll
         for (int r = 0; r < R; ++r) orow[r] = out + (size_t)min(b0 + r, n_rows - 1) * ld_out;
-        if constexpr (VEC) {
-            // rows are 16-byte aligned and ld_out % 4 == 0: one 128-bit store per 4 consecutive node ids
-            const int q0 = (n0 + 3) >> 2, q1 = n1 >> 2;  // interior quads
-            const uint2* slot4 = reinterpret_cast<const uint2*>(P.node_slot);
-            constexpr int U = 2;
-            for (int qb = q0 + tid; qb < q1; qb += U * kThreads) {
-                uint2 sl[U];
+        constexpr int U = 4;
+        for (int nb = n0 + tid; nb < n1; nb += U * kThreads) {
+            int sl[U];
 #pragma unroll
-                for (int u = 0; u < U; ++u) sl[u] = __ldg(slot4 + min(qb + u * kThreads, q1 - 1));
+            for (int u = 0; u < U; ++u) sl[u] = __ldg(P.node_slot + min(nb + u * kThreads, n1 - 1));
 #pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    const int q = qb + u * kThreads;
-                    if (q < q1) {
-                        const RV x0 = RV::load(vals + (sl[u].x & 0xFFFFu) * R), x1 = RV::load(vals + (sl[u].x >> 16) * R);
-                        const RV x2 = RV::load(vals + (sl[u].y & 0xFFFFu) * R), x3 = RV::load(vals + (sl[u].y >> 16) * R);
-#pragma unroll
-                        for (int r = 0; r < R; ++r)
-                            if (r < nrows) store4_stream<VT>(orow[r] + 4 * q, x0.v[r], x1.v[r], x2.v[r], x3.v[r]);
-                    }
-                }
-            }
-            // the (at most 6) nodes of the interval outside the interior quads
-            if (tid < 8) {
-                const int n = tid < 4 ? n0 + tid : (q1 << 2) + (tid - 4);
-                const bool head = tid < 4 && n < min(q0 << 2, n1), tail = tid >= 4 && n >= max(q0 << 2, n0) && n < n1 && q1 >= q0;
-                if (head || tail) {
-                    const RV x = RV::load(vals + (int)__ldg(P.node_slot + n) * R);
+            for (int u = 0; u < U; ++u) {
+                const int n = nb + u * kThreads;
+                if (n < n1) {
+                    const RV x = RV::load(vals + sl[u] * R);
 #pragma unroll
                     for (int r = 0; r < R; ++r)
-                        if (r < nrows) orow[r][n] = x.v[r];
-                }
-            }
-        } else {
-            constexpr int U = 4;
-            for (int nb = n0 + tid; nb < n1; nb += U * kThreads) {
-                int sl[U];
-#pragma unroll
-                for (int u = 0; u < U; ++u) sl[u] = __ldg(P.node_slot + min(nb + u * kThreads, n1 - 1));
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    const int n = nb + u * kThreads;
-                    if (n < n1) {
-                        const RV x = RV::load(vals + sl[u] * R);
-#pragma unroll
-                        for (int r = 0; r < R; ++r)
-                            if (r < nrows) __stcs(orow[r] + n, x.v[r]);
-                    }
+                        if (r < nrows) __stcs(orow[r] + n, x.v[r]);
                 }
             }
         }
     }
-
 }
 
 // ---- phase 3: nodes whose leaf range crosses tiles, reduced from their per-tile pieces (fp64 for sums) ------------
@@ -628,14 +621,8 @@ static int launch_tile(const PlanView& v, const Scratch<VT>& sc, VT* out, int64_
     }
     const size_t smem = tile_smem<VT, R>(v);
     dim3 grid((unsigned)v.NT, (unsigned)((rows + R - 1) / R));
-    const bool vec = (ld_out % 4 == 0) && (reinterpret_cast<uintptr_t>(out) % (4 * sizeof(VT)) == 0);
-    if (vec) {
-        GT_CUDA(allow_smem(tile_kernel<VT, R, OP, true>, smem));
-        tile_kernel<VT, R, OP, true><<<grid, kThreads, smem, st>>>(v, sc.z, out, ld_out, sc.part, rows);
-    } else {
-        GT_CUDA(allow_smem(tile_kernel<VT, R, OP, false>, smem));
-        tile_kernel<VT, R, OP, false><<<grid, kThreads, smem, st>>>(v, sc.z, out, ld_out, sc.part, rows);
-    }
+    GT_CUDA(allow_smem(tile_kernel<VT, R, OP>, smem));
+    tile_kernel<VT, R, OP><<<grid, kThreads, smem, st>>>(v, sc.z, out, ld_out, sc.part, rows);
     GT_CUDA(cudaGetLastError());
     if (v.n_span > 0) {
         dim3 sgrid((unsigned)((v.n_span + 255) / 256), (unsigned)std::min(rows, 4096));

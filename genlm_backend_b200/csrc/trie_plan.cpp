@@ -55,12 +55,38 @@ int build_plan(const Layout& L, int32_t T, int32_t Q, Plan& P) {
     P.p2_slot.assign((size_t)z, 0xFFFF);
     std::vector<uint16_t> z_src((size_t)z, 0xFFFF);  // position inside the source segment
     {
-        std::vector<int64_t> fill(run_off.begin(), run_off.end() - 1);
-        for (int64_t r = 0; r < V; ++r) {  // ascending DFS rank inside each run
+        // Order inside a run is free (both kernels follow these tables).  The tile kernel scatters element
+        // 4*g + e of a run with lane g (for e = 0..3), 16 lanes per shared-memory wavefront, so we give group g
+        // elements whose slot is congruent to g mod 16: the 16 lanes of a wavefront then hit 16 different bank
+        // groups (8-byte slots).  Leftovers (classes are only roughly balanced) fill the remaining places.
+        std::vector<std::vector<std::pair<uint16_t, uint16_t>>> runs((size_t)NT * NS);  // (slot, src)
+        for (int64_t r = 0; r < V; ++r) {
             const int32_t t = (int32_t)(r / T), pos = L.perm[(size_t)r], s = pos / Q;
-            const int64_t at = fill[(size_t)t * NS + s]++;
-            P.p2_slot[(size_t)at] = (uint16_t)(r - (int64_t)t * T);
-            z_src[(size_t)at] = (uint16_t)(pos - s * Q);
+            runs[(size_t)t * NS + s].push_back({(uint16_t)(r - (int64_t)t * T), (uint16_t)(pos - s * Q)});
+        }
+        for (size_t ri = 0; ri < runs.size(); ++ri) {
+            auto& run = runs[ri];
+            const size_t n = run.size();
+            std::vector<std::vector<std::pair<uint16_t, uint16_t>>> cls(16);
+            for (auto& e : run) cls[e.first & 15].push_back(e);
+            std::vector<std::pair<uint16_t, uint16_t>> placed(n);
+            std::vector<uint8_t> used(n, 0);
+            std::vector<size_t> next(16, 0);
+            for (size_t pos = 0; pos < n; ++pos) {
+                const size_t want = (pos / 4) & 15;
+                if (next[want] < cls[want].size()) { placed[pos] = cls[want][next[want]++]; used[pos] = 1; }
+            }
+            size_t c = 0;
+            for (size_t pos = 0; pos < n; ++pos) {
+                if (used[pos]) continue;
+                while (next[c] >= cls[c].size()) ++c;
+                placed[pos] = cls[c][next[c]++];
+            }
+            const int64_t at = run_off[ri];
+            for (size_t pos = 0; pos < n; ++pos) {
+                P.p2_slot[(size_t)(at + (int64_t)pos)] = placed[pos].first;
+                z_src[(size_t)(at + (int64_t)pos)] = placed[pos].second;
+            }
         }
     }
     // phase-1 records: segment-major
@@ -169,12 +195,29 @@ int build_plan(const Layout& L, int32_t T, int32_t Q, Plan& P) {
             const int32_t k = (int32_t)m[order[j0]].terms.size();
             P.ell_desc.push_back((int32_t)(P.ell_terms.size() / 32));
             P.ell_desc.push_back(k);
-            for (int32_t kk = 0; kk < k; ++kk)
+            // The order in which a range adds its terms is free: per term row pick, lane by lane, a remaining term
+            // whose bank group (8-byte slots, 16 lanes per wavefront) is not taken yet in this half-warp.
+            std::vector<std::vector<uint16_t>> left(32);
+            for (size_t lane = 0; lane < cn; ++lane) left[lane] = m[order[j0 + lane]].terms;
+            for (int32_t kk = 0; kk < k; ++kk) {
+                uint32_t taken[2] = {0, 0};
+                uint16_t row[32];
                 for (size_t lane = 0; lane < 32; ++lane) {
                     uint16_t sl = IDENT;
-                    if (lane < cn && kk < (int32_t)m[order[j0 + lane]].terms.size()) sl = m[order[j0 + lane]].terms[kk];
-                    P.ell_terms.push_back(sl);
+                    auto& rem = left[lane];
+                    if (!rem.empty()) {
+                        size_t pick = 0;
+                        for (size_t q = 0; q < rem.size(); ++q)
+                            if (!(taken[lane >> 4] & (1u << (rem[q] & 15)))) { pick = q; break; }
+                        sl = rem[pick];
+                        rem.erase(rem.begin() + (long)pick);
+                        taken[lane >> 4] |= 1u << (sl & 15);
+                    }
+                    row[lane] = sl;
                 }
+                // lanes whose range is exhausted read the identity slot (a broadcast, no conflict)
+                for (size_t lane = 0; lane < 32; ++lane) P.ell_terms.push_back(row[lane]);
+            }
         }
         P.n_multi += (int64_t)m.size();
         for (auto& e : m) P.n_terms += (int64_t)e.terms.size();
