@@ -40,6 +40,7 @@ struct PlanView {
     const int32_t* tile_node_lo; const uint16_t* node_slot;
     const int32_t* piece_ptr; const uint16_t* piece_slot; const int32_t* piece_idx;
     int32_t n_span, n_pieces; const int32_t* span_node; const int32_t* span_pp;
+    int32_t debug_stop;  // profiling aid (GT_DEBUG_STOP): 0 = normal; k = tile_kernel returns after phase k; 9 = emit only
 };
 
 struct DevicePlan {
@@ -317,13 +318,21 @@ __global__ void __launch_bounds__(kThreads, 2) tile_kernel(PlanView P, const VT*
         for (const char* p = s0 + (size_t)tid * 128; p < s1; p += (size_t)kThreads * 128) prefetch_l1(p);
     }
 
-    // row pointers; rows past the batch are clamped for loads (their results are never stored)
-    const VT* zrow[R];
+    // CTA-uniform base pointers plus 32-bit row offsets.  Rows past the end of the batch alias the last valid row:
+    // they load, compute and store exactly what that row does (same values to the same addresses), which keeps
+    // every loop free of per-row predicates.
+    const VT* zbase = z + (size_t)b0 * P.Zrow + zlo;
+    VT* obase = out + (size_t)b0 * ld_out;
+    VT* pbase = part + (size_t)b0 * P.n_pieces;
+    int zoff[R], ooff[R], poff[R];
 #pragma unroll
-    for (int r = 0; r < R; ++r) zrow[r] = z + (size_t)min(b0 + r, n_rows - 1) * P.Zrow + zlo;
+    for (int r = 0; r < R; ++r) {
+        const int rr = min(r, nrows - 1);
+        zoff[r] = rr * (int)P.Zrow; ooff[r] = rr * (int)ld_out; poff[r] = rr * P.n_pieces;
+    }
 
     // 1. staged tile -> DFS-ordered leaf slots
-    {
+    if (P.debug_stop != 9) {
         const int zn4 = (zhi - zlo) >> 2;
         const uint2* slot4 = reinterpret_cast<const uint2*>(P.p2_slot + zlo);
         constexpr int U = 2;
@@ -335,7 +344,7 @@ __global__ void __launch_bounds__(kThreads, 2) tile_kernel(PlanView P, const VT*
                 const int i = min(ib + u * kThreads, zn4 - 1);  // clamped duplicate instead of a predicate
                 sl[u] = __ldg(slot4 + i);
 #pragma unroll
-                for (int r = 0; r < R; ++r) load4<VT>(zrow[r] + 4 * i, v[u][r][0], v[u][r][1], v[u][r][2], v[u][r][3]);
+                for (int r = 0; r < R; ++r) load4<VT>(zbase + zoff[r] + 4 * i, v[u][r][0], v[u][r][1], v[u][r][2], v[u][r][3]);
             }
 #pragma unroll
             for (int u = 0; u < U; ++u) {
@@ -354,11 +363,12 @@ __global__ void __launch_bounds__(kThreads, 2) tile_kernel(PlanView P, const VT*
         if (tid == 0) RV::template ident<OP>().store(vals + (2 * T - 1) * R);  // identity slot (ELL padding)
     }
     __syncthreads();
+    if (P.debug_stop == 1) return;
 
     // 2. pyramid of aligned blocks: level k block i at slot 2T - (T >> (k-1)) + i.  One warp builds levels 1..8
     //    of a 256-leaf block.  Lane l loads the 16-byte chunks j*32 + l (conflict-free), reduces inside the
     //    chunk, then across lanes by shuffles, then across its J chunks.
-    {
+    if (P.debug_stop != 9) {
         constexpr int E = (16 / (int)(sizeof(VT) * R)) > 0 ? (16 / (int)(sizeof(VT) * R)) : 1;  // slots per chunk
         constexpr int LE = E == 4 ? 2 : (E == 2 ? 1 : 0);
         constexpr int J = 8 / E;  // chunks per lane: J * 32 * E = 256 leaves
@@ -416,59 +426,55 @@ __global__ void __launch_bounds__(kThreads, 2) tile_kernel(PlanView P, const VT*
         }
     }
     __syncthreads();
+    if (P.debug_stop == 2) return;
 
     // 3. ranges that need more than one block: ELL chunks of 32 ranges, one warp per chunk; the chunk's terms
-    //    are fetched 8 rows (8 independent coalesced loads) at a time
-    {
+    //    are fetched 4 rows (4 independent coalesced loads) at a time
+    if (P.debug_stop != 9) {
         int it = 0;
         for (int c = ec0 + warp; c < ec1; c += kWarps, ++it) {
             const int off32 = __shfl_sync(0xffffffffu, my_desc.x, it), k = __shfl_sync(0xffffffffu, my_desc.y, it);
             const uint16_t* tp = P.ell_terms + (size_t)off32 * 32 + lane;
             RV acc = RV::template ident<OP>();
-            for (int kb = 0; kb < k; kb += 4) {  // k >= 2; rows past k are clamped re-reads that are not accumulated
+            for (int kb = 0; kb < k; kb += 4) {  // k is a multiple of 4: the planner pads term rows with the identity slot
                 int sl[4];
 #pragma unroll
-                for (int e = 0; e < 4; ++e) sl[e] = __ldg(tp + min(kb + e, k - 1) * 32);
+                for (int e = 0; e < 4; ++e) sl[e] = __ldg(tp + (kb + e) * 32);
 #pragma unroll
-                for (int e = 0; e < 4; ++e)
-                    if (kb + e < k) acc = RV::template combine<OP>(acc, RV::load(vals + sl[e] * R));
+                for (int e = 0; e < 4; ++e) acc = RV::template combine<OP>(acc, RV::load(vals + sl[e] * R));
             }
             acc.store(vals + (2 * T + (c - ec0) * 32 + lane) * R);
         }
     }
     __syncthreads();
+    if (P.debug_stop == 3) return;
 
     // 4. pieces of spanning nodes that overlap this tile (reduced by span_kernel, which runs next on the stream)
     for (int i = pc0 + tid; i < pc1; i += kThreads) {
         const RV x = RV::load(vals + (int)__ldg(P.piece_slot + i) * R);
         const int idx = __ldg(P.piece_idx + i);
 #pragma unroll
-        for (int r = 0; r < R; ++r)
-            if (r < nrows) part[(size_t)(b0 + r) * P.n_pieces + idx] = x.v[r];
+        for (int r = 0; r < R; ++r) pbase[poff[r] + idx] = x.v[r];
     }
 
     // 5. emit the tile's node-id interval: lane = consecutive node id, so the slot reads of a warp cluster on a few
     //    neighbouring slots (unary chains broadcast) and every store instruction writes one full 128-byte line per
     //    row.  Spanning nodes inside the interval carry the identity slot: what is written for them here is
-    //    overwritten by span_kernel.
+    //    overwritten by span_kernel.  The last iteration clamps to the final node instead of predicating.
     {
-        VT* orow[R];
-#pragma unroll
-        for (int r = 0; r < R; ++r) orow[r] = out + (size_t)min(b0 + r, n_rows - 1) * ld_out;
         constexpr int U = 4;
         for (int nb = n0 + tid; nb < n1; nb += U * kThreads) {
-            int sl[U];
-#pragma unroll
-            for (int u = 0; u < U; ++u) sl[u] = __ldg(P.node_slot + min(nb + u * kThreads, n1 - 1));
+            int n[U], sl[U];
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                const int n = nb + u * kThreads;
-                if (n < n1) {
-                    const RV x = RV::load(vals + sl[u] * R);
+                n[u] = min(nb + u * kThreads, n1 - 1);
+                sl[u] = __ldg(P.node_slot + n[u]);
+            }
 #pragma unroll
-                    for (int r = 0; r < R; ++r)
-                        if (r < nrows) __stcs(orow[r] + n, x.v[r]);
-                }
+            for (int u = 0; u < U; ++u) {
+                const RV x = RV::load(vals + sl[u] * R);
+#pragma unroll
+                for (int r = 0; r < R; ++r) __stcs(obase + (ooff[r] + n[u]), x.v[r]);
             }
         }
     }
@@ -556,6 +562,7 @@ static DevicePlan* upload_plan(const Layout& L, const Plan& P, int device) {
     v.piece_idx = (const int32_t*)(base + o_piece_idx);
     v.n_span = (int32_t)P.span_node.size(); v.n_pieces = P.n_pieces;
     v.span_node = (const int32_t*)(base + o_span_node); v.span_pp = (const int32_t*)(base + o_span_pp);
+    { const char* e = getenv("GT_DEBUG_STOP"); v.debug_stop = e && *e ? atoi(e) : 0; }
     return d;
 }
 
@@ -734,6 +741,10 @@ int gt_weight_reduce(const gt_trie* t, const void* ws, int in_type, int64_t n_ro
     if (n_rows == 0) return GT_OK;
     if ((t->layout.V > 0 && !ws) || ((ops & GT_OP_SUM) && !out_sum) || ((ops & GT_OP_MAX) && !out_max)) {
         gt::set_error("gt_weight_reduce: null data pointer"); return GT_ERR_ARG;
+    }
+    if (ld_out > ((int64_t)1 << 28)) {  // the kernels index a row group with 32-bit offsets
+        gt::set_error("gt_weight_reduce: output row stride %lld exceeds 2^28 elements", (long long)ld_out);
+        return GT_ERR_LIMIT;
     }
     if (ld_ws < t->layout.V || ld_out < t->layout.N) {
         gt::set_error("gt_weight_reduce: row stride smaller than row length (ld_ws=%lld V=%lld ld_out=%lld N=%lld)",

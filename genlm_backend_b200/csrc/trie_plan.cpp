@@ -192,7 +192,8 @@ int build_plan(const Layout& L, int32_t T, int32_t Q, Plan& P) {
         P.ell_chunk_ptr[t] = (int32_t)(P.ell_desc.size() / 2);
         for (size_t j0 = 0; j0 < order.size(); j0 += 32) {
             const size_t cn = std::min<size_t>(32, order.size() - j0);
-            const int32_t k = (int32_t)m[order[j0]].terms.size();
+            const int32_t k_real = (int32_t)m[order[j0]].terms.size();
+            const int32_t k = (k_real + 3) & ~3;  // whole batches of 4 term rows; the padding reads the identity slot
             P.ell_desc.push_back((int32_t)(P.ell_terms.size() / 32));
             P.ell_desc.push_back(k);
             // The order in which a range adds its terms is free: per term row pick, lane by lane, a remaining term
