@@ -32,8 +32,23 @@ struct Layout {
 // Source segments: vocabulary positions [s*Q, (s+1)*Q).   Tiles: DFS leaf ranks [t*T, (t+1)*T).
 // Staging buffer z (one row = Zrow floats, tile-major): tile t occupies [z_tile_off[t], z_tile_off[t+1]),
 // inside it one run per source segment (padded to 4 elements).
+// Shared-memory slot swizzle.  Slots below 2T (leaves + pyramid) are stored at swizzle_slot(s): the 16-byte
+// chunk index c is XORed with (c >> 3) & (slot_bytes/2 - 1), a bijection inside every aligned group of 8 chunks.
+// It makes "lane u touches slots 8u .. 8u+7" (the in-lane pyramid levels) and its strided level stores
+// bank-conflict free.  All slot numbers in the plan tables are already swizzled; only code that computes a
+// slot arithmetically applies it.
+inline int32_t swizzle_slot(int32_t s, int32_t slot_bytes) {
+    const int cs = slot_bytes == 4 ? 2 : (slot_bytes == 8 ? 1 : 0);  // log2(slots per 16-byte chunk)
+    const int32_t c = s >> cs;
+    const int32_t c2 = c ^ ((c >> 3) & (slot_bytes / 2 - 1));
+    return (c2 << cs) | (s & ((1 << cs) - 1));
+}
+
 struct Plan {
     int32_t T = 0, Q = 0, NT = 0, NS = 0;
+    int32_t R = 0;           // rows per CTA of the fp32 pipeline (the fp64 pipeline uses R/2: same slot size)
+    int32_t slot_bytes = 0;  // 4 * R
+    int32_t max_tile_nodes = 0, max_tile_ell_rows = 0;  // sizes of the shared-memory metadata stages
     int64_t Zrow = 0;  // floats per staged row (multiple of 4)
 
     // phase 1 (permute): per segment s, records of 4 staged elements.
@@ -56,6 +71,7 @@ struct Plan {
     std::vector<int32_t> ell_chunk_ptr;  // [NT+1]
     std::vector<int32_t> ell_desc;       // [2 * n_chunks]  (off32, k)
     std::vector<uint16_t> ell_terms;
+    std::vector<int32_t> ell_row_ptr;    // [NT+1]  first term row (of 32 slots) of each tile
     int32_t max_levels = 0, max_tile_values = 0;
     int64_t n_multi = 0, n_terms = 0;
 
@@ -90,5 +106,5 @@ struct gt_trie {
 
 namespace gt {
 // trie_plan.cpp
-int build_plan(const Layout& L, int32_t T, int32_t Q, Plan& P);
+int build_plan(const Layout& L, int32_t T, int32_t Q, int32_t R, Plan& P);
 }

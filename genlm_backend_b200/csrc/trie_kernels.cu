@@ -32,11 +32,12 @@
 namespace gt {
 
 struct PlanView {
-    int32_t T, logT, Q, NT, NS, SV;  // SV = per-row value-array length in shared memory
+    int32_t T, logT, Q, NT, NS, SV;  // SV = value slots per tile in shared memory
+    int32_t R, max_tile_nodes, max_tile_ell_rows;
     int64_t V, N, Zrow;
     const int32_t* p1_chunk_ptr; const int4* p1_rec;
     const int32_t* z_tile_off; const uint16_t* p2_slot;
-    const int32_t* ell_chunk_ptr; const int2* ell_desc; const uint16_t* ell_terms;
+    const int32_t* ell_chunk_ptr; const int2* ell_desc; const uint16_t* ell_terms; const int32_t* ell_row_ptr;
     const int32_t* tile_node_lo; const uint16_t* node_slot;
     const int32_t* piece_ptr; const uint16_t* piece_slot; const int32_t* piece_idx;
     int32_t n_span, n_pieces; const int32_t* span_node; const int32_t* span_pp;
@@ -232,15 +233,18 @@ __global__ void __launch_bounds__(kThreads) permute_kernel(PlanView P, const IN_
 
 // ---- phase 2: per-tile pyramid, multi-term ranges, emit, spanning pieces -------------------------------------
 
-__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
-// first / one-past-last ELL term row (in units of 32 terms) of a tile's chunk range
-__device__ __forceinline__ int my_first_off(const PlanView& P, int ec0, int ec1) {
-    return ec1 > ec0 ? __ldg(P.ell_desc + ec0).x : 0;
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
 }
-__device__ __forceinline__ int my_last_off(const PlanView& P, int ec0, int ec1) {
-    if (ec1 <= ec0) return 0;
-    const int2 d = __ldg(P.ell_desc + ec1 - 1);
-    return d.x + d.y;
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// Device twin of gt::swizzle_slot (trie_internal.h) for slots below 2T; B = bytes per slot.
+template <int B> __device__ __forceinline__ int swz(int s) {
+    constexpr int cs = B == 4 ? 2 : (B == 8 ? 1 : 0);
+    const int c = s >> cs;
+    return ((c ^ ((c >> 3) & (B / 2 - 1))) << cs) | (s & ((1 << cs) - 1));
 }
 
 // R consecutive rows share a CTA and live interleaved in shared memory: vals[slot * R + r].  One vector
@@ -289,33 +293,43 @@ template <typename VT, int R, int OP>
 __global__ void __launch_bounds__(kThreads, 2) tile_kernel(PlanView P, const VT* __restrict__ z, VT* __restrict__ out,
                                                            int64_t ld_out, VT* __restrict__ part, int n_rows) {
     using RV = RowVec<VT, R>;
+    constexpr int B = (int)sizeof(VT) * R;  // bytes per slot
+    static_assert(B == 4 || B == 8 || B == 16, "slot must be 4, 8 or 16 bytes");
+    constexpr int SPC = 16 / B;             // slots per 16-byte chunk
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    VT* vals = reinterpret_cast<VT*>(smem_raw);  // [SV + 1][R]; slot SV is the trash slot for padding elements
+    VT* vals = reinterpret_cast<VT*>(smem_raw);  // [SV + 4][R]; slot SV is the trash slot for staged padding
+    uint16_t* s_slots = reinterpret_cast<uint16_t*>(smem_raw + (size_t)(P.SV + 4) * B);  // emit slots of the tile
+    uint16_t* s_terms = s_slots + P.max_tile_nodes;                                      // ELL term rows of the tile
     const int T = P.T;
     const int t = blockIdx.x;
     const int b0 = blockIdx.y * R;
     const int nrows = min(R, n_rows - b0);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int kWarps = kThreads / 32;
+    auto slot_ptr = [&](int s) { return vals + swz<B>(s) * R; };               // s < 2T, computed arithmetically
+    auto level_slot = [&](int k, int i) { return 2 * T - (T >> (k - 1)) + i; };  // level k >= 1, block i
 
-    // per-tile scalars, fetched once up front (each is an L2 round trip if loaded where it is first needed)
+    // per-tile scalars, fetched once up front
     const int zlo = __ldg(P.z_tile_off + t), zhi = __ldg(P.z_tile_off + t + 1);
     const int ec0 = __ldg(P.ell_chunk_ptr + t), ec1 = __ldg(P.ell_chunk_ptr + t + 1);
+    const int er0 = __ldg(P.ell_row_ptr + t), er1 = __ldg(P.ell_row_ptr + t + 1);
     const int n0 = __ldg(P.tile_node_lo + t), n1 = __ldg(P.tile_node_lo + t + 1);
     const int pc0 = __ldg(P.piece_ptr + t), pc1 = __ldg(P.piece_ptr + t + 1);
+    const int na = n0 & ~7;  // emit slots are staged from the 16-byte aligned start at or below n0
     // ELL descriptors of the chunks this warp will process: lane i holds the i-th one (<= 32 per warp)
     int2 my_desc = make_int2(0, 0);
     if (ec0 + warp + kWarps * lane < ec1) my_desc = __ldg(P.ell_desc + ec0 + warp + kWarps * lane);
 
-    // the ELL term rows and the emit slots are read once, late in the kernel: start pulling their lines into L1
-    // now so those phases do not pay an L2 round trip per batch
+    // The ELL term rows and the emit slots are needed late: copy them into shared memory asynchronously now
+    // (cp.async, no registers), so phases 3 and 5 never wait on L2.
     {
-        const char* e0 = reinterpret_cast<const char*>(P.ell_terms + (size_t)my_first_off(P, ec0, ec1) * 32);
-        const char* e1 = reinterpret_cast<const char*>(P.ell_terms + (size_t)my_last_off(P, ec0, ec1) * 32);
-        for (const char* p = e0 + (size_t)tid * 128; p < e1; p += (size_t)kThreads * 128) prefetch_l1(p);
-        const char* s0 = reinterpret_cast<const char*>(P.node_slot + n0);
-        const char* s1 = reinterpret_cast<const char*>(P.node_slot + n1);
-        for (const char* p = s0 + (size_t)tid * 128; p < s1; p += (size_t)kThreads * 128) prefetch_l1(p);
+        const uint4* src = reinterpret_cast<const uint4*>(P.node_slot + na);
+        const int nch = (n1 - na + 7) >> 3;
+        for (int i = tid; i < nch; i += kThreads) cp_async16(s_slots + 8 * i, src + i);
+        const uint4* tsrc = reinterpret_cast<const uint4*>(P.ell_terms + (size_t)er0 * 32);
+        const int tch = (er1 - er0) * 4;
+        for (int i = tid; i < tch; i += kThreads) cp_async16(s_terms + 8 * i, tsrc + i);
+        cp_async_commit();
     }
 
     // CTA-uniform base pointers plus 32-bit row offsets.  Rows past the end of the batch alias the last valid row:
@@ -331,11 +345,11 @@ __global__ void __launch_bounds__(kThreads, 2) tile_kernel(PlanView P, const VT*
         zoff[r] = rr * (int)P.Zrow; ooff[r] = rr * (int)ld_out; poff[r] = rr * P.n_pieces;
     }
 
-    // 1. staged tile -> DFS-ordered leaf slots
+    // 1. staged tile -> DFS-ordered leaf slots (slot numbers in p2_slot are already swizzled)
     if (P.debug_stop != 9) {
         const int zn4 = (zhi - zlo) >> 2;
         const uint2* slot4 = reinterpret_cast<const uint2*>(P.p2_slot + zlo);
-        constexpr int U = 2;
+        constexpr int U = R >= 4 ? 1 : 2;
         for (int ib = tid; ib < zn4; ib += U * kThreads) {
             uint2 sl[U];
             VT v[U][R][4];
@@ -359,87 +373,70 @@ __global__ void __launch_bounds__(kThreads, 2) tile_kernel(PlanView P, const VT*
             }
         }
         const int nleaf = (int)min((int64_t)T, P.V - (int64_t)t * T);
-        for (int i = nleaf + tid; i < T; i += kThreads) RV::template ident<OP>().store(vals + i * R);
-        if (tid == 0) RV::template ident<OP>().store(vals + (2 * T - 1) * R);  // identity slot (ELL padding)
+        for (int i = nleaf + tid; i < T; i += kThreads) RV::template ident<OP>().store(slot_ptr(i));
+        if (tid == 0) RV::template ident<OP>().store(slot_ptr(2 * T - 1));  // identity slot (ELL padding, spanning nodes)
     }
     __syncthreads();
     if (P.debug_stop == 1) return;
 
-    // 2. pyramid of aligned blocks: level k block i at slot 2T - (T >> (k-1)) + i.  One warp builds levels 1..8
-    //    of a 256-leaf block.  Lane l loads the 16-byte chunks j*32 + l (conflict-free), reduces inside the
-    //    chunk, then across lanes by shuffles, then across its J chunks.
+    // 2. pyramid of aligned blocks: level k block i at (swizzled) slot 2T - (T >> (k-1)) + i.
+    //    Lane u owns leaves 8u .. 8u+7: levels 1..3 in registers, 4..8 by warp shuffles (256 leaves per warp).
+    //    The swizzle makes the 16-byte chunk loads and the strided level stores bank-conflict free.
     if (P.debug_stop != 9) {
-        constexpr int E = (16 / (int)(sizeof(VT) * R)) > 0 ? (16 / (int)(sizeof(VT) * R)) : 1;  // slots per chunk
-        constexpr int LE = E == 4 ? 2 : (E == 2 ? 1 : 0);
-        constexpr int J = 8 / E;  // chunks per lane: J * 32 * E = 256 leaves
-        auto level_slot = [&](int k, int i) { return 2 * T - (T >> (k - 1)) + i; };
-        for (int blk = warp; blk < (T >> 8); blk += kWarps) {
-            const int base = blk << 8;
-            RV top[J];
+        for (int ub = warp * 32; ub < (T >> 3); ub += kWarps * 32) {
+            const int u = ub + lane;
+            RV x[8];
 #pragma unroll
-            for (int j = 0; j < J; ++j) {
-                const int c = j * 32 + lane;       // chunk inside the block
-                const int s0 = base + c * E;       // its first leaf slot
-                RV y;
-                if constexpr (E == 1) {
-                    y = RV::load(vals + s0 * R);
-                } else if constexpr (E == 2) {
-                    const RV x0 = RV::load(vals + s0 * R), x1 = RV::load(vals + (s0 + 1) * R);
-                    y = RV::template combine<OP>(x0, x1);
-                    y.store(vals + level_slot(1, s0 >> 1) * R);
-                } else {
-                    const RV x0 = RV::load(vals + s0 * R), x1 = RV::load(vals + (s0 + 1) * R);
-                    const RV x2 = RV::load(vals + (s0 + 2) * R), x3 = RV::load(vals + (s0 + 3) * R);
-                    const RV a0 = RV::template combine<OP>(x0, x1), a1 = RV::template combine<OP>(x2, x3);
-                    a0.store(vals + level_slot(1, s0 >> 1) * R);
-                    a1.store(vals + level_slot(1, (s0 >> 1) + 1) * R);
-                    y = RV::template combine<OP>(a0, a1);
-                    y.store(vals + level_slot(2, s0 >> 2) * R);
-                }
-#pragma unroll
-                for (int st = 1; st <= 5; ++st) {
-                    y = RV::template combine<OP>(y, y.shfl_down(1 << (st - 1)));
-                    if ((lane & ((1 << st) - 1)) == 0) y.store(vals + level_slot(LE + st, s0 >> (LE + st)) * R);
-                }
-                top[j] = y;  // lane 0: the level LE+5 block j of this 256-leaf block
+            for (int ch = 0; ch < 8 / SPC; ++ch) {
+                const int c = (8 * u) / SPC + ch;
+                const int cc = c ^ ((c >> 3) & (B / 2 - 1));
+                const float4 raw = *reinterpret_cast<const float4*>(reinterpret_cast<const unsigned char*>(vals) + (size_t)cc * 16);
+                memcpy(&x[ch * SPC], &raw, 16);
             }
-            if (lane == 0) {
+            RV a[4];
 #pragma unroll
-                for (int w = J, k = LE + 6; w > 1; w >>= 1, ++k) {
+            for (int e = 0; e < 4; ++e) {
+                a[e] = RV::template combine<OP>(x[2 * e], x[2 * e + 1]);
+                a[e].store(slot_ptr(level_slot(1, 4 * u + e)));
+            }
+            const RV c0 = RV::template combine<OP>(a[0], a[1]), c1 = RV::template combine<OP>(a[2], a[3]);
+            c0.store(slot_ptr(level_slot(2, 2 * u)));
+            c1.store(slot_ptr(level_slot(2, 2 * u + 1)));
+            RV y = RV::template combine<OP>(c0, c1);
+            y.store(slot_ptr(level_slot(3, u)));
 #pragma unroll
-                    for (int j = 0; j < w / 2; ++j) {
-                        top[j] = RV::template combine<OP>(top[2 * j], top[2 * j + 1]);
-                        top[j].store(vals + level_slot(k, (base >> k) + j) * R);
-                    }
-                }
+            for (int j = 1; j <= 5; ++j) {
+                y = RV::template combine<OP>(y, y.shfl_down(1 << (j - 1)));
+                if ((lane & ((1 << j) - 1)) == 0) y.store(slot_ptr(level_slot(3 + j, u >> j)));
             }
         }
     }
     __syncthreads();
     //    Levels 9..logT: T/256 <= 32 level-8 blocks, one warp.
-    if (warp == 0 && P.logT > 8) {
+    if (warp == 0 && P.logT > 8 && P.debug_stop != 9) {
         const int n8 = T >> 8;
-        RV y = lane < n8 ? RV::load(vals + (2 * T - (T >> 7) + lane) * R) : RV::template ident<OP>();
+        RV y = lane < n8 ? RV::load(slot_ptr(level_slot(8, lane))) : RV::template ident<OP>();
         for (int j = 1; j <= P.logT - 8; ++j) {
             y = RV::template combine<OP>(y, y.shfl_down(1 << (j - 1)));
-            if ((lane & ((1 << j) - 1)) == 0 && lane < n8) y.store(vals + (2 * T - (T >> (7 + j)) + (lane >> j)) * R);
+            if ((lane & ((1 << j) - 1)) == 0 && lane < n8) y.store(slot_ptr(level_slot(8 + j, lane >> j)));
         }
     }
+    cp_async_wait_all();  // this thread's share of the staged metadata has landed; the barrier publishes all of it
     __syncthreads();
     if (P.debug_stop == 2) return;
 
-    // 3. ranges that need more than one block: ELL chunks of 32 ranges, one warp per chunk; the chunk's terms
-    //    are fetched 4 rows (4 independent coalesced loads) at a time
+    // 3. ranges that need more than one block: ELL chunks of 32 ranges, one warp per chunk, term rows read from
+    //    shared memory (k is a multiple of 4: the planner pads rows with the identity slot)
     if (P.debug_stop != 9) {
         int it = 0;
         for (int c = ec0 + warp; c < ec1; c += kWarps, ++it) {
             const int off32 = __shfl_sync(0xffffffffu, my_desc.x, it), k = __shfl_sync(0xffffffffu, my_desc.y, it);
-            const uint16_t* tp = P.ell_terms + (size_t)off32 * 32 + lane;
+            const uint16_t* tp = s_terms + (off32 - er0) * 32 + lane;
             RV acc = RV::template ident<OP>();
-            for (int kb = 0; kb < k; kb += 4) {  // k is a multiple of 4: the planner pads term rows with the identity slot
+            for (int kb = 0; kb < k; kb += 4) {
                 int sl[4];
 #pragma unroll
-                for (int e = 0; e < 4; ++e) sl[e] = __ldg(tp + (kb + e) * 32);
+                for (int e = 0; e < 4; ++e) sl[e] = tp[(kb + e) * 32];
 #pragma unroll
                 for (int e = 0; e < 4; ++e) acc = RV::template combine<OP>(acc, RV::load(vals + sl[e] * R));
             }
@@ -463,18 +460,14 @@ __global__ void __launch_bounds__(kThreads, 2) tile_kernel(PlanView P, const VT*
     //    overwritten by span_kernel.  The last iteration clamps to the final node instead of predicating.
     {
         constexpr int U = 4;
+        const uint16_t* sl_base = s_slots - na;
         for (int nb = n0 + tid; nb < n1; nb += U * kThreads) {
-            int n[U], sl[U];
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                n[u] = min(nb + u * kThreads, n1 - 1);
-                sl[u] = __ldg(P.node_slot + n[u]);
-            }
+                const int n = min(nb + u * kThreads, n1 - 1);
+                const RV x = RV::load(vals + (int)sl_base[n] * R);
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const RV x = RV::load(vals + sl[u] * R);
-#pragma unroll
-                for (int r = 0; r < R; ++r) __stcs(obase + (ooff[r] + n[u]), x.v[r]);
+                for (int r = 0; r < R; ++r) __stcs(obase + (ooff[r] + n), x.v[r]);
             }
         }
     }
@@ -515,6 +508,7 @@ static DevicePlan* upload_plan(const Layout& L, const Plan& P, int device) {
     const size_t o_p1_chunk_ptr = ADDV(P.p1_chunk_ptr), o_p1_rec = ADDV(P.p1_rec);
     const size_t o_z_tile_off = ADDV(P.z_tile_off), o_p2_slot = ADDV(P.p2_slot);
     const size_t o_ell_chunk_ptr = ADDV(P.ell_chunk_ptr), o_ell_desc = ADDV(P.ell_desc), o_ell_terms = ADDV(P.ell_terms);
+    const size_t o_ell_row_ptr = ADDV(P.ell_row_ptr);
     const size_t o_tile_node_lo = ADDV(P.tile_node_lo), o_node_slot = ADDV(P.node_slot);
     const size_t o_piece_ptr = ADDV(P.piece_ptr), o_piece_slot = ADDV(P.piece_slot), o_piece_idx = ADDV(P.piece_idx);
     const size_t o_span_node = ADDV(P.span_node), o_span_pp = ADDV(P.span_pp);
@@ -556,7 +550,8 @@ static DevicePlan* upload_plan(const Layout& L, const Plan& P, int device) {
     v.p1_chunk_ptr = (const int32_t*)(base + o_p1_chunk_ptr); v.p1_rec = (const int4*)(base + o_p1_rec);
     v.z_tile_off = (const int32_t*)(base + o_z_tile_off); v.p2_slot = (const uint16_t*)(base + o_p2_slot);
     v.ell_chunk_ptr = (const int32_t*)(base + o_ell_chunk_ptr); v.ell_desc = (const int2*)(base + o_ell_desc);
-    v.ell_terms = (const uint16_t*)(base + o_ell_terms);
+    v.ell_terms = (const uint16_t*)(base + o_ell_terms); v.ell_row_ptr = (const int32_t*)(base + o_ell_row_ptr);
+    v.R = P.R; v.max_tile_nodes = P.max_tile_nodes; v.max_tile_ell_rows = P.max_tile_ell_rows;
     v.tile_node_lo = (const int32_t*)(base + o_tile_node_lo); v.node_slot = (const uint16_t*)(base + o_node_slot);
     v.piece_ptr = (const int32_t*)(base + o_piece_ptr); v.piece_slot = (const uint16_t*)(base + o_piece_slot);
     v.piece_idx = (const int32_t*)(base + o_piece_idx);
@@ -566,11 +561,11 @@ static DevicePlan* upload_plan(const Layout& L, const Plan& P, int device) {
     return d;
 }
 
-constexpr int R_F32 = 2;  // rows per CTA, float pipeline
-constexpr int R_F64 = 1;  // rows per CTA, double pipeline
 
 template <typename VT, int R> static size_t permute_smem(const PlanView& v) { return (size_t)R * (v.Q + kSegPad) * sizeof(VT); }
-template <typename VT, int R> static size_t tile_smem(const PlanView& v) { return (size_t)R * (v.SV + 4) * sizeof(VT); }
+template <typename VT, int R> static size_t tile_smem(const PlanView& v) {
+    return (size_t)R * (v.SV + 4) * sizeof(VT) + (size_t)v.max_tile_nodes * 2 + (size_t)v.max_tile_ell_rows * 64;
+}
 
 // Opt in to > 48 KB dynamic shared memory once per (kernel, device, size): the attribute call is kept off the
 // steady-state launch path (and out of CUDA graph captures).  Keyed by the kernel's address: instantiations
@@ -665,8 +660,9 @@ static int reduce_typed(const PlanView& v, const void* ws, int in_type, int64_t 
         int rc = GT_OK;
         if (v.NT > 0 && (phases & GT_FLAG_PHASE_PERMUTE)) {
             // rows per CTA in the permute phase: R unless the segment buffer would not fit in shared memory
-            const bool wide = permute_smem<VT, R>(v) <= kMaxSmem;
-#define GT_PERMUTE(IN_T) (wide ? launch_permute<VT, IN_T, R>(v, wsr, ld_ws, sc, rows, log_input, st) \
+            constexpr int RP = sizeof(VT) == 4 ? 2 : 1;  // rows per CTA of the permute kernel
+            const bool wide = permute_smem<VT, RP>(v) <= kMaxSmem;
+#define GT_PERMUTE(IN_T) (wide ? launch_permute<VT, IN_T, RP>(v, wsr, ld_ws, sc, rows, log_input, st) \
                                : launch_permute<VT, IN_T, 1>(v, wsr, ld_ws, sc, rows, log_input, st))
             switch (in_type) {
                 case GT_F32: rc = GT_PERMUTE(float); break;
@@ -698,7 +694,7 @@ int gt_upload(gt_trie* t, int device) {
     if (!t) { gt::set_error("gt_upload: null trie"); return GT_ERR_ARG; }
     if (t->dev.count(device)) return GT_OK;
     if (!t->plan) {
-        const int rc = gt_plan(t, 0, 0);
+        const int rc = gt_plan(t, 0, 0, 0);
         if (rc != GT_OK) return rc;
     }
     gt::DevicePlan* d = gt::upload_plan(t->layout, *t->plan, device);
@@ -714,7 +710,7 @@ int gt_get_plan_info(const gt_trie* t, gt_plan_info* info) {
     memset(info, 0, sizeof *info);
     info->n_tokens = t->layout.V; info->n_nodes = t->layout.N;
     info->tile_leaves = P.T; info->seg_positions = P.Q; info->n_tiles = P.NT; info->n_segs = P.NS;
-    info->rows_per_item = gt::R_F32;
+    info->rows_per_item = P.R;
     info->n_span = (int32_t)P.span_node.size(); info->span_terms = (int64_t)P.n_pieces;
     info->max_levels = P.max_levels; info->max_tile_values = P.max_tile_values;
     info->staged_row_elems = P.Zrow;
@@ -758,12 +754,12 @@ int gt_weight_reduce(const gt_trie* t, const void* ws, int in_type, int64_t n_ro
     const gt::PlanView& v = it->second->view;
     if (!workspace) { gt::set_error("gt_weight_reduce: null workspace"); return GT_ERR_ARG; }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (out_type == GT_F32)
-        return gt::reduce_typed<float, gt::R_F32>(v, ws, in_type, n_rows, ld_ws, out_sum, out_max, ld_out, ops, flags,
-                                                  workspace, workspace_bytes, st);
-    if (out_type == GT_F64)
-        return gt::reduce_typed<double, gt::R_F64>(v, ws, in_type, n_rows, ld_ws, out_sum, out_max, ld_out, ops, flags,
-                                                   workspace, workspace_bytes, st);
+#define GT_REDUCE(VT, R) gt::reduce_typed<VT, R>(v, ws, in_type, n_rows, ld_ws, out_sum, out_max, ld_out, ops, flags, \
+                                                workspace, workspace_bytes, st)
+    // the fp64 pipeline runs half as many rows per CTA, so both pipelines share the plan's slot size
+    if (out_type == GT_F32) return v.R == 4 ? GT_REDUCE(float, 4) : GT_REDUCE(float, 2);
+    if (out_type == GT_F64) return v.R == 4 ? GT_REDUCE(double, 2) : GT_REDUCE(double, 1);
+#undef GT_REDUCE
     gt::set_error("gt_weight_reduce: output type must be GT_F32 or GT_F64");
     return GT_ERR_ARG;
 }

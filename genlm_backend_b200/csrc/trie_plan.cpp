@@ -23,13 +23,17 @@ namespace gt {
 
 static inline int ilog2(int32_t x) { int k = 0; while ((1 << (k + 1)) <= x) ++k; return k; }
 
-int build_plan(const Layout& L, int32_t T, int32_t Q, Plan& P) {
+int build_plan(const Layout& L, int32_t T, int32_t Q, int32_t R, Plan& P) {
     const int64_t V = L.V, N = L.N;
     if (T < 1024 || T > 8192 || (T & (T - 1))) { set_error("tile size must be a power of two in [1024, 8192]"); return GT_ERR_ARG; }
     // Q*8 bytes (one fp64 row segment) must fit in shared memory
     if (Q < 4 || Q > 16384 || (Q & 3)) { set_error("segment size must be a multiple of 4 in [4, 16384]"); return GT_ERR_ARG; }
+    if (R != 2 && R != 4) { set_error("rows per CTA must be 2 or 4"); return GT_ERR_ARG; }
     const int logT = ilog2(T);
-    P.T = T; P.Q = Q;
+    P.T = T; P.Q = Q; P.R = R; P.slot_bytes = 4 * R;
+    const int32_t SB = P.slot_bytes;
+    auto swz = [&](int32_t s) -> uint16_t { return (uint16_t)(s < 2 * T ? swizzle_slot(s, SB) : s); };
+    const int bank_mod = 128 / SB;  // slots per 128-byte shared-memory wavefront
     P.NT = (int32_t)((V + T - 1) / T);
     P.NS = (int32_t)((V + Q - 1) / Q);
     const int32_t NT = P.NT, NS = P.NS;
@@ -67,13 +71,13 @@ int build_plan(const Layout& L, int32_t T, int32_t Q, Plan& P) {
         for (size_t ri = 0; ri < runs.size(); ++ri) {
             auto& run = runs[ri];
             const size_t n = run.size();
-            std::vector<std::vector<std::pair<uint16_t, uint16_t>>> cls(16);
-            for (auto& e : run) cls[e.first & 15].push_back(e);
+            std::vector<std::vector<std::pair<uint16_t, uint16_t>>> cls((size_t)bank_mod);
+            for (auto& e : run) { e.first = swz(e.first); cls[e.first % bank_mod].push_back(e); }
             std::vector<std::pair<uint16_t, uint16_t>> placed(n);
             std::vector<uint8_t> used(n, 0);
-            std::vector<size_t> next(16, 0);
+            std::vector<size_t> next((size_t)bank_mod, 0);
             for (size_t pos = 0; pos < n; ++pos) {
-                const size_t want = (pos / 4) & 15;
+                const size_t want = (pos / 4) % (size_t)bank_mod;
                 if (next[want] < cls[want].size()) { placed[pos] = cls[want][next[want]++]; used[pos] = 1; }
             }
             size_t c = 0;
@@ -118,9 +122,9 @@ int build_plan(const Layout& L, int32_t T, int32_t Q, Plan& P) {
     // ---- value slots ------------------------------------------------------------------------------
     // A leaf range [a,b) inside tile t resolves to a slot: a leaf, one aligned pyramid block, or a
     // multi-term range (deduplicated per tile) whose slot is known after sorting by term count.
-    const uint16_t IDENT = (uint16_t)(2 * T - 1);
+    const uint16_t IDENT = swz(2 * T - 1);
     auto block_slot = [&](int k, int32_t i) -> uint16_t {
-        return (uint16_t)(k == 0 ? i : 2 * T - (T >> (k - 1)) + i);
+        return swz(k == 0 ? i : 2 * T - (T >> (k - 1)) + i);
     };
     struct Multi { std::vector<uint16_t> terms; };
     std::vector<std::vector<Multi>> multi((size_t)NT);
@@ -201,7 +205,8 @@ int build_plan(const Layout& L, int32_t T, int32_t Q, Plan& P) {
             std::vector<std::vector<uint16_t>> left(32);
             for (size_t lane = 0; lane < cn; ++lane) left[lane] = m[order[j0 + lane]].terms;
             for (int32_t kk = 0; kk < k; ++kk) {
-                uint32_t taken[2] = {0, 0};
+                uint32_t taken[4] = {0, 0, 0, 0};
+                const int lanes_per_wf = bank_mod;  // lanes served by one 128-byte wavefront
                 uint16_t row[32];
                 for (size_t lane = 0; lane < 32; ++lane) {
                     uint16_t sl = IDENT;
@@ -209,10 +214,10 @@ int build_plan(const Layout& L, int32_t T, int32_t Q, Plan& P) {
                     if (!rem.empty()) {
                         size_t pick = 0;
                         for (size_t q = 0; q < rem.size(); ++q)
-                            if (!(taken[lane >> 4] & (1u << (rem[q] & 15)))) { pick = q; break; }
+                            if (!(taken[lane / lanes_per_wf] & (1u << (rem[q] % bank_mod)))) { pick = q; break; }
                         sl = rem[pick];
                         rem.erase(rem.begin() + (long)pick);
-                        taken[lane >> 4] |= 1u << (sl & 15);
+                        taken[lane / lanes_per_wf] |= 1u << (sl % bank_mod);
                     }
                     row[lane] = sl;
                 }
@@ -245,6 +250,18 @@ int build_plan(const Layout& L, int32_t T, int32_t Q, Plan& P) {
         }
     }
     P.piece_ptr[NT] = (int32_t)P.piece_slot.size();
+    P.max_tile_nodes = 0; P.max_tile_ell_rows = 0;
+    P.ell_row_ptr.assign((size_t)NT + 1, 0);
+    for (int32_t t = 0; t < NT; ++t) {
+        // the emit stage is copied from the 16-byte aligned start at or below the interval
+        const int32_t a = P.tile_node_lo[t] & ~7;
+        P.max_tile_nodes = std::max(P.max_tile_nodes, ((P.tile_node_lo[t + 1] - a + 7) & ~7));
+        int32_t rows = 0;
+        for (int32_t c = P.ell_chunk_ptr[t]; c < P.ell_chunk_ptr[t + 1]; ++c) rows += P.ell_desc[2 * (size_t)c + 1];
+        P.max_tile_ell_rows = std::max(P.max_tile_ell_rows, rows);
+        P.ell_row_ptr[(size_t)t + 1] = P.ell_row_ptr[(size_t)t] + rows;
+    }
+    if ((int64_t)P.ell_row_ptr[(size_t)NT] * 32 != (int64_t)P.ell_terms.size()) { set_error("internal: ELL row count"); return GT_ERR_STATE; }
     // staged padding elements land in the trash slot one past the value array (same for every tile)
     P.max_tile_values = (P.max_tile_values + 3) & ~3;
     for (auto& sl : P.p2_slot) if (sl == 0xFFFF) sl = (uint16_t)P.max_tile_values;
@@ -255,20 +272,22 @@ int build_plan(const Layout& L, int32_t T, int32_t Q, Plan& P) {
 
 extern "C" {
 
-int gt_plan(gt_trie* t, int32_t tile_leaves, int32_t seg_positions) {
+int gt_plan(gt_trie* t, int32_t tile_leaves, int32_t seg_positions, int32_t rows_per_cta) {
     if (!t) { gt::set_error("gt_plan: null trie"); return GT_ERR_ARG; }
     auto env_int = [](const char* name, int dflt) { const char* s = getenv(name); return s && *s ? atoi(s) : dflt; };
     if (t->plan && tile_leaves <= 0) tile_leaves = t->plan->T;
     if (t->plan && seg_positions <= 0) seg_positions = t->plan->Q;
-    if (tile_leaves <= 0) tile_leaves = env_int("GT_TILE_LEAVES", 4096);
-    if (seg_positions <= 0) seg_positions = env_int("GT_SEG_POSITIONS", 8192);
+    if (t->plan && rows_per_cta <= 0) rows_per_cta = t->plan->R;
+    if (tile_leaves <= 0) tile_leaves = env_int("GT_TILE_LEAVES", 2048);
+    if (seg_positions <= 0) seg_positions = env_int("GT_SEG_POSITIONS", 4096);
+    if (rows_per_cta <= 0) rows_per_cta = env_int("GT_ROWS_PER_CTA", 4);
     if (t->plan) {
-        if (t->plan->T == tile_leaves && t->plan->Q == seg_positions) return GT_OK;
-        gt::set_error("gt_plan: a plan with T=%d Q=%d already exists", t->plan->T, t->plan->Q);
+        if (t->plan->T == tile_leaves && t->plan->Q == seg_positions && t->plan->R == rows_per_cta) return GT_OK;
+        gt::set_error("gt_plan: a plan with T=%d Q=%d R=%d already exists", t->plan->T, t->plan->Q, t->plan->R);
         return GT_ERR_STATE;
     }
     std::unique_ptr<gt::Plan> p(new gt::Plan());
-    const int rc = gt::build_plan(t->layout, tile_leaves, seg_positions, *p);
+    const int rc = gt::build_plan(t->layout, tile_leaves, seg_positions, rows_per_cta, *p);
     if (rc != GT_OK) return rc;
     t->plan = std::move(p);
     return GT_OK;
@@ -280,7 +299,7 @@ int64_t gt_export_plan_array(const gt_trie* t, const char* name, void* dst, int6
     const void* src = nullptr; int64_t n = -1; int32_t es = 4;
 #define GT_ARR(field) if (!strcmp(name, #field)) { src = P.field.data(); n = (int64_t)P.field.size(); es = (int32_t)sizeof(P.field[0]); }
     GT_ARR(p1_chunk_ptr) GT_ARR(p1_rec) GT_ARR(z_tile_off) GT_ARR(p2_slot) GT_ARR(ell_chunk_ptr) GT_ARR(ell_desc)
-    GT_ARR(ell_terms) GT_ARR(tile_node_lo) GT_ARR(node_slot) GT_ARR(piece_ptr) GT_ARR(piece_slot) GT_ARR(piece_idx)
+    GT_ARR(ell_terms) GT_ARR(ell_row_ptr) GT_ARR(tile_node_lo) GT_ARR(node_slot) GT_ARR(piece_ptr) GT_ARR(piece_slot) GT_ARR(piece_idx)
     GT_ARR(span_node) GT_ARR(span_pp)
 #undef GT_ARR
     if (n < 0) { gt::set_error("gt_export_plan_array: unknown array '%s'", name); return -1; }

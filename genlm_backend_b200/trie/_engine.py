@@ -74,8 +74,8 @@ class TrieEngine:
         check(lib.gt_export_reachability(self._handle, rows.ctypes.data, cols.ctypes.data), "gt_export_reachability")
         return rows, cols
 
-    def plan(self, tile_leaves=0, seg_positions=0):
-        check(lib.gt_plan(self._handle, tile_leaves, seg_positions), "gt_plan")
+    def plan(self, tile_leaves=0, seg_positions=0, rows_per_cta=0):
+        check(lib.gt_plan(self._handle, tile_leaves, seg_positions, rows_per_cta), "gt_plan")
 
     def plan_info(self):
         self.plan()

@@ -102,11 +102,12 @@ int gt_get_plan_info(const gt_trie* t, gt_plan_info* info);
 
 /* Host-only: build the tile plan without touching a device (gt_upload calls this with its defaults when
  * no plan exists yet).  tile_leaves: power of two in [1024, 8192]; seg_positions: multiple of 4, <= 16384;
+ * rows_per_cta: 2 or 4 (rows of a batch that share one CTA of the fp32 pipeline; the fp64 pipeline uses half);
  * pass 0 for the defaults.  Fails if a plan already exists with different parameters. */
-int gt_plan(gt_trie* t, int32_t tile_leaves, int32_t seg_positions);
+int gt_plan(gt_trie* t, int32_t tile_leaves, int32_t seg_positions, int32_t rows_per_cta);
 
 /* Host-only introspection of the plan arrays, used by the CPU tests that emulate the kernels' data flow.
- * `name` is one of: p1_chunk_ptr p1_rec z_tile_off p2_slot ell_chunk_ptr ell_desc ell_terms tile_node_lo
+ * `name` is one of: p1_chunk_ptr p1_rec z_tile_off p2_slot ell_chunk_ptr ell_desc ell_terms ell_row_ptr tile_node_lo
  * node_slot piece_ptr piece_slot piece_idx span_node span_pp.  Returns the element count (or -1), and copies
  * min(count, capacity) elements into dst when dst != NULL.  elem_size receives 2 or 4. */
 int64_t gt_export_plan_array(const gt_trie* t, const char* name, void* dst, int64_t capacity, int32_t* elem_size);

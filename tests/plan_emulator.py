@@ -6,6 +6,13 @@ Float32 arithmetic in the same association order as the kernels (pairwise pyrami
 import numpy as np
 
 
+def swizzle_slot(s, slot_bytes):
+    """Python twin of gt::swizzle_slot (csrc/trie_internal.h)."""
+    cs = {4: 2, 8: 1, 16: 0}[slot_bytes]
+    c = s >> cs
+    return ((c ^ ((c >> 3) & (slot_bytes // 2 - 1))) << cs) | (s & ((1 << cs) - 1))
+
+
 def emulate(engine, ws, op="sum"):
     """ws: float32 [B, V].  Returns float32 [B, N] computed the way permute/tile/span kernels do."""
     info = engine.plan_info()
@@ -15,6 +22,7 @@ def emulate(engine, ws, op="sum"):
     T, Q, NT, NS = info["tile_leaves"], info["seg_positions"], info["n_tiles"], info["n_segs"]
     V, N, Zrow = info["n_tokens"], info["n_nodes"], info["staged_row_elems"]
     logT = T.bit_length() - 1
+    phys = swizzle_slot(np.arange(2 * T), 4 * info["rows_per_item"])  # where logical slot s < 2T lives
     ws = np.asarray(ws, dtype=np.float32)
     B = ws.shape[0]
     red = np.add if op == "sum" else np.fmax
@@ -48,20 +56,20 @@ def emulate(engine, ws, op="sum"):
         vals = np.full((B, SV + 1), np.nan, dtype=np.float32)  # slot SV = trash slot for staged padding
         zlo, zhi = A["z_tile_off"][t], A["z_tile_off"][t + 1]
         slot = A["p2_slot"][zlo:zhi]
-        assert slot.max() <= SV and np.array_equal(np.sort(slot[slot < SV]), np.arange((slot < SV).sum()))
-        vals[:, slot] = z[:, zlo:zhi]
         nleaf = min(T, V - t * T)
-        vals[:, nleaf:T] = ident
-        assert not np.isnan(vals[:, :nleaf]).any() or np.isnan(ws).any()
-        # phase 2.2: pyramid, level k block i at 2T - (T >> (k-1)) + i
-        prev = vals[:, :T]
+        assert slot.max() <= SV and np.array_equal(np.sort(slot[slot < SV]), np.sort(phys[:nleaf]))
+        vals[:, slot] = z[:, zlo:zhi]
+        vals[:, phys[nleaf:T]] = ident
+        assert not np.isnan(vals[:, phys[:nleaf]]).any() or np.isnan(ws).any()
+        # phase 2.2: pyramid, level k block i at logical slot 2T - (T >> (k-1)) + i (physical: swizzled)
+        prev = vals[:, phys[:T]]
         for k in range(1, logT + 1):
             cur = red(prev[:, 0::2], prev[:, 1::2]).astype(np.float32)
             off = 2 * T - (T >> (k - 1))
-            vals[:, off:off + cur.shape[1]] = cur
+            vals[:, phys[off:off + cur.shape[1]]] = cur
             prev = cur
         # phase 2.3: multi-term ranges, ELL chunks of 32 (padding = identity slot 2T-1)
-        vals[:, 2 * T - 1] = ident
+        vals[:, phys[2 * T - 1]] = ident
         c0, c1 = A["ell_chunk_ptr"][t], A["ell_chunk_ptr"][t + 1]
         desc = A["ell_desc"].reshape(-1, 2)
         for c in range(c0, c1):

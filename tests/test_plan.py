@@ -7,7 +7,7 @@ import oracle
 from genlm_backend_b200 import TokenCharacterTrie, Token
 from genlm_backend_b200.synthetic import synth_vocab, dirichlet_rows
 from helpers import rel_err
-from plan_emulator import emulate
+from plan_emulator import emulate, swizzle_slot
 
 
 def oracle_for(trie):
@@ -15,11 +15,12 @@ def oracle_for(trie):
     return oracle.OracleLayout(trie.idx_to_leaf, lay["child_ptr"], lay["child_idx"])
 
 
-@pytest.mark.parametrize("V,T,Q", [(1, 1024, 4), (5, 1024, 4), (700, 1024, 128), (3000, 1024, 512), (3000, 2048, 8192),
-                                   (20011, 4096, 8192), (20011, 1024, 1000), (20011, 8192, 16384), (50257, 4096, 8192)])
-def test_emulated_kernels_match_oracle(V, T, Q):
+@pytest.mark.parametrize("V,T,Q,R", [(1, 1024, 4, 2), (5, 1024, 4, 4), (700, 1024, 128, 2), (3000, 1024, 512, 4),
+                                     (3000, 2048, 8192, 2), (20011, 4096, 8192, 2), (20011, 1024, 1000, 4),
+                                     (20011, 8192, 16384, 2), (20011, 2048, 4096, 4), (50257, 2048, 4096, 4)])
+def test_emulated_kernels_match_oracle(V, T, Q, R):
     trie = TokenCharacterTrie(synth_vocab(max(V, 256), seed=2)[-V:])
-    trie._engine.plan(T, Q)
+    trie._engine.plan(T, Q, R)
     ws = dirichlet_rows(3, V, alpha=0.1, seed=1)
     o = oracle_for(trie)
     have = emulate(trie._engine, ws, "sum")
@@ -54,7 +55,8 @@ def test_plan_invariants():
     assert lo[0] == 0 and lo[-1] == len(trie) and (np.diff(lo) > 0).all()
     slot = eng.plan_array("node_slot")
     spanning = (lay["lo"] // T) != ((lay["hi"] - 1) // T)
-    assert np.array_equal(slot == 2 * T - 1, spanning)  # spanning nodes point at the identity slot
+    ident = swizzle_slot(2 * T - 1, 4 * info["rows_per_item"])
+    assert np.array_equal(slot == ident, spanning)  # spanning nodes point at the identity slot
     assert np.array_equal(np.sort(eng.plan_array("span_node")), np.flatnonzero(spanning))
     # every spanning node has one piece per tile it overlaps, each written by exactly one tile
     pp, sn = eng.plan_array("span_pp"), eng.plan_array("span_node")
@@ -65,17 +67,19 @@ def test_plan_invariants():
     assert info["n_span"] == int(spanning.sum()) and info["span_terms"] == pp[-1]
     # ELL padding uses the identity slot; real terms never point at it or past the tile's value array
     terms = eng.plan_array("ell_terms")
-    assert terms.max() <= 2 * T - 1 and (terms != 2 * T - 1).sum() > 0
+    assert terms.max() <= 2 * T - 1 and (terms != ident).sum() > 0
+    rows = eng.plan_array("ell_row_ptr")
+    assert rows[0] == 0 and rows[-1] * 32 == len(terms) and (eng.plan_array("ell_desc").reshape(-1, 2)[:, 1] % 4 == 0).all()
 
 
 def test_plan_parameter_validation():
     trie = TokenCharacterTrie([Token(0, b"a")])
     from genlm_backend_b200._lib import GtError
 
-    for T, Q in [(1000, 8192), (512, 8192), (16384, 8192), (4096, 6), (4096, 32768)]:
+    for T, Q, R in [(1000, 8192, 2), (512, 8192, 2), (16384, 8192, 2), (4096, 6, 2), (4096, 32768, 2), (4096, 4096, 3)]:
         with pytest.raises(GtError):
-            trie._engine.plan(T, Q)
-    trie._engine.plan(2048, 4096)
+            trie._engine.plan(T, Q, R)
+    trie._engine.plan(2048, 4096, 2)
     trie._engine.plan()  # defaults resolve to the existing plan
     with pytest.raises(GtError):
         trie._engine.plan(4096, 4096)
