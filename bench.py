@@ -217,8 +217,9 @@ def run_ours(args):
     base = dirichlet_rows(B, V, alpha=args.alpha, seed=1 + rank)
     nsets = max(1, args.sets)
     ws_sets = [torch.tensor(np.roll(base, k, axis=0)).to(dev) for k in range(nsets)]
-    sum_sets = [torch.empty((B, N), dtype=torch.float32, device=dev) for _ in range(nsets)]
-    max_sets = [torch.empty((B, N), dtype=torch.float32, device=dev) for _ in range(nsets)]
+    # output slabs as the engine allocates them: [B, N] views of rows padded to whole 128-byte lines
+    sum_sets = [eng.alloc_out(B, torch.float32, dev) for _ in range(nsets)]
+    max_sets = [eng.alloc_out(B, torch.float32, dev) for _ in range(nsets)]
     set_bytes = B * V * 4 + 2 * B * N * 4
     l2_bytes = torch.cuda.get_device_properties(dev).L2_cache_size
 

@@ -49,6 +49,7 @@ struct Plan {
     int32_t R = 0;           // rows per CTA of the fp32 pipeline (the fp64 pipeline uses R/2: same slot size)
     int32_t slot_bytes = 0;  // 4 * R
     int32_t max_tile_nodes = 0, max_tile_ell_rows = 0;  // sizes of the shared-memory metadata stages
+    int32_t max_tile_chunks = 0, max_tile_z = 0;        // ELL chunks / staged elements of the largest tile
     int64_t Zrow = 0;  // floats per staged row (multiple of 4)
 
     // phase 1 (permute): per segment s, records of 4 staged elements.
@@ -63,7 +64,7 @@ struct Plan {
     std::vector<int32_t> z_tile_off;    // [NT+1]
     std::vector<uint16_t> p2_slot;      // [Zrow]
 
-    // per-tile value array: slots [0,T) leaves in DFS order, [T,2T-1) pyramid of aligned blocks,
+    // per-tile value array: slots [0,T) leaves in DFS order, [T,2T-1) pyramid of aligned blocks (levels 1..8),
     // 2T-1 the identity element, [2T, ..) multi-term ranges.
     // Multi-term ranges in ELL form: per tile chunks of 32 ranges (sorted by descending term count);
     // chunk c holds ell_k[c] rows of 32 uint16 slots starting at ell_terms[32 * ell_off[c]], padded with

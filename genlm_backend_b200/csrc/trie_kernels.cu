@@ -33,7 +33,7 @@ namespace gt {
 
 struct PlanView {
     int32_t T, logT, Q, NT, NS, SV;  // SV = value slots per tile in shared memory
-    int32_t R, max_tile_nodes, max_tile_ell_rows;
+    int32_t R, max_tile_nodes, max_tile_ell_rows, max_tile_chunks, max_tile_z;
     int64_t V, N, Zrow;
     const int32_t* p1_chunk_ptr; const int4* p1_rec;
     const int32_t* z_tile_off; const uint16_t* p2_slot;
@@ -232,13 +232,49 @@ __global__ void __launch_bounds__(kThreads) permute_kernel(PlanView P, const IN_
 }
 
 // ---- phase 2: per-tile pyramid, multi-term ranges, emit, spanning pieces -------------------------------------
+//
+// Persistent kernel.  A work item is (tile t, row group g of R rows); items are numbered tile-major and every CTA
+// takes one contiguous run of them, so consecutive items of a CTA share the tile metadata, which stays in shared
+// memory.  Everything an item reads from global memory arrives by bulk copies (cp.async.bulk, the TMA engine)
+// issued one step ahead by one thread and tracked by three mbarriers:
+//     barrier A (armed after the scatter of item i)  staged rows of item i+1 (+ the slot table of its tile if new)
+//     barrier B (armed after the ELL phase)          ELL term rows + descriptors of the next tile, if new
+//     barrier C (armed after the emit)               emit slots of the next tile, if new
+// Each barrier is armed exactly once per item (with 0 bytes when there is nothing to fetch), so its phase parity
+// is the item parity.  In steady state no phase waits on L2/HBM latency and the only global-memory instructions
+// executed in line are the output stores.
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
     const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// mbarrier + bulk-copy (TMA) primitives.  One elected thread arms the barrier with the byte count and issues the
+// copies; the copy engine signals the barrier when the bytes have landed, so no LSU instruction is spent per 16 bytes.
+__device__ __forceinline__ void mbar_init(uint64_t* b, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(b)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* b, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(b)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* b, unsigned parity) {
+    const unsigned addr = (unsigned)__cvta_generic_to_shared(b);
+    unsigned done;
+    do {  // try_wait suspends the thread in hardware for a bounded time; loop until the phase has completed
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                     : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+    } while (!done);
+}
+// bytes: multiple of 16; both addresses 16-byte aligned
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, unsigned bytes, uint64_t* b) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     (unsigned)__cvta_generic_to_shared(smem_dst)),
+                 "l"(gsrc), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(b))
+                 : "memory");
+}
 
 // Device twin of gt::swizzle_slot (trie_internal.h) for slots below 2T; B = bytes per slot.
 template <int B> __device__ __forceinline__ int swz(int s) {
@@ -289,187 +325,268 @@ template <typename VT, int R> struct RowVec {
     }
 };
 
+constexpr int kTileThreads = 512;
+
+// Shared-memory carve-up of tile_kernel (all sections 16-byte aligned).
+struct TileSmem {
+    size_t vals, stage, p2, slots, terms, desc, bars, total;
+    __host__ __device__ TileSmem(const PlanView& P, int slot_bytes, int elem_bytes, int R) {
+        size_t o = 0;
+        vals = o;  o += (size_t)(P.SV + 4) * slot_bytes;                    // value slots + trash slot
+        stage = o; o += (size_t)R * P.max_tile_z * elem_bytes;              // staged rows of the next item
+        p2 = o;    o += (size_t)P.max_tile_z * 2;                           // staged element -> value slot
+        slots = o; o += (size_t)P.max_tile_nodes * 2;                       // node -> value slot (emit)
+        terms = o; o += (size_t)P.max_tile_ell_rows * 64;                   // ELL term rows
+        desc = o;  o += ((size_t)(P.max_tile_chunks + 2) * 8 + 15) & ~size_t(15); // ELL chunk descriptors (+ alignment slack)
+        bars = o;  o += 32;                                                 // three mbarriers
+        total = o;
+    }
+};
+
 template <typename VT, int R, int OP>
-__global__ void __launch_bounds__(kThreads, 2) tile_kernel(PlanView P, const VT* __restrict__ z, VT* __restrict__ out,
-                                                           int64_t ld_out, VT* __restrict__ part, int n_rows) {
+__global__ void __launch_bounds__(kTileThreads, 2) tile_kernel(PlanView P, const VT* __restrict__ z, VT* __restrict__ out,
+                                                               int64_t ld_out, VT* __restrict__ part, int n_rows) {
     using RV = RowVec<VT, R>;
     constexpr int B = (int)sizeof(VT) * R;  // bytes per slot
     static_assert(B == 4 || B == 8 || B == 16, "slot must be 4, 8 or 16 bytes");
     constexpr int SPC = 16 / B;             // slots per 16-byte chunk
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    VT* vals = reinterpret_cast<VT*>(smem_raw);  // [SV + 4][R]; slot SV is the trash slot for staged padding
-    uint16_t* s_slots = reinterpret_cast<uint16_t*>(smem_raw + (size_t)(P.SV + 4) * B);  // emit slots of the tile
-    uint16_t* s_terms = s_slots + P.max_tile_nodes;                                      // ELL term rows of the tile
+    constexpr int kWarps = kTileThreads / 32;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const TileSmem L(P, B, (int)sizeof(VT), R);
+    VT* vals = reinterpret_cast<VT*>(smem_raw + L.vals);
+    VT* stage = reinterpret_cast<VT*>(smem_raw + L.stage);
+    uint16_t* s_p2 = reinterpret_cast<uint16_t*>(smem_raw + L.p2);
+    uint16_t* s_slots = reinterpret_cast<uint16_t*>(smem_raw + L.slots);
+    uint16_t* s_terms = reinterpret_cast<uint16_t*>(smem_raw + L.terms);
+    int2* s_desc = reinterpret_cast<int2*>(smem_raw + L.desc);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + L.bars);  // [0] rows (+p2), [1] terms + desc, [2] emit slots
+
     const int T = P.T;
-    const int t = blockIdx.x;
-    const int b0 = blockIdx.y * R;
-    const int nrows = min(R, n_rows - b0);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    constexpr int kWarps = kThreads / 32;
+    const int RG = (n_rows + R - 1) / R;
+    const int n_items = P.NT * RG;
+    const int i0 = (int)((int64_t)blockIdx.x * n_items / gridDim.x);
+    const int i1 = (int)((int64_t)(blockIdx.x + 1) * n_items / gridDim.x);
+    if (i0 >= i1) return;
+    const int zpitch = P.max_tile_z;
+    const int dbg = P.debug_stop;
     auto slot_ptr = [&](int s) { return vals + swz<B>(s) * R; };               // s < 2T, computed arithmetically
     auto level_slot = [&](int k, int i) { return 2 * T - (T >> (k - 1)) + i; };  // level k >= 1, block i
 
-    // per-tile scalars, fetched once up front
-    const int zlo = __ldg(P.z_tile_off + t), zhi = __ldg(P.z_tile_off + t + 1);
-    const int ec0 = __ldg(P.ell_chunk_ptr + t), ec1 = __ldg(P.ell_chunk_ptr + t + 1);
-    const int er0 = __ldg(P.ell_row_ptr + t), er1 = __ldg(P.ell_row_ptr + t + 1);
-    const int n0 = __ldg(P.tile_node_lo + t), n1 = __ldg(P.tile_node_lo + t + 1);
-    const int pc0 = __ldg(P.piece_ptr + t), pc1 = __ldg(P.piece_ptr + t + 1);
-    const int na = n0 & ~7;  // emit slots are staged from the 16-byte aligned start at or below n0
-    // ELL descriptors of the chunks this warp will process: lane i holds the i-th one (<= 32 per warp)
-    int2 my_desc = make_int2(0, 0);
-    if (ec0 + warp + kWarps * lane < ec1) my_desc = __ldg(P.ell_desc + ec0 + warp + kWarps * lane);
+    // ---- asynchronous fetches (thread 0 only) ------------------------------------------------------------------
+    // Barrier A: staged rows of item (t, g): R rows of the tile's z range, plus the tile's slot table when with_p2.
+    // Rows past the end of the batch alias the last valid row (they then compute and store exactly what that row
+    // does, which keeps every loop free of row predicates).
+    auto fetch_rows = [&](int t, int g, bool with_p2) {
+        const int zlo = __ldg(P.z_tile_off + t), zn = __ldg(P.z_tile_off + t + 1) - zlo;
+        const unsigned row_bytes = (unsigned)zn * (unsigned)sizeof(VT);
+        mbar_expect_tx(&bars[0], R * row_bytes + (with_p2 ? (unsigned)zn * 2u : 0u));
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int row = min(g * R + r, n_rows - 1);
+            bulk_g2s(stage + (size_t)r * zpitch, z + (size_t)row * P.Zrow + zlo, row_bytes, &bars[0]);
+        }
+        if (with_p2) bulk_g2s(s_p2, P.p2_slot + zlo, (unsigned)zn * 2u, &bars[0]);
+    };
+    // Barrier B: ELL term rows and chunk descriptors (8 bytes each, copied from the 16-byte aligned pair at or
+    // below the first one).
+    auto fetch_terms = [&](int t) {
+        const int er0 = __ldg(P.ell_row_ptr + t), er1 = __ldg(P.ell_row_ptr + t + 1);
+        const int ec0 = __ldg(P.ell_chunk_ptr + t), ec1 = __ldg(P.ell_chunk_ptr + t + 1);
+        const int ea = ec0 & ~1;
+        const unsigned tb = (unsigned)(er1 - er0) * 64u, db = (unsigned)((ec1 - ea + 1) >> 1) * 16u;
+        mbar_expect_tx(&bars[1], tb + db);
+        if (tb) bulk_g2s(s_terms, P.ell_terms + (size_t)er0 * 32, tb, &bars[1]);
+        if (db) bulk_g2s(s_desc, P.ell_desc + ea, db, &bars[1]);
+    };
+    // Barrier C: emit slots, staged from the 16-byte aligned start at or below the tile's first node.
+    auto fetch_slots = [&](int t) {
+        const int n0 = __ldg(P.tile_node_lo + t), n1 = __ldg(P.tile_node_lo + t + 1);
+        const int na = n0 & ~7;
+        const unsigned sb = (unsigned)((n1 - na + 7) >> 3) * 16u;
+        mbar_expect_tx(&bars[2], sb);
+        bulk_g2s(s_slots, P.node_slot + na, sb, &bars[2]);
+    };
 
-    // The ELL term rows and the emit slots are needed late: copy them into shared memory asynchronously now
-    // (cp.async, no registers), so phases 3 and 5 never wait on L2.
-    {
-        const uint4* src = reinterpret_cast<const uint4*>(P.node_slot + na);
-        const int nch = (n1 - na + 7) >> 3;
-        for (int i = tid; i < nch; i += kThreads) cp_async16(s_slots + 8 * i, src + i);
-        const uint4* tsrc = reinterpret_cast<const uint4*>(P.ell_terms + (size_t)er0 * 32);
-        const int tch = (er1 - er0) * 4;
-        for (int i = tid; i < tch; i += kThreads) cp_async16(s_terms + 8 * i, tsrc + i);
-        cp_async_commit();
+    int t = i0 / RG, g = i0 - t * RG;
+    if (tid == 0) {
+        mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_init(&bars[2], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        fetch_rows(t, g, true);
+        fetch_terms(t);
+        fetch_slots(t);
     }
+    __syncthreads();  // barriers initialised before anyone waits on them
 
-    // CTA-uniform base pointers plus 32-bit row offsets.  Rows past the end of the batch alias the last valid row:
-    // they load, compute and store exactly what that row does (same values to the same addresses), which keeps
-    // every loop free of per-row predicates.
-    const VT* zbase = z + (size_t)b0 * P.Zrow + zlo;
-    VT* obase = out + (size_t)b0 * ld_out;
-    VT* pbase = part + (size_t)b0 * P.n_pieces;
-    int zoff[R], ooff[R], poff[R];
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-        const int rr = min(r, nrows - 1);
-        zoff[r] = rr * (int)P.Zrow; ooff[r] = rr * (int)ld_out; poff[r] = rr * P.n_pieces;
-    }
+    int zn4 = 0, ec0 = 0, ec1 = 0, n0 = 0, n1 = 0, pc0 = 0, pc1 = 0, nleaf = 0;
+    bool new_tile = true;
+    unsigned parity = 0;
+    for (int item = i0; item < i1; ++item, parity ^= 1u) {
+        if (new_tile) {  // per-tile scalars
+            zn4 = (__ldg(P.z_tile_off + t + 1) - __ldg(P.z_tile_off + t)) >> 2;
+            ec0 = __ldg(P.ell_chunk_ptr + t); ec1 = __ldg(P.ell_chunk_ptr + t + 1);
+            n0 = __ldg(P.tile_node_lo + t); n1 = __ldg(P.tile_node_lo + t + 1);
+            pc0 = __ldg(P.piece_ptr + t); pc1 = __ldg(P.piece_ptr + t + 1);
+            nleaf = (int)min((int64_t)T, P.V - (int64_t)t * T);
+        }
+        // the item after this one
+        int tn = t, gn = g + 1;
+        if (gn == RG) { gn = 0; ++tn; }
+        const bool has_next = item + 1 < i1;
+        const bool next_new = has_next && tn != t;
 
-    // 1. staged tile -> DFS-ordered leaf slots (slot numbers in p2_slot are already swizzled)
-    if (P.debug_stop != 9) {
-        const int zn4 = (zhi - zlo) >> 2;
-        const uint2* slot4 = reinterpret_cast<const uint2*>(P.p2_slot + zlo);
-        constexpr int U = R >= 4 ? 1 : 2;
-        for (int ib = tid; ib < zn4; ib += U * kThreads) {
-            uint2 sl[U];
-            VT v[U][R][4];
+        // 1. staged rows -> DFS-ordered leaf slots (slot numbers in the table are already swizzled)
+        mbar_wait(&bars[0], parity);
+        __syncthreads();  // the previous item's emit has finished reading vals
+        if (dbg != 9) {
+            for (int q = tid; q < zn4; q += kTileThreads) {
+                const uint2 sl = *reinterpret_cast<const uint2*>(s_p2 + 4 * q);
+                VT v[R][4];
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int i = min(ib + u * kThreads, zn4 - 1);  // clamped duplicate instead of a predicate
-                sl[u] = __ldg(slot4 + i);
-#pragma unroll
-                for (int r = 0; r < R; ++r) load4<VT>(zbase + zoff[r] + 4 * i, v[u][r][0], v[u][r][1], v[u][r][2], v[u][r][3]);
-            }
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const unsigned s4[4] = {sl[u].x & 0xFFFFu, sl[u].x >> 16, sl[u].y & 0xFFFFu, sl[u].y >> 16};
+                for (int r = 0; r < R; ++r) load4<VT>(stage + (size_t)r * zpitch + 4 * q, v[r][0], v[r][1], v[r][2], v[r][3]);
+                const unsigned s4[4] = {sl.x & 0xFFFFu, sl.x >> 16, sl.y & 0xFFFFu, sl.y >> 16};
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                     RV x;
 #pragma unroll
-                    for (int r = 0; r < R; ++r) x.v[r] = v[u][r][e];
+                    for (int r = 0; r < R; ++r) x.v[r] = v[r][e];
                     x.store(vals + s4[e] * R);
                 }
             }
+            for (int i = nleaf + tid; i < T; i += kTileThreads) RV::template ident<OP>().store(slot_ptr(i));
+            if (tid == 0) RV::template ident<OP>().store(slot_ptr(2 * T - 1));  // identity slot (ELL padding, spanning nodes)
         }
-        const int nleaf = (int)min((int64_t)T, P.V - (int64_t)t * T);
-        for (int i = nleaf + tid; i < T; i += kThreads) RV::template ident<OP>().store(slot_ptr(i));
-        if (tid == 0) RV::template ident<OP>().store(slot_ptr(2 * T - 1));  // identity slot (ELL padding, spanning nodes)
-    }
-    __syncthreads();
-    if (P.debug_stop == 1) return;
+        __syncthreads();
+        // the staging buffer (and, on a tile change, the slot table) is free again: fetch the next item's rows
+        if (tid == 0) {
+            if (has_next) fetch_rows(tn, gn, next_new);
+            else mbar_expect_tx(&bars[0], 0);
+        }
 
-    // 2. pyramid of aligned blocks: level k block i at (swizzled) slot 2T - (T >> (k-1)) + i.
-    //    Lane u owns leaves 8u .. 8u+7: levels 1..3 in registers, 4..8 by warp shuffles (256 leaves per warp).
-    //    The swizzle makes the 16-byte chunk loads and the strided level stores bank-conflict free.
-    if (P.debug_stop != 9) {
-        for (int ub = warp * 32; ub < (T >> 3); ub += kWarps * 32) {
-            const int u = ub + lane;
-            RV x[8];
+        // 2. pyramid of aligned blocks: level k block i at (swizzled) slot 2T - (T >> (k-1)) + i.
+        //    Lane u owns leaves 8u .. 8u+7: levels 1..3 in registers, 4..8 by warp shuffles (256 leaves per warp).
+        //    The swizzle makes the 16-byte chunk loads and the strided level stores bank-conflict free.
+        if (dbg != 9 && dbg != 1) {
+            for (int ub = warp * 32; ub < (T >> 3); ub += kWarps * 32) {
+                const int u = ub + lane;
+                RV x[8];
 #pragma unroll
-            for (int ch = 0; ch < 8 / SPC; ++ch) {
-                const int c = (8 * u) / SPC + ch;
-                const int cc = c ^ ((c >> 3) & (B / 2 - 1));
-                const float4 raw = *reinterpret_cast<const float4*>(reinterpret_cast<const unsigned char*>(vals) + (size_t)cc * 16);
-                memcpy(&x[ch * SPC], &raw, 16);
-            }
-            RV a[4];
+                for (int ch = 0; ch < 8 / SPC; ++ch) {
+                    const int c = (8 * u) / SPC + ch;
+                    const int cc = c ^ ((c >> 3) & (B / 2 - 1));
+                    const float4 raw = *reinterpret_cast<const float4*>(reinterpret_cast<const unsigned char*>(vals) + (size_t)cc * 16);
+                    memcpy(&x[ch * SPC], &raw, 16);
+                }
+                RV a[4];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                a[e] = RV::template combine<OP>(x[2 * e], x[2 * e + 1]);
-                a[e].store(slot_ptr(level_slot(1, 4 * u + e)));
-            }
-            const RV c0 = RV::template combine<OP>(a[0], a[1]), c1 = RV::template combine<OP>(a[2], a[3]);
-            c0.store(slot_ptr(level_slot(2, 2 * u)));
-            c1.store(slot_ptr(level_slot(2, 2 * u + 1)));
-            RV y = RV::template combine<OP>(c0, c1);
-            y.store(slot_ptr(level_slot(3, u)));
+                for (int e = 0; e < 4; ++e) {
+                    a[e] = RV::template combine<OP>(x[2 * e], x[2 * e + 1]);
+                    a[e].store(slot_ptr(level_slot(1, 4 * u + e)));
+                }
+                const RV c0 = RV::template combine<OP>(a[0], a[1]), c1 = RV::template combine<OP>(a[2], a[3]);
+                c0.store(slot_ptr(level_slot(2, 2 * u)));
+                c1.store(slot_ptr(level_slot(2, 2 * u + 1)));
+                RV y = RV::template combine<OP>(c0, c1);
+                y.store(slot_ptr(level_slot(3, u)));
 #pragma unroll
-            for (int j = 1; j <= 5; ++j) {
-                y = RV::template combine<OP>(y, y.shfl_down(1 << (j - 1)));
-                if ((lane & ((1 << j) - 1)) == 0) y.store(slot_ptr(level_slot(3 + j, u >> j)));
+                for (int j = 1; j <= 5; ++j) {
+                    y = RV::template combine<OP>(y, y.shfl_down(1 << (j - 1)));
+                    if ((lane & ((1 << j) - 1)) == 0) y.store(slot_ptr(level_slot(3 + j, u >> j)));
+                }
             }
         }
-    }
-    __syncthreads();
-    //    Levels 9..logT: T/256 <= 32 level-8 blocks, one warp.
-    if (warp == 0 && P.logT > 8 && P.debug_stop != 9) {
-        const int n8 = T >> 8;
-        RV y = lane < n8 ? RV::load(slot_ptr(level_slot(8, lane))) : RV::template ident<OP>();
-        for (int j = 1; j <= P.logT - 8; ++j) {
-            y = RV::template combine<OP>(y, y.shfl_down(1 << (j - 1)));
-            if ((lane & ((1 << j) - 1)) == 0 && lane < n8) y.store(slot_ptr(level_slot(8 + j, lane >> j)));
-        }
-    }
-    cp_async_wait_all();  // this thread's share of the staged metadata has landed; the barrier publishes all of it
-    __syncthreads();
-    if (P.debug_stop == 2) return;
+        mbar_wait(&bars[1], parity);  // ELL terms + descriptors of this tile
+        __syncthreads();
 
-    // 3. ranges that need more than one block: ELL chunks of 32 ranges, one warp per chunk, term rows read from
-    //    shared memory (k is a multiple of 4: the planner pads rows with the identity slot)
-    if (P.debug_stop != 9) {
-        int it = 0;
-        for (int c = ec0 + warp; c < ec1; c += kWarps, ++it) {
-            const int off32 = __shfl_sync(0xffffffffu, my_desc.x, it), k = __shfl_sync(0xffffffffu, my_desc.y, it);
-            const uint16_t* tp = s_terms + (off32 - er0) * 32 + lane;
-            RV acc = RV::template ident<OP>();
-            for (int kb = 0; kb < k; kb += 4) {
-                int sl[4];
+        // 3. ranges that need more than one block: ELL chunks of 32 ranges, one warp per chunk, term rows read from
+        //    shared memory (k is a multiple of 4: the planner pads rows with the identity slot)
+        if (dbg != 9 && dbg != 1 && dbg != 2) {
+            const int2* dsc = s_desc + (ec0 & 1);
+            const int er0 = dsc[0].x;  // first chunk's row offset == the tile's first term row (unused if no chunk)
+            for (int c = warp; c < ec1 - ec0; c += kWarps) {
+                const int2 d = dsc[c];
+                const uint16_t* tp = s_terms + (d.x - er0) * 32 + lane;
+                RV acc = RV::template ident<OP>();
+                for (int kb = 0; kb < d.y; kb += 4) {
+                    int sl[4];
 #pragma unroll
-                for (int e = 0; e < 4; ++e) sl[e] = tp[(kb + e) * 32];
+                    for (int e = 0; e < 4; ++e) sl[e] = tp[(kb + e) * 32];
 #pragma unroll
-                for (int e = 0; e < 4; ++e) acc = RV::template combine<OP>(acc, RV::load(vals + sl[e] * R));
-            }
-            acc.store(vals + (2 * T + (c - ec0) * 32 + lane) * R);
-        }
-    }
-    __syncthreads();
-    if (P.debug_stop == 3) return;
-
-    // 4. pieces of spanning nodes that overlap this tile (reduced by span_kernel, which runs next on the stream)
-    for (int i = pc0 + tid; i < pc1; i += kThreads) {
-        const RV x = RV::load(vals + (int)__ldg(P.piece_slot + i) * R);
-        const int idx = __ldg(P.piece_idx + i);
-#pragma unroll
-        for (int r = 0; r < R; ++r) pbase[poff[r] + idx] = x.v[r];
-    }
-
-    // 5. emit the tile's node-id interval: lane = consecutive node id, so the slot reads of a warp cluster on a few
-    //    neighbouring slots (unary chains broadcast) and every store instruction writes one full 128-byte line per
-    //    row.  Spanning nodes inside the interval carry the identity slot: what is written for them here is
-    //    overwritten by span_kernel.  The last iteration clamps to the final node instead of predicating.
-    {
-        constexpr int U = 4;
-        const uint16_t* sl_base = s_slots - na;
-        for (int nb = n0 + tid; nb < n1; nb += U * kThreads) {
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int n = min(nb + u * kThreads, n1 - 1);
-                const RV x = RV::load(vals + (int)sl_base[n] * R);
-#pragma unroll
-                for (int r = 0; r < R; ++r) __stcs(obase + (ooff[r] + n), x.v[r]);
+                    for (int e = 0; e < 4; ++e) acc = RV::template combine<OP>(acc, RV::load(vals + sl[e] * R));
+                }
+                acc.store(vals + (2 * T + c * 32 + lane) * R);
             }
         }
+        // every wait on a barrier sits before a CTA barrier and every re-arm after it, so no thread can still be
+        // waiting on a phase when the next one completes
+        mbar_wait(&bars[2], parity);  // emit slots of this tile
+        __syncthreads();
+        if (tid == 0) {
+            if (next_new) fetch_terms(tn);
+            else mbar_expect_tx(&bars[1], 0);
+        }
+
+        if (dbg == 0 || dbg == 9) {
+            const int b0 = g * R;
+            VT* orow[R];
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                orow[r] = out + (size_t)min(b0 + r, n_rows - 1) * ld_out;
+                asm volatile("" : "+l"(orow[r]));  // keep the row pointers in registers (no rematerialisation per store)
+            }
+
+            // 4. pieces of spanning nodes that overlap this tile (reduced by span_kernel, which runs next on the
+            //    stream).  The table entries are requested first and consumed after the emit loop.
+            const int pi = pc0 + tid;
+            int p_slot = 0, p_idx = 0;
+            if (pi < pc1) { p_slot = __ldg(P.piece_slot + pi); p_idx = __ldg(P.piece_idx + pi); }
+
+            // 5. emit the tile's node-id interval: lane = consecutive node id, so the slot reads of a warp cluster on
+            //    a few neighbouring slots (unary chains broadcast) and every store instruction writes 128 contiguous
+            //    bytes per row.  The sweep starts at the 128-byte line of row 0 that holds node n0, so with a row
+            //    stride that is a multiple of 32 elements every store instruction covers exactly one line.
+            //    Spanning nodes inside the interval carry the identity slot: what is written for them here is
+            //    overwritten by span_kernel.
+            constexpr int U = 4;
+            const int na = n0 & ~7;
+            const int lead = (int)(((reinterpret_cast<uintptr_t>(orow[0]) / sizeof(VT)) + (unsigned)n0) & 31u);
+            const unsigned count = (unsigned)(n1 - n0);
+            const uint16_t* sl_base = s_slots - na;
+            const unsigned char* vbytes = reinterpret_cast<const unsigned char*>(vals);
+            for (int nb = n0 - lead + tid; nb < n1; nb += U * kTileThreads) {
+                VT* p[R];
+#pragma unroll
+                for (int r = 0; r < R; ++r) p[r] = orow[r] + nb;
+                RV x[U];
+                bool ok[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int n = nb + u * kTileThreads;
+                    ok[u] = (unsigned)(n - n0) < count;
+                    if (ok[u]) x[u] = RV::load(reinterpret_cast<const VT*>(vbytes + (unsigned)sl_base[n] * (unsigned)B));
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+                    if (ok[u]) {
+#pragma unroll
+                        for (int r = 0; r < R; ++r) __stcs(p[r] + u * kTileThreads, x[u].v[r]);
+                    }
+            }
+
+            for (int i = pi; i < pc1; i += kTileThreads) {
+                if (i != pi) { p_slot = __ldg(P.piece_slot + i); p_idx = __ldg(P.piece_idx + i); }
+                const RV x = RV::load(vals + p_slot * R);
+#pragma unroll
+                for (int r = 0; r < R; ++r) part[(size_t)min(b0 + r, n_rows - 1) * P.n_pieces + p_idx] = x.v[r];
+            }
+        }
+        if (next_new) __syncthreads();  // everyone is done with this tile's emit slots
+        if (tid == 0) {
+            if (next_new) fetch_slots(tn);
+            else mbar_expect_tx(&bars[2], 0);
+        }
+        new_tile = next_new;
+        t = tn; g = gn;
     }
 }
 
@@ -552,6 +669,7 @@ static DevicePlan* upload_plan(const Layout& L, const Plan& P, int device) {
     v.ell_chunk_ptr = (const int32_t*)(base + o_ell_chunk_ptr); v.ell_desc = (const int2*)(base + o_ell_desc);
     v.ell_terms = (const uint16_t*)(base + o_ell_terms); v.ell_row_ptr = (const int32_t*)(base + o_ell_row_ptr);
     v.R = P.R; v.max_tile_nodes = P.max_tile_nodes; v.max_tile_ell_rows = P.max_tile_ell_rows;
+    v.max_tile_chunks = P.max_tile_chunks; v.max_tile_z = P.max_tile_z;
     v.tile_node_lo = (const int32_t*)(base + o_tile_node_lo); v.node_slot = (const uint16_t*)(base + o_node_slot);
     v.piece_ptr = (const int32_t*)(base + o_piece_ptr); v.piece_slot = (const uint16_t*)(base + o_piece_slot);
     v.piece_idx = (const int32_t*)(base + o_piece_idx);
@@ -563,9 +681,7 @@ static DevicePlan* upload_plan(const Layout& L, const Plan& P, int device) {
 
 
 template <typename VT, int R> static size_t permute_smem(const PlanView& v) { return (size_t)R * (v.Q + kSegPad) * sizeof(VT); }
-template <typename VT, int R> static size_t tile_smem(const PlanView& v) {
-    return (size_t)R * (v.SV + 4) * sizeof(VT) + (size_t)v.max_tile_nodes * 2 + (size_t)v.max_tile_ell_rows * 64;
-}
+template <typename VT, int R> static size_t tile_smem(const PlanView& v) { return TileSmem(v, (int)sizeof(VT) * R, (int)sizeof(VT), R).total; }
 
 // Opt in to > 48 KB dynamic shared memory once per (kernel, device, size): the attribute call is kept off the
 // steady-state launch path (and out of CUDA graph captures).  Keyed by the kernel's address: instantiations
@@ -615,6 +731,36 @@ static int launch_permute(const PlanView& v, const void* ws, int64_t ld_ws, cons
     return GT_OK;
 }
 
+// Resident CTAs per SM of a kernel at a given dynamic shared-memory size (cached: the query is not free).
+static int resident_ctas(const void* kernel, int threads, size_t smem) {
+    static std::mutex mu;
+    static std::map<std::pair<const void*, size_t>, int> cache;
+    std::lock_guard<std::mutex> lock(mu);
+    auto key = std::make_pair(kernel, smem);
+    auto it = cache.find(key);
+    if (it != cache.end()) return it->second;
+    int n = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, threads, smem) != cudaSuccess || n < 1) {
+        (void)cudaGetLastError();
+        n = 1;
+    }
+    cache[key] = n;
+    return n;
+}
+static int sm_count() {
+    static std::mutex mu;
+    static std::map<int, int> cache;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = cache.find(dev);
+    if (it != cache.end()) return it->second;
+    int n = 148;
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    cache[dev] = n;
+    return n;
+}
+
 template <typename VT, int R, int OP>
 static int launch_tile(const PlanView& v, const Scratch<VT>& sc, VT* out, int64_t ld_out, int rows, cudaStream_t st) {
     if (v.NT == 0) {  // empty vocabulary: the root is the only node and has no mass
@@ -622,9 +768,12 @@ static int launch_tile(const PlanView& v, const Scratch<VT>& sc, VT* out, int64_
         return GT_OK;
     }
     const size_t smem = tile_smem<VT, R>(v);
-    dim3 grid((unsigned)v.NT, (unsigned)((rows + R - 1) / R));
     GT_CUDA(allow_smem(tile_kernel<VT, R, OP>, smem));
-    tile_kernel<VT, R, OP><<<grid, kThreads, smem, st>>>(v, sc.z, out, ld_out, sc.part, rows);
+    // persistent grid: one CTA per resident slot, each takes a contiguous run of (tile, row group) items
+    const int64_t items = (int64_t)v.NT * ((rows + R - 1) / R);
+    const int slots = sm_count() * resident_ctas(reinterpret_cast<const void*>(tile_kernel<VT, R, OP>), kTileThreads, smem);
+    const unsigned grid = (unsigned)std::min<int64_t>(items, slots);
+    tile_kernel<VT, R, OP><<<grid, kTileThreads, smem, st>>>(v, sc.z, out, ld_out, sc.part, rows);
     GT_CUDA(cudaGetLastError());
     if (v.n_span > 0) {
         dim3 sgrid((unsigned)((v.n_span + 255) / 256), (unsigned)std::min(rows, 4096));
@@ -638,16 +787,17 @@ template <typename VT, int R>
 static int reduce_typed(const PlanView& v, const void* ws, int in_type, int64_t n_rows, int64_t ld_ws, void* out_sum,
                         void* out_max, int64_t ld_out, unsigned ops, unsigned flags, void* workspace,
                         size_t workspace_bytes, cudaStream_t st) {
-    // rows per chunk: what the caller's scratch can stage (multiple of R so row groups never straddle chunks)
+    // rows per chunk: what the caller's scratch can stage, rounded down to whole row groups when it holds at least
+    // one (a partial row group is legal: the kernels alias the missing rows to the last valid one)
+    const size_t per_row = (size_t)(v.Zrow + v.n_pieces) * sizeof(VT);
     int64_t chunk = std::min<int64_t>(n_rows, 32768);
-    while (chunk > 0 && Scratch<VT>::total(v, chunk) > workspace_bytes) chunk = chunk > 2 * R ? (chunk / 2 / R) * R : chunk - 1;
+    if (Scratch<VT>::total(v, chunk) > workspace_bytes) {
+        chunk = std::min<int64_t>(chunk, (int64_t)(workspace_bytes / std::max<size_t>(per_row, 1)));
+        while (chunk > 0 && Scratch<VT>::total(v, chunk) > workspace_bytes) --chunk;
+        if (chunk >= R) chunk = (chunk / R) * R;
+    }
     if (chunk < 1) {
         set_error("workspace too small: %zu bytes given, one row needs %zu", workspace_bytes, Scratch<VT>::total(v, 1));
-        return GT_ERR_STATE;
-    }
-    if (chunk < n_rows) chunk = std::max<int64_t>(R, (chunk / R) * R);
-    if (Scratch<VT>::total(v, std::min(chunk, n_rows)) > workspace_bytes) {
-        set_error("workspace too small: %zu bytes given, %d rows need %zu", workspace_bytes, R, Scratch<VT>::total(v, R));
         return GT_ERR_STATE;
     }
     const bool log_input = (flags & GT_FLAG_LOG_INPUT) != 0;

@@ -30,6 +30,9 @@ int build_plan(const Layout& L, int32_t T, int32_t Q, int32_t R, Plan& P) {
     if (Q < 4 || Q > 16384 || (Q & 3)) { set_error("segment size must be a multiple of 4 in [4, 16384]"); return GT_ERR_ARG; }
     if (R != 2 && R != 4) { set_error("rows per CTA must be 2 or 4"); return GT_ERR_ARG; }
     const int logT = ilog2(T);
+    // Aligned blocks stop at 256 leaves (level 8): one warp builds levels 1..8 of its 256 leaves with shuffles, so
+    // the pyramid needs no cross-warp step; the few ranges longer than that just carry more terms.
+    const int kTop = std::min(logT, 8);
     P.T = T; P.Q = Q; P.R = R; P.slot_bytes = 4 * R;
     const int32_t SB = P.slot_bytes;
     auto swz = [&](int32_t s) -> uint16_t { return (uint16_t)(s < 2 * T ? swizzle_slot(s, SB) : s); };
@@ -45,12 +48,20 @@ int build_plan(const Layout& L, int32_t T, int32_t Q, int32_t R, Plan& P) {
     std::vector<int64_t> run_off((size_t)NT * NS + 1, 0);  // start of run (t,s) in a staged row
     P.z_tile_off.assign((size_t)NT + 1, 0);
     int64_t z = 0;
+    // run_len[t][s]: staged length of run (t,s): the count padded to 4; the last run of a tile absorbs what is
+    // needed to make the tile's staged range a multiple of 8 elements (16-byte aligned uint16 slot tables, and
+    // 16-byte cp.async granules for every row type)
+    std::vector<int32_t> run_len((size_t)NT * NS, 0);
     for (int32_t t = 0; t < NT; ++t) {
         P.z_tile_off[t] = (int32_t)z;
         for (int32_t s = 0; s < NS; ++s) {
             run_off[(size_t)t * NS + s] = z;
-            z += (cnt[(size_t)t * NS + s] + 3) & ~3;
+            int32_t len = (cnt[(size_t)t * NS + s] + 3) & ~3;
+            if (s == NS - 1 && ((z + len) & 7)) len += 4;
+            run_len[(size_t)t * NS + s] = len;
+            z += len;
         }
+        P.max_tile_z = std::max<int32_t>(P.max_tile_z, (int32_t)(z - P.z_tile_off[t]));
     }
     P.z_tile_off[NT] = (int32_t)z;
     P.Zrow = z;
@@ -101,7 +112,7 @@ int build_plan(const Layout& L, int32_t T, int32_t Q, int32_t R, Plan& P) {
         P.p1_chunk_ptr[s] = (int32_t)(P.p1_rec.size() / 4);
         for (int32_t t = 0; t < NT; ++t) {
             const int64_t a = run_off[(size_t)t * NS + s];
-            const int64_t n = (cnt[(size_t)t * NS + s] + 3) & ~3;
+            const int64_t n = run_len[(size_t)t * NS + s];
             for (int64_t k = 0; k < n; k += 4) {
                 const uint32_t s0 = z_src[(size_t)(a + k)], s1 = z_src[(size_t)(a + k + 1)];
                 const uint32_t s2 = z_src[(size_t)(a + k + 2)], s3 = z_src[(size_t)(a + k + 3)];
@@ -134,7 +145,7 @@ int build_plan(const Layout& L, int32_t T, int32_t Q, int32_t R, Plan& P) {
         std::vector<uint16_t> terms;
         int32_t x = a;
         while (x < b) {
-            int k = x == 0 ? logT : std::min(logT, __builtin_ctz((unsigned)x));
+            int k = x == 0 ? kTop : std::min(kTop, __builtin_ctz((unsigned)x));
             while (x + (1 << k) > b) --k;
             terms.push_back(block_slot(k, x >> k));
             x += 1 << k;
@@ -232,7 +243,7 @@ int build_plan(const Layout& L, int32_t T, int32_t Q, int32_t R, Plan& P) {
         P.max_tile_values = std::max<int32_t>(P.max_tile_values, (int32_t)values);
     }
     P.ell_chunk_ptr[NT] = (int32_t)(P.ell_desc.size() / 2);
-    P.max_levels = logT;
+    P.max_levels = kTop;
 
     auto final_slot = [&](int32_t t, int32_t res) -> uint16_t {
         return res >= 0 ? (uint16_t)res : (uint16_t)(2 * T + rank_of[t][-(res + 1)]);
@@ -250,7 +261,7 @@ int build_plan(const Layout& L, int32_t T, int32_t Q, int32_t R, Plan& P) {
         }
     }
     P.piece_ptr[NT] = (int32_t)P.piece_slot.size();
-    P.max_tile_nodes = 0; P.max_tile_ell_rows = 0;
+    P.max_tile_nodes = 0; P.max_tile_ell_rows = 0; P.max_tile_chunks = 0;
     P.ell_row_ptr.assign((size_t)NT + 1, 0);
     for (int32_t t = 0; t < NT; ++t) {
         // the emit stage is copied from the 16-byte aligned start at or below the interval
@@ -259,6 +270,7 @@ int build_plan(const Layout& L, int32_t T, int32_t Q, int32_t R, Plan& P) {
         int32_t rows = 0;
         for (int32_t c = P.ell_chunk_ptr[t]; c < P.ell_chunk_ptr[t + 1]; ++c) rows += P.ell_desc[2 * (size_t)c + 1];
         P.max_tile_ell_rows = std::max(P.max_tile_ell_rows, rows);
+        P.max_tile_chunks = std::max(P.max_tile_chunks, P.ell_chunk_ptr[t + 1] - P.ell_chunk_ptr[t]);
         P.ell_row_ptr[(size_t)t + 1] = P.ell_row_ptr[(size_t)t] + rows;
     }
     if ((int64_t)P.ell_row_ptr[(size_t)NT] * 32 != (int64_t)P.ell_terms.size()) { set_error("internal: ELL row count"); return GT_ERR_STATE; }
@@ -278,7 +290,7 @@ int gt_plan(gt_trie* t, int32_t tile_leaves, int32_t seg_positions, int32_t rows
     if (t->plan && tile_leaves <= 0) tile_leaves = t->plan->T;
     if (t->plan && seg_positions <= 0) seg_positions = t->plan->Q;
     if (t->plan && rows_per_cta <= 0) rows_per_cta = t->plan->R;
-    if (tile_leaves <= 0) tile_leaves = env_int("GT_TILE_LEAVES", 2048);
+    if (tile_leaves <= 0) tile_leaves = env_int("GT_TILE_LEAVES", 1024);
     if (seg_positions <= 0) seg_positions = env_int("GT_SEG_POSITIONS", 4096);
     if (rows_per_cta <= 0) rows_per_cta = env_int("GT_ROWS_PER_CTA", 4);
     if (t->plan) {

@@ -108,6 +108,18 @@ class TrieEngine:
             self._workspaces[key] = buf
         return buf
 
+    def row_stride(self, dtype=torch.float32):
+        """Row stride (elements) of the output slabs the engine allocates: N rounded up to a whole number of
+        128-byte lines, so every row starts line-aligned and the emit stores of all rows of a row group are
+        line-aligned together."""
+        per_line = 128 // torch.empty((), dtype=dtype).element_size()
+        return (self.N + per_line - 1) // per_line * per_line
+
+    def alloc_out(self, B, dtype, device):
+        """``[B, N]`` view of a ``[B, row_stride]`` device slab (rows are padded to 128-byte lines)."""
+        ld = self.row_stride(dtype)
+        return torch.empty((max(B, 1), ld), dtype=dtype, device=device)[:B, : self.N]
+
     def reduce(self, ws, ops, out_dtype=torch.float32, log_input=False, out_sum=None, out_max=None, slot=0, phases=0):
         """Launch the mass kernels for a ``[B, V]`` CUDA tensor on its device's current stream.
 
@@ -134,7 +146,7 @@ class TrieEngine:
 
         def _out(t):
             if t is None:
-                return torch.empty((B, self.N), dtype=out_dtype, device=ws.device)
+                return self.alloc_out(B, out_dtype, ws.device)
             if not (t.is_cuda and t.device == ws.device and t.dtype == out_dtype and t.shape == (B, self.N) and (t.stride(1) == 1 or self.N <= 1)):
                 raise ValueError("out tensor must be a [B, N] tensor of the output dtype on the input's device")
             return t

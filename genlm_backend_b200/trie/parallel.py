@@ -125,9 +125,12 @@ class ParallelTokenCharacterTrie(TokenCharacterTrie):
         ws = self._as_batch(ws)
         B, N = ws.shape[0], len(self)
         devices = self._device_list()
-        outs = {op: torch.empty((B, N), dtype=torch.float32, pin_memory=True) for op in ops}
+        # pinned host slabs with the device slabs' padded row stride, so every D2H copy is one flat contiguous
+        # transfer; callers get the [B, N] view (each row is a contiguous float32 array)
+        ld = self._engine.row_stride(torch.float32)
+        outs = {op: torch.empty((B, ld), dtype=torch.float32, pin_memory=True) for op in ops}
         if B == 0:
-            return {op: o.numpy() for op, o in outs.items()}
+            return {op: o.numpy()[:, :N] for op, o in outs.items()}
         per = (B + len(devices) - 1) // len(devices)
         used = []
         keep = []
@@ -149,15 +152,15 @@ class ParallelTokenCharacterTrie(TokenCharacterTrie):
                         chunk = chunk.to(dev, non_blocking=True)
                     o_sum, o_max = self._engine.reduce(chunk, ops, log_input=log_input, slot=k % _PIPE_SLOTS)
                     if o_sum is not None:
-                        outs["sum"][r0:r1].copy_(o_sum, non_blocking=True)
+                        outs["sum"][r0:r1].copy_(o_sum._base[: r1 - r0], non_blocking=True)
                     if o_max is not None:
-                        outs["max"][r0:r1].copy_(o_max, non_blocking=True)
+                        outs["max"][r0:r1].copy_(o_max._base[: r1 - r0], non_blocking=True)
                     keep.append((chunk, o_sum, o_max))
             used.extend(streams)
         for st in used:
             st.synchronize()
         del keep
-        return {op: o.numpy() for op, o in outs.items()}
+        return {op: o.numpy()[:, :N] for op, o in outs.items()}
 
     def weight_sum(self, ws):
         """Node sums for one weight vector -> ``float32[num_nodes]`` (``parallel.py:77-90``)."""

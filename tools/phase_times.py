@@ -10,7 +10,7 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
     sets = 4
     base = dirichlet_rows(B, V, alpha=1.0, seed=1)
     ws = [torch.tensor(np.roll(base, k, axis=0)).cuda() for k in range(sets)]
-    osum = [torch.empty((B, N), device="cuda") for _ in range(sets)]
+    osum = [eng.alloc_out(B, torch.float32, torch.device("cuda", 0)) for _ in range(sets)]
     for k in range(sets):
         eng.reduce(ws[k], ("sum",), out_sum=osum[k])
     torch.cuda.synchronize()

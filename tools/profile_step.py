@@ -22,8 +22,8 @@ N = len(trie)
 sets = 4
 base = dirichlet_rows(args.batch, args.vocab, alpha=1.0, seed=1)
 ws = [torch.tensor(np.roll(base, k, axis=0)).cuda() for k in range(sets)]
-osum = [torch.empty((args.batch, N), device="cuda") for _ in range(sets)]
-omax = [torch.empty((args.batch, N), device="cuda") for _ in range(sets)]
+osum = [trie._engine.alloc_out(args.batch, torch.float32, torch.device("cuda", 0)) for _ in range(sets)]
+omax = [trie._engine.alloc_out(args.batch, torch.float32, torch.device("cuda", 0)) for _ in range(sets)]
 for i in range(args.steps):
     k = i % sets
     trie._engine.reduce(ws[k], ("sum", "max"), out_sum=osum[k], out_max=omax[k])
