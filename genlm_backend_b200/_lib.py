@@ -45,6 +45,7 @@ SIGNATURES = {
     "gt_get_plan_info": (c_int, [c_void_p, ctypes.POINTER(PlanInfo)]),
     "gt_plan": (c_int, [c_void_p, c_int32, c_int32, c_int32]),
     "gt_export_plan_array": (c_int64, [c_void_p, c_char_p, c_void_p, c_int64, ctypes.POINTER(c_int32)]),
+    "gt_debug_read_trace": (c_int64, [c_void_p, c_int, c_void_p, c_int64, c_void_p]),
     "gt_workspace_bytes": (c_size_t, [c_void_p, c_int64]),
     "gt_weight_reduce": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int64, c_void_p, c_void_p, c_int, c_int64,
                                  c_uint, c_uint, c_void_p, c_size_t, c_void_p]),

@@ -41,7 +41,8 @@ struct PlanView {
     const int32_t* tile_node_lo; const uint16_t* node_slot;
     const int32_t* piece_ptr; const uint16_t* piece_slot; const int32_t* piece_idx;
     int32_t n_span, n_pieces; const int32_t* span_node; const int32_t* span_pp;
-    int32_t debug_stop;  // profiling aid (GT_DEBUG_STOP): 0 = normal; k = tile_kernel returns after phase k; 9 = emit only
+    int32_t debug_stop;  // profiling aid (GT_DEBUG_STOP): 0 = normal; 3 = tile_kernel skips the emit stores; 9 = emit only
+    long long* trace;    // profiling aid (GT_TRACE=1): per (CTA, item) SM-clock stamps of the pipeline events, else null
 };
 
 struct DevicePlan {
@@ -50,6 +51,7 @@ struct DevicePlan {
     size_t blob_bytes = 0;
     PlanView view{};
     bool attrs_set = false;
+    long long* trace = nullptr;  // GT_TRACE=1 only
 };
 
 void free_device_plan(DevicePlan* d) {
@@ -59,6 +61,7 @@ void free_device_plan(DevicePlan* d) {
         cudaGetDevice(&cur);
         cudaSetDevice(d->device);
         cudaFree(d->blob);
+        if (d->trace) cudaFree(d->trace);
         cudaSetDevice(cur);
     }
     delete d;
@@ -233,16 +236,21 @@ __global__ void __launch_bounds__(kThreads) permute_kernel(PlanView P, const IN_
 
 // ---- phase 2: per-tile pyramid, multi-term ranges, emit, spanning pieces -------------------------------------
 //
-// Persistent kernel.  A work item is (tile t, row group g of R rows); items are numbered tile-major and every CTA
-// takes one contiguous run of them, so consecutive items of a CTA share the tile metadata, which stays in shared
-// memory.  Everything an item reads from global memory arrives by bulk copies (cp.async.bulk, the TMA engine)
-// issued one step ahead by one thread and tracked by three mbarriers:
-//     barrier A (armed after the scatter of item i)  staged rows of item i+1 (+ the slot table of its tile if new)
-//     barrier B (armed after the ELL phase)          ELL term rows + descriptors of the next tile, if new
-//     barrier C (armed after the emit)               emit slots of the next tile, if new
-// Each barrier is armed exactly once per item (with 0 bytes when there is nothing to fetch), so its phase parity
-// is the item parity.  In steady state no phase waits on L2/HBM latency and the only global-memory instructions
-// executed in line are the output stores.
+// Persistent, warp-specialised kernel.  A work item is (tile t, row group g of R rows); items are numbered
+// tile-major and every CTA takes one contiguous run of them, so consecutive items of a CTA share the tile metadata,
+// which stays in shared memory.  The CTA is split into two groups that run one item apart over a double-buffered
+// value array:
+//     compute warps  staged rows -> leaf slots -> pyramid -> multi-term ranges           (fill  vals[item & 1])
+//     emit warps     node-id interval of the tile -> global memory, spanning-node pieces  (drain vals[item & 1])
+// so the output stores -- the HBM-bound part -- stream continuously while the next item is being built.
+// Everything read from global memory arrives by bulk copies (cp.async.bulk, the TMA engine) issued one step ahead
+// by one thread of the group that consumes it, tracked by mbarriers:
+//     A   staged rows of the next item (+ the slot table of its tile if new)   armed after each scatter
+//     B   ELL term rows + descriptors of the next tile                         armed after the last ELL of a tile
+//     C   emit slots of the next tile                                          armed after the last emit of a tile
+//     full[2] / empty[2]   hand-over of the two value arrays between the groups
+// Every wait on A/B/C precedes a group barrier and every re-arm follows it, so no thread can still be waiting on
+// a phase when the next one completes.
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
     const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -326,22 +334,39 @@ template <typename VT, int R> struct RowVec {
 };
 
 constexpr int kTileThreads = 512;
+// trace layout: [kTraceCtas][kTraceItems][kTraceEvents] SM-clock stamps
+constexpr int kTraceCtas = 512, kTraceItems = 32, kTraceEvents = 12;
+#define GT_TRACE(ev)                                                                                         \
+    do {                                                                                                     \
+        if (P.trace && tid == 0 && blockIdx.x < kTraceCtas && k < kTraceItems)                                \
+            P.trace[((size_t)blockIdx.x * kTraceItems + k) * kTraceEvents + (ev)] = clock64();               \
+    } while (0)
+constexpr int kComputeThreads = 256;                          // warps 0..7
+constexpr int kEmitThreads = kTileThreads - kComputeThreads;  // warps 8..15
 
 // Shared-memory carve-up of tile_kernel (all sections 16-byte aligned).
 struct TileSmem {
-    size_t vals, stage, p2, slots, terms, desc, bars, total;
+    size_t vals, vals_bytes, stage, p2, slots, terms, desc, bars, total;
     __host__ __device__ TileSmem(const PlanView& P, int slot_bytes, int elem_bytes, int R) {
         size_t o = 0;
-        vals = o;  o += (size_t)(P.SV + 4) * slot_bytes;                    // value slots + trash slot
+        vals_bytes = (size_t)(P.SV + 4) * slot_bytes;                       // value slots + trash slot
+        vals = o;  o += 2 * vals_bytes;                                     // double-buffered between the groups
         stage = o; o += (size_t)R * P.max_tile_z * elem_bytes;              // staged rows of the next item
         p2 = o;    o += (size_t)P.max_tile_z * 2;                           // staged element -> value slot
         slots = o; o += (size_t)P.max_tile_nodes * 2;                       // node -> value slot (emit)
         terms = o; o += (size_t)P.max_tile_ell_rows * 64;                   // ELL term rows
         desc = o;  o += ((size_t)(P.max_tile_chunks + 2) * 8 + 15) & ~size_t(15); // ELL chunk descriptors (+ alignment slack)
-        bars = o;  o += 32;                                                 // three mbarriers
+        bars = o;  o += 64;                                                 // seven mbarriers
         total = o;
     }
 };
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* b) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((unsigned)__cvta_generic_to_shared(b)) : "memory");
+}
+template <int ID, int COUNT> __device__ __forceinline__ void group_sync() {
+    asm volatile("bar.sync %0, %1;" ::"n"(ID), "n"(COUNT) : "memory");
+}
 
 template <typename VT, int R, int OP>
 __global__ void __launch_bounds__(kTileThreads, 2) tile_kernel(PlanView P, const VT* __restrict__ z, VT* __restrict__ out,
@@ -350,183 +375,212 @@ __global__ void __launch_bounds__(kTileThreads, 2) tile_kernel(PlanView P, const
     constexpr int B = (int)sizeof(VT) * R;  // bytes per slot
     static_assert(B == 4 || B == 8 || B == 16, "slot must be 4, 8 or 16 bytes");
     constexpr int SPC = 16 / B;             // slots per 16-byte chunk
-    constexpr int kWarps = kTileThreads / 32;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const TileSmem L(P, B, (int)sizeof(VT), R);
-    VT* vals = reinterpret_cast<VT*>(smem_raw + L.vals);
     VT* stage = reinterpret_cast<VT*>(smem_raw + L.stage);
     uint16_t* s_p2 = reinterpret_cast<uint16_t*>(smem_raw + L.p2);
     uint16_t* s_slots = reinterpret_cast<uint16_t*>(smem_raw + L.slots);
     uint16_t* s_terms = reinterpret_cast<uint16_t*>(smem_raw + L.terms);
     int2* s_desc = reinterpret_cast<int2*>(smem_raw + L.desc);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + L.bars);  // [0] rows (+p2), [1] terms + desc, [2] emit slots
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + L.bars);
+    uint64_t* barA = bars;          // rows (+ p2)
+    uint64_t* barB = bars + 1;      // terms + descriptors
+    uint64_t* barC = bars + 2;      // emit slots
+    uint64_t* full = bars + 3;      // [2] value array filled by the compute group
+    uint64_t* empty = bars + 5;     // [2] value array drained by the emit group
 
     const int T = P.T;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int RG = (n_rows + R - 1) / R;
     const int n_items = P.NT * RG;
     const int i0 = (int)((int64_t)blockIdx.x * n_items / gridDim.x);
     const int i1 = (int)((int64_t)(blockIdx.x + 1) * n_items / gridDim.x);
     if (i0 >= i1) return;
     const int zpitch = P.max_tile_z;
-    const int dbg = P.debug_stop;
-    auto slot_ptr = [&](int s) { return vals + swz<B>(s) * R; };               // s < 2T, computed arithmetically
-    auto level_slot = [&](int k, int i) { return 2 * T - (T >> (k - 1)) + i; };  // level k >= 1, block i
+    const int dbg = P.debug_stop;  // profiling aid: 3 = no emit stores, 9 = emit only (compute phases skipped)
 
-    // ---- asynchronous fetches (thread 0 only) ------------------------------------------------------------------
-    // Barrier A: staged rows of item (t, g): R rows of the tile's z range, plus the tile's slot table when with_p2.
-    // Rows past the end of the batch alias the last valid row (they then compute and store exactly what that row
-    // does, which keeps every loop free of row predicates).
-    auto fetch_rows = [&](int t, int g, bool with_p2) {
-        const int zlo = __ldg(P.z_tile_off + t), zn = __ldg(P.z_tile_off + t + 1) - zlo;
-        const unsigned row_bytes = (unsigned)zn * (unsigned)sizeof(VT);
-        mbar_expect_tx(&bars[0], R * row_bytes + (with_p2 ? (unsigned)zn * 2u : 0u));
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-            const int row = min(g * R + r, n_rows - 1);
-            bulk_g2s(stage + (size_t)r * zpitch, z + (size_t)row * P.Zrow + zlo, row_bytes, &bars[0]);
-        }
-        if (with_p2) bulk_g2s(s_p2, P.p2_slot + zlo, (unsigned)zn * 2u, &bars[0]);
-    };
-    // Barrier B: ELL term rows and chunk descriptors (8 bytes each, copied from the 16-byte aligned pair at or
-    // below the first one).
-    auto fetch_terms = [&](int t) {
-        const int er0 = __ldg(P.ell_row_ptr + t), er1 = __ldg(P.ell_row_ptr + t + 1);
-        const int ec0 = __ldg(P.ell_chunk_ptr + t), ec1 = __ldg(P.ell_chunk_ptr + t + 1);
-        const int ea = ec0 & ~1;
-        const unsigned tb = (unsigned)(er1 - er0) * 64u, db = (unsigned)((ec1 - ea + 1) >> 1) * 16u;
-        mbar_expect_tx(&bars[1], tb + db);
-        if (tb) bulk_g2s(s_terms, P.ell_terms + (size_t)er0 * 32, tb, &bars[1]);
-        if (db) bulk_g2s(s_desc, P.ell_desc + ea, db, &bars[1]);
-    };
-    // Barrier C: emit slots, staged from the 16-byte aligned start at or below the tile's first node.
-    auto fetch_slots = [&](int t) {
-        const int n0 = __ldg(P.tile_node_lo + t), n1 = __ldg(P.tile_node_lo + t + 1);
-        const int na = n0 & ~7;
-        const unsigned sb = (unsigned)((n1 - na + 7) >> 3) * 16u;
-        mbar_expect_tx(&bars[2], sb);
-        bulk_g2s(s_slots, P.node_slot + na, sb, &bars[2]);
-    };
-
-    int t = i0 / RG, g = i0 - t * RG;
-    if (tid == 0) {
-        mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_init(&bars[2], 1);
+    if (threadIdx.x == 0) {
+        mbar_init(barA, 1); mbar_init(barB, 1); mbar_init(barC, 1);
+        mbar_init(full, kComputeThreads); mbar_init(full + 1, kComputeThreads);
+        mbar_init(empty, kEmitThreads); mbar_init(empty + 1, kEmitThreads);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        fetch_rows(t, g, true);
-        fetch_terms(t);
-        fetch_slots(t);
     }
-    __syncthreads();  // barriers initialised before anyone waits on them
+    __syncthreads();
 
-    int zn4 = 0, ec0 = 0, ec1 = 0, n0 = 0, n1 = 0, pc0 = 0, pc1 = 0, nleaf = 0;
-    bool new_tile = true;
-    unsigned parity = 0;
-    for (int item = i0; item < i1; ++item, parity ^= 1u) {
-        if (new_tile) {  // per-tile scalars
-            zn4 = (__ldg(P.z_tile_off + t + 1) - __ldg(P.z_tile_off + t)) >> 2;
-            ec0 = __ldg(P.ell_chunk_ptr + t); ec1 = __ldg(P.ell_chunk_ptr + t + 1);
-            n0 = __ldg(P.tile_node_lo + t); n1 = __ldg(P.tile_node_lo + t + 1);
-            pc0 = __ldg(P.piece_ptr + t); pc1 = __ldg(P.piece_ptr + t + 1);
-            nleaf = (int)min((int64_t)T, P.V - (int64_t)t * T);
-        }
-        // the item after this one
-        int tn = t, gn = g + 1;
-        if (gn == RG) { gn = 0; ++tn; }
-        const bool has_next = item + 1 < i1;
-        const bool next_new = has_next && tn != t;
+    if (threadIdx.x < kComputeThreads) {
+        // =========================== compute group ===========================================================
+        const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+        constexpr int kWarps = kComputeThreads / 32;
+        auto level_slot = [&](int k, int i) { return 2 * T - (T >> (k - 1)) + i; };  // level k >= 1, block i
 
-        // 1. staged rows -> DFS-ordered leaf slots (slot numbers in the table are already swizzled)
-        mbar_wait(&bars[0], parity);
-        __syncthreads();  // the previous item's emit has finished reading vals
-        if (dbg != 9) {
-            for (int q = tid; q < zn4; q += kTileThreads) {
-                const uint2 sl = *reinterpret_cast<const uint2*>(s_p2 + 4 * q);
-                VT v[R][4];
+        // staged rows of item (t, g) (+ the tile's slot table).  Rows past the end of the batch alias the last valid
+        // row: they compute and store exactly what that row does, which keeps every loop free of row predicates.
+        auto fetch_rows = [&](int t, int g, bool with_p2) {
+            const int zlo = __ldg(P.z_tile_off + t), zn = __ldg(P.z_tile_off + t + 1) - zlo;
+            const unsigned row_bytes = (unsigned)zn * (unsigned)sizeof(VT);
+            mbar_expect_tx(barA, R * row_bytes + (with_p2 ? (unsigned)zn * 2u : 0u));
 #pragma unroll
-                for (int r = 0; r < R; ++r) load4<VT>(stage + (size_t)r * zpitch + 4 * q, v[r][0], v[r][1], v[r][2], v[r][3]);
-                const unsigned s4[4] = {sl.x & 0xFFFFu, sl.x >> 16, sl.y & 0xFFFFu, sl.y >> 16};
+            for (int r = 0; r < R; ++r) {
+                const int row = min(g * R + r, n_rows - 1);
+                bulk_g2s(stage + (size_t)r * zpitch, z + (size_t)row * P.Zrow + zlo, row_bytes, barA);
+            }
+            if (with_p2) bulk_g2s(s_p2, P.p2_slot + zlo, (unsigned)zn * 2u, barA);
+        };
+        // ELL term rows and chunk descriptors (8 bytes each, copied from the 16-byte aligned pair at or below the
+        // first one)
+        auto fetch_terms = [&](int t) {
+            const int er0 = __ldg(P.ell_row_ptr + t), er1 = __ldg(P.ell_row_ptr + t + 1);
+            const int ec0 = __ldg(P.ell_chunk_ptr + t), ec1 = __ldg(P.ell_chunk_ptr + t + 1);
+            const int ea = ec0 & ~1;
+            const unsigned tb = (unsigned)(er1 - er0) * 64u, db = (unsigned)((ec1 - ea + 1) >> 1) * 16u;
+            mbar_expect_tx(barB, tb + db);
+            if (tb) bulk_g2s(s_terms, P.ell_terms + (size_t)er0 * 32, tb, barB);
+            if (db) bulk_g2s(s_desc, P.ell_desc + ea, db, barB);
+        };
+
+        int t = i0 / RG, g = i0 - t * RG;
+        if (tid == 0) { fetch_rows(t, g, true); fetch_terms(t); }
+        int zn4 = 0, ec0 = 0, nchunks = 0, nleaf = 0;
+        bool new_tile = true;
+        unsigned parB = 0;
+        for (int item = i0; item < i1; ++item) {
+            const int k = item - i0;
+            VT* vals = reinterpret_cast<VT*>(smem_raw + L.vals + (size_t)(k & 1) * L.vals_bytes);
+            if (new_tile) {
+                zn4 = (__ldg(P.z_tile_off + t + 1) - __ldg(P.z_tile_off + t)) >> 2;
+                ec0 = __ldg(P.ell_chunk_ptr + t); nchunks = __ldg(P.ell_chunk_ptr + t + 1) - ec0;
+                nleaf = (int)min((int64_t)T, P.V - (int64_t)t * T);
+            }
+            int tn = t, gn = g + 1;
+            if (gn == RG) { gn = 0; ++tn; }
+            const bool has_next = item + 1 < i1;
+            const bool next_new = has_next && tn != t;
+
+            // 1. staged rows -> DFS-ordered leaf slots (slot numbers in the table are already swizzled)
+            GT_TRACE(0);
+            mbar_wait(empty + (k & 1), ((unsigned)(k >> 1) & 1u) ^ 1u);  // the emit group has drained this value array
+            GT_TRACE(1);
+            mbar_wait(barA, (unsigned)k & 1u);
+            GT_TRACE(2);
+            if (dbg != 9) {
+                for (int q = tid; q < zn4; q += kComputeThreads) {
+                    const uint2 sl = *reinterpret_cast<const uint2*>(s_p2 + 4 * q);
+                    VT v[R][4];
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    RV x;
+                    for (int r = 0; r < R; ++r) load4<VT>(stage + (size_t)r * zpitch + 4 * q, v[r][0], v[r][1], v[r][2], v[r][3]);
+                    const unsigned s4[4] = {sl.x & 0xFFFFu, sl.x >> 16, sl.y & 0xFFFFu, sl.y >> 16};
 #pragma unroll
-                    for (int r = 0; r < R; ++r) x.v[r] = v[r][e];
-                    x.store(vals + s4[e] * R);
+                    for (int e = 0; e < 4; ++e) {
+                        RV x;
+#pragma unroll
+                        for (int r = 0; r < R; ++r) x.v[r] = v[r][e];
+                        x.store(vals + s4[e] * R);
+                    }
+                }
+                for (int i = nleaf + tid; i < T; i += kComputeThreads) RV::template ident<OP>().store(vals + swz<B>(i) * R);
+                if (tid == 0) RV::template ident<OP>().store(vals + swz<B>(2 * T - 1) * R);  // identity slot (ELL padding, spanning nodes)
+            }
+            group_sync<1, kComputeThreads>();
+            GT_TRACE(3);
+            // the staging buffer (and, on a tile change, the slot table) is free again: fetch the next item's rows
+            if (tid == 0) {
+                if (has_next) fetch_rows(tn, gn, next_new);
+                else mbar_expect_tx(barA, 0);
+            }
+            GT_TRACE(4);
+
+            // 2. pyramid of aligned blocks: level k block i at (swizzled) slot 2T - (T >> (k-1)) + i.
+            //    Lane u owns leaves 8u .. 8u+7: levels 1..3 in registers, 4..8 by warp shuffles (256 leaves per warp).
+            //    The swizzle makes the 16-byte chunk loads and the strided level stores bank-conflict free.
+            if (dbg != 9) {
+                for (int ub = warp * 32; ub < (T >> 3); ub += kWarps * 32) {
+                    const int u = ub + lane;
+                    RV x[8];
+#pragma unroll
+                    for (int ch = 0; ch < 8 / SPC; ++ch) {
+                        const int c = (8 * u) / SPC + ch;
+                        const int cc = c ^ ((c >> 3) & (B / 2 - 1));
+                        const float4 raw = *reinterpret_cast<const float4*>(reinterpret_cast<const unsigned char*>(vals) + (size_t)cc * 16);
+                        memcpy(&x[ch * SPC], &raw, 16);
+                    }
+                    RV a[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        a[e] = RV::template combine<OP>(x[2 * e], x[2 * e + 1]);
+                        a[e].store(vals + swz<B>(level_slot(1, 4 * u + e)) * R);
+                    }
+                    const RV c0 = RV::template combine<OP>(a[0], a[1]), c1 = RV::template combine<OP>(a[2], a[3]);
+                    c0.store(vals + swz<B>(level_slot(2, 2 * u)) * R);
+                    c1.store(vals + swz<B>(level_slot(2, 2 * u + 1)) * R);
+                    RV y = RV::template combine<OP>(c0, c1);
+                    y.store(vals + swz<B>(level_slot(3, u)) * R);
+#pragma unroll
+                    for (int j = 1; j <= 5; ++j) {
+                        y = RV::template combine<OP>(y, y.shfl_down(1 << (j - 1)));
+                        if ((lane & ((1 << j) - 1)) == 0) y.store(vals + swz<B>(level_slot(3 + j, u >> j)) * R);
+                    }
                 }
             }
-            for (int i = nleaf + tid; i < T; i += kTileThreads) RV::template ident<OP>().store(slot_ptr(i));
-            if (tid == 0) RV::template ident<OP>().store(slot_ptr(2 * T - 1));  // identity slot (ELL padding, spanning nodes)
-        }
-        __syncthreads();
-        // the staging buffer (and, on a tile change, the slot table) is free again: fetch the next item's rows
-        if (tid == 0) {
-            if (has_next) fetch_rows(tn, gn, next_new);
-            else mbar_expect_tx(&bars[0], 0);
-        }
+            GT_TRACE(5);
+            if (new_tile) { mbar_wait(barB, parB); parB ^= 1u; }  // ELL terms + descriptors of this tile
+            group_sync<1, kComputeThreads>();
+            GT_TRACE(6);
 
-        // 2. pyramid of aligned blocks: level k block i at (swizzled) slot 2T - (T >> (k-1)) + i.
-        //    Lane u owns leaves 8u .. 8u+7: levels 1..3 in registers, 4..8 by warp shuffles (256 leaves per warp).
-        //    The swizzle makes the 16-byte chunk loads and the strided level stores bank-conflict free.
-        if (dbg != 9 && dbg != 1) {
-            for (int ub = warp * 32; ub < (T >> 3); ub += kWarps * 32) {
-                const int u = ub + lane;
-                RV x[8];
+            // 3. ranges that need more than one block: ELL chunks of 32 ranges, one warp per chunk, term rows read
+            //    from shared memory (k is a multiple of 4: the planner pads rows with the identity slot)
+            if (dbg != 9) {
+                const int2* dsc = s_desc + (ec0 & 1);
+                const int er0 = dsc[0].x;  // first chunk's row offset == the tile's first term row (unused if no chunk)
+                for (int c = warp; c < nchunks; c += kWarps) {
+                    const int2 d = dsc[c];
+                    const uint16_t* tp = s_terms + (d.x - er0) * 32 + lane;
+                    RV acc = RV::template ident<OP>();
+                    for (int kb = 0; kb < d.y; kb += 4) {
+                        int sl[4];
 #pragma unroll
-                for (int ch = 0; ch < 8 / SPC; ++ch) {
-                    const int c = (8 * u) / SPC + ch;
-                    const int cc = c ^ ((c >> 3) & (B / 2 - 1));
-                    const float4 raw = *reinterpret_cast<const float4*>(reinterpret_cast<const unsigned char*>(vals) + (size_t)cc * 16);
-                    memcpy(&x[ch * SPC], &raw, 16);
-                }
-                RV a[4];
+                        for (int e = 0; e < 4; ++e) sl[e] = tp[(kb + e) * 32];
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    a[e] = RV::template combine<OP>(x[2 * e], x[2 * e + 1]);
-                    a[e].store(slot_ptr(level_slot(1, 4 * u + e)));
-                }
-                const RV c0 = RV::template combine<OP>(a[0], a[1]), c1 = RV::template combine<OP>(a[2], a[3]);
-                c0.store(slot_ptr(level_slot(2, 2 * u)));
-                c1.store(slot_ptr(level_slot(2, 2 * u + 1)));
-                RV y = RV::template combine<OP>(c0, c1);
-                y.store(slot_ptr(level_slot(3, u)));
-#pragma unroll
-                for (int j = 1; j <= 5; ++j) {
-                    y = RV::template combine<OP>(y, y.shfl_down(1 << (j - 1)));
-                    if ((lane & ((1 << j) - 1)) == 0) y.store(slot_ptr(level_slot(3 + j, u >> j)));
+                        for (int e = 0; e < 4; ++e) acc = RV::template combine<OP>(acc, RV::load(vals + sl[e] * R));
+                    }
+                    acc.store(vals + (2 * T + c * 32 + lane) * R);
                 }
             }
-        }
-        mbar_wait(&bars[1], parity);  // ELL terms + descriptors of this tile
-        __syncthreads();
-
-        // 3. ranges that need more than one block: ELL chunks of 32 ranges, one warp per chunk, term rows read from
-        //    shared memory (k is a multiple of 4: the planner pads rows with the identity slot)
-        if (dbg != 9 && dbg != 1 && dbg != 2) {
-            const int2* dsc = s_desc + (ec0 & 1);
-            const int er0 = dsc[0].x;  // first chunk's row offset == the tile's first term row (unused if no chunk)
-            for (int c = warp; c < ec1 - ec0; c += kWarps) {
-                const int2 d = dsc[c];
-                const uint16_t* tp = s_terms + (d.x - er0) * 32 + lane;
-                RV acc = RV::template ident<OP>();
-                for (int kb = 0; kb < d.y; kb += 4) {
-                    int sl[4];
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) sl[e] = tp[(kb + e) * 32];
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) acc = RV::template combine<OP>(acc, RV::load(vals + sl[e] * R));
-                }
-                acc.store(vals + (2 * T + c * 32 + lane) * R);
+            GT_TRACE(7);
+            mbar_arrive(full + (k & 1));  // this thread's share of the value array is complete
+            if (next_new) {
+                group_sync<1, kComputeThreads>();  // everyone is done with this tile's terms
+                if (tid == 0) fetch_terms(tn);
             }
+            new_tile = next_new;
+            t = tn; g = gn;
         }
-        // every wait on a barrier sits before a CTA barrier and every re-arm after it, so no thread can still be
-        // waiting on a phase when the next one completes
-        mbar_wait(&bars[2], parity);  // emit slots of this tile
-        __syncthreads();
-        if (tid == 0) {
-            if (next_new) fetch_terms(tn);
-            else mbar_expect_tx(&bars[1], 0);
-        }
+    } else {
+        // =========================== emit group ==============================================================
+        const int tid = threadIdx.x - kComputeThreads;
+        // emit slots of a tile, staged from the 16-byte aligned start at or below its first node
+        auto fetch_slots = [&](int t) {
+            const int n0 = __ldg(P.tile_node_lo + t), n1 = __ldg(P.tile_node_lo + t + 1);
+            const int na = n0 & ~7;
+            const unsigned sb = (unsigned)((n1 - na + 7) >> 3) * 16u;
+            mbar_expect_tx(barC, sb);
+            bulk_g2s(s_slots, P.node_slot + na, sb, barC);
+        };
+        int t = i0 / RG, g = i0 - t * RG;
+        if (tid == 0) fetch_slots(t);
+        int n0 = 0, n1 = 0, pc0 = 0, pc1 = 0;
+        bool new_tile = true;
+        unsigned parC = 0;
+        for (int item = i0; item < i1; ++item) {
+            const int k = item - i0;
+            const VT* vals = reinterpret_cast<const VT*>(smem_raw + L.vals + (size_t)(k & 1) * L.vals_bytes);
+            if (new_tile) {
+                n0 = __ldg(P.tile_node_lo + t); n1 = __ldg(P.tile_node_lo + t + 1);
+                pc0 = __ldg(P.piece_ptr + t); pc1 = __ldg(P.piece_ptr + t + 1);
+                mbar_wait(barC, parC); parC ^= 1u;
+            }
+            int tn = t, gn = g + 1;
+            if (gn == RG) { gn = 0; ++tn; }
+            const bool next_new = item + 1 < i1 && tn != t;
 
-        if (dbg == 0 || dbg == 9) {
             const int b0 = g * R;
             VT* orow[R];
 #pragma unroll
@@ -534,12 +588,15 @@ __global__ void __launch_bounds__(kTileThreads, 2) tile_kernel(PlanView P, const
                 orow[r] = out + (size_t)min(b0 + r, n_rows - 1) * ld_out;
                 asm volatile("" : "+l"(orow[r]));  // keep the row pointers in registers (no rematerialisation per store)
             }
-
             // 4. pieces of spanning nodes that overlap this tile (reduced by span_kernel, which runs next on the
             //    stream).  The table entries are requested first and consumed after the emit loop.
             const int pi = pc0 + tid;
             int p_slot = 0, p_idx = 0;
             if (pi < pc1) { p_slot = __ldg(P.piece_slot + pi); p_idx = __ldg(P.piece_idx + pi); }
+
+            GT_TRACE(8);
+            mbar_wait(full + (k & 1), (unsigned)(k >> 1) & 1u);  // the compute group has filled this value array
+            GT_TRACE(9);
 
             // 5. emit the tile's node-id interval: lane = consecutive node id, so the slot reads of a warp cluster on
             //    a few neighbouring slots (unary chains broadcast) and every store instruction writes 128 contiguous
@@ -547,46 +604,48 @@ __global__ void __launch_bounds__(kTileThreads, 2) tile_kernel(PlanView P, const
             //    stride that is a multiple of 32 elements every store instruction covers exactly one line.
             //    Spanning nodes inside the interval carry the identity slot: what is written for them here is
             //    overwritten by span_kernel.
-            constexpr int U = 4;
-            const int na = n0 & ~7;
-            const int lead = (int)(((reinterpret_cast<uintptr_t>(orow[0]) / sizeof(VT)) + (unsigned)n0) & 31u);
-            const unsigned count = (unsigned)(n1 - n0);
-            const uint16_t* sl_base = s_slots - na;
-            const unsigned char* vbytes = reinterpret_cast<const unsigned char*>(vals);
-            for (int nb = n0 - lead + tid; nb < n1; nb += U * kTileThreads) {
-                VT* p[R];
+            if (dbg != 3) {
+                constexpr int U = 4;
+                const int na = n0 & ~7;
+                const int lead = (int)(((reinterpret_cast<uintptr_t>(orow[0]) / sizeof(VT)) + (unsigned)n0) & 31u);
+                const unsigned count = (unsigned)(n1 - n0);
+                const uint16_t* sl_base = s_slots - na;
+                const unsigned char* vbytes = reinterpret_cast<const unsigned char*>(vals);
+                for (int nb = n0 - lead + tid; nb < n1; nb += U * kEmitThreads) {
+                    VT* p[R];
 #pragma unroll
-                for (int r = 0; r < R; ++r) p[r] = orow[r] + nb;
-                RV x[U];
-                bool ok[U];
+                    for (int r = 0; r < R; ++r) p[r] = orow[r] + nb;
+                    RV x[U];
+                    bool ok[U];
 #pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    const int n = nb + u * kTileThreads;
-                    ok[u] = (unsigned)(n - n0) < count;
-                    if (ok[u]) x[u] = RV::load(reinterpret_cast<const VT*>(vbytes + (unsigned)sl_base[n] * (unsigned)B));
-                }
-#pragma unroll
-                for (int u = 0; u < U; ++u)
-                    if (ok[u]) {
-#pragma unroll
-                        for (int r = 0; r < R; ++r) __stcs(p[r] + u * kTileThreads, x[u].v[r]);
+                    for (int u = 0; u < U; ++u) {
+                        const int n = nb + u * kEmitThreads;
+                        ok[u] = (unsigned)(n - n0) < count;
+                        if (ok[u]) x[u] = RV::load(reinterpret_cast<const VT*>(vbytes + (unsigned)sl_base[n] * (unsigned)B));
                     }
-            }
-
-            for (int i = pi; i < pc1; i += kTileThreads) {
-                if (i != pi) { p_slot = __ldg(P.piece_slot + i); p_idx = __ldg(P.piece_idx + i); }
-                const RV x = RV::load(vals + p_slot * R);
 #pragma unroll
-                for (int r = 0; r < R; ++r) part[(size_t)min(b0 + r, n_rows - 1) * P.n_pieces + p_idx] = x.v[r];
+                    for (int u = 0; u < U; ++u)
+                        if (ok[u]) {
+#pragma unroll
+                            for (int r = 0; r < R; ++r) __stcs(p[r] + u * kEmitThreads, x[u].v[r]);
+                        }
+                }
+                for (int i = pi; i < pc1; i += kEmitThreads) {
+                    if (i != pi) { p_slot = __ldg(P.piece_slot + i); p_idx = __ldg(P.piece_idx + i); }
+                    const RV x = RV::load(vals + p_slot * R);
+#pragma unroll
+                    for (int r = 0; r < R; ++r) part[(size_t)min(b0 + r, n_rows - 1) * P.n_pieces + p_idx] = x.v[r];
+                }
             }
+            GT_TRACE(10);
+            mbar_arrive(empty + (k & 1));  // this thread no longer reads the value array
+            if (next_new) {
+                group_sync<2, kEmitThreads>();  // everyone is done with this tile's emit slots
+                if (tid == 0) fetch_slots(tn);
+            }
+            new_tile = next_new;
+            t = tn; g = gn;
         }
-        if (next_new) __syncthreads();  // everyone is done with this tile's emit slots
-        if (tid == 0) {
-            if (next_new) fetch_slots(tn);
-            else mbar_expect_tx(&bars[2], 0);
-        }
-        new_tile = next_new;
-        t = tn; g = gn;
     }
 }
 
@@ -676,6 +735,16 @@ static DevicePlan* upload_plan(const Layout& L, const Plan& P, int device) {
     v.n_span = (int32_t)P.span_node.size(); v.n_pieces = P.n_pieces;
     v.span_node = (const int32_t*)(base + o_span_node); v.span_pp = (const int32_t*)(base + o_span_pp);
     { const char* e = getenv("GT_DEBUG_STOP"); v.debug_stop = e && *e ? atoi(e) : 0; }
+    v.trace = nullptr;
+    if (const char* e = getenv("GT_TRACE")) {
+        if (*e && atoi(e) != 0) {
+            const size_t bytes = (size_t)kTraceCtas * kTraceItems * kTraceEvents * sizeof(long long);
+            cudaSetDevice(device);
+            if (cudaMalloc(&d->trace, bytes) == cudaSuccess) { cudaMemset(d->trace, 0, bytes); v.trace = d->trace; }
+            else { d->trace = nullptr; (void)cudaGetLastError(); }
+            cudaSetDevice(cur);
+        }
+    }
     return d;
 }
 
@@ -768,6 +837,10 @@ static int launch_tile(const PlanView& v, const Scratch<VT>& sc, VT* out, int64_
         return GT_OK;
     }
     const size_t smem = tile_smem<VT, R>(v);
+    if (smem > 227 * 1024) {
+        set_error("tile plan needs %zu bytes of shared memory per CTA (limit 232448): use a smaller tile or fewer rows per CTA", smem);
+        return GT_ERR_LIMIT;
+    }
     GT_CUDA(allow_smem(tile_kernel<VT, R, OP>, smem));
     // persistent grid: one CTA per resident slot, each takes a contiguous run of (tile, row group) items
     const int64_t items = (int64_t)v.NT * ((rows + R - 1) / R);
@@ -868,6 +941,25 @@ int gt_get_plan_info(const gt_trie* t, gt_plan_info* info) {
     for (auto& kv : t->dev) { meta = kv.second->blob_bytes; break; }
     info->meta_bytes = (int64_t)meta;
     return GT_OK;
+}
+
+int64_t gt_debug_read_trace(const gt_trie* t, int device, long long* dst, int64_t capacity, int32_t dims[3]) {
+    if (!t) { gt::set_error("gt_debug_read_trace: null trie"); return -1; }
+    auto it = t->dev.find(device);
+    if (it == t->dev.end() || !it->second->trace) { gt::set_error("no trace buffer on device %d (set GT_TRACE=1 before gt_upload)", device); return -1; }
+    const int64_t n = (int64_t)gt::kTraceCtas * gt::kTraceItems * gt::kTraceEvents;
+    if (dims) { dims[0] = gt::kTraceCtas; dims[1] = gt::kTraceItems; dims[2] = gt::kTraceEvents; }
+    if (dst && capacity > 0) {
+        int cur = 0;
+        cudaGetDevice(&cur);
+        cudaSetDevice(device);
+        cudaDeviceSynchronize();
+        const cudaError_t e = cudaMemcpy(dst, it->second->trace, (size_t)std::min(n, capacity) * sizeof(long long), cudaMemcpyDeviceToHost);
+        cudaMemset(it->second->trace, 0, (size_t)n * sizeof(long long));
+        cudaSetDevice(cur);
+        if (e != cudaSuccess) { gt::set_error("trace copy failed: %s", cudaGetErrorString(e)); return -1; }
+    }
+    return n;
 }
 
 size_t gt_workspace_bytes(const gt_trie* t, int64_t max_rows) {

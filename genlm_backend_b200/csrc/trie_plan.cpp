@@ -25,7 +25,7 @@ static inline int ilog2(int32_t x) { int k = 0; while ((1 << (k + 1)) <= x) ++k;
 
 int build_plan(const Layout& L, int32_t T, int32_t Q, int32_t R, Plan& P) {
     const int64_t V = L.V, N = L.N;
-    if (T < 1024 || T > 8192 || (T & (T - 1))) { set_error("tile size must be a power of two in [1024, 8192]"); return GT_ERR_ARG; }
+    if ((T != 1024 && T != 2048)) { set_error("tile size must be 1024 or 2048 leaves (two value arrays of a tile must fit in shared memory)"); return GT_ERR_ARG; }
     // Q*8 bytes (one fp64 row segment) must fit in shared memory
     if (Q < 4 || Q > 16384 || (Q & 3)) { set_error("segment size must be a multiple of 4 in [4, 16384]"); return GT_ERR_ARG; }
     if (R != 2 && R != 4) { set_error("rows per CTA must be 2 or 4"); return GT_ERR_ARG; }

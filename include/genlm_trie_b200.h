@@ -101,7 +101,7 @@ typedef struct gt_plan_info {
 int gt_get_plan_info(const gt_trie* t, gt_plan_info* info);
 
 /* Host-only: build the tile plan without touching a device (gt_upload calls this with its defaults when
- * no plan exists yet).  tile_leaves: power of two in [1024, 8192]; seg_positions: multiple of 4, <= 16384;
+ * no plan exists yet).  tile_leaves: 1024 or 2048; seg_positions: multiple of 4, <= 16384;
  * rows_per_cta: 2 or 4 (rows of a batch that share one CTA of the fp32 pipeline; the fp64 pipeline uses half);
  * pass 0 for the defaults.  Fails if a plan already exists with different parameters. */
 int gt_plan(gt_trie* t, int32_t tile_leaves, int32_t seg_positions, int32_t rows_per_cta);
@@ -111,6 +111,11 @@ int gt_plan(gt_trie* t, int32_t tile_leaves, int32_t seg_positions, int32_t rows
  * node_slot piece_ptr piece_slot piece_idx span_node span_pp.  Returns the element count (or -1), and copies
  * min(count, capacity) elements into dst when dst != NULL.  elem_size receives 2 or 4. */
 int64_t gt_export_plan_array(const gt_trie* t, const char* name, void* dst, int64_t capacity, int32_t* elem_size);
+
+/* Profiling aid.  With GT_TRACE=1 in the environment at gt_upload() time, the tile kernel stamps the SM clock at
+ * its pipeline events per (CTA, item); this copies the stamps out (dims = {ctas, items, events}) and clears them.
+ * Returns the element count, or -1 when no trace buffer exists.  tools/trace_tile.py prints the phase durations. */
+int64_t gt_debug_read_trace(const gt_trie* t, int device, long long* dst, int64_t capacity, int32_t dims[3]);
 
 /* Caller-owned scratch needed for a batch of up to max_rows rows on the current device. */
 size_t gt_workspace_bytes(const gt_trie* t, int64_t max_rows);

@@ -16,8 +16,8 @@ def oracle_for(trie):
 
 
 @pytest.mark.parametrize("V,T,Q,R", [(1, 1024, 4, 2), (5, 1024, 4, 4), (700, 1024, 128, 2), (3000, 1024, 512, 4),
-                                     (3000, 2048, 8192, 2), (20011, 4096, 8192, 2), (20011, 1024, 1000, 4),
-                                     (20011, 8192, 16384, 2), (20011, 2048, 4096, 4), (50257, 2048, 4096, 4)])
+                                     (3000, 2048, 8192, 2), (20011, 2048, 8192, 2), (20011, 1024, 1000, 4),
+                                     (20011, 1024, 16384, 2), (20011, 2048, 4096, 4), (50257, 1024, 4096, 4)])
 def test_emulated_kernels_match_oracle(V, T, Q, R):
     trie = TokenCharacterTrie(synth_vocab(max(V, 256), seed=2)[-V:])
     trie._engine.plan(T, Q, R)
@@ -76,10 +76,10 @@ def test_plan_parameter_validation():
     trie = TokenCharacterTrie([Token(0, b"a")])
     from genlm_backend_b200._lib import GtError
 
-    for T, Q, R in [(1000, 8192, 2), (512, 8192, 2), (16384, 8192, 2), (4096, 6, 2), (4096, 32768, 2), (4096, 4096, 3)]:
+    for T, Q, R in [(1000, 8192, 2), (512, 8192, 2), (4096, 8192, 2), (2048, 6, 2), (2048, 32768, 2), (2048, 4096, 3)]:
         with pytest.raises(GtError):
             trie._engine.plan(T, Q, R)
     trie._engine.plan(2048, 4096, 2)
     trie._engine.plan()  # defaults resolve to the existing plan
     with pytest.raises(GtError):
-        trie._engine.plan(4096, 4096)
+        trie._engine.plan(1024, 4096)
