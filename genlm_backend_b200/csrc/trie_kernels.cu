@@ -236,21 +236,17 @@ __global__ void __launch_bounds__(kThreads) permute_kernel(PlanView P, const IN_
 
 // ---- phase 2: per-tile pyramid, multi-term ranges, emit, spanning pieces -------------------------------------
 //
-// Persistent, warp-specialised kernel.  A work item is (tile t, row group g of R rows); items are numbered
-// tile-major and every CTA takes one contiguous run of them, so consecutive items of a CTA share the tile metadata,
-// which stays in shared memory.  The CTA is split into two groups that run one item apart over a double-buffered
-// value array:
-//     compute warps  staged rows -> leaf slots -> pyramid -> multi-term ranges           (fill  vals[item & 1])
-//     emit warps     node-id interval of the tile -> global memory, spanning-node pieces  (drain vals[item & 1])
-// so the output stores -- the HBM-bound part -- stream continuously while the next item is being built.
-// Everything read from global memory arrives by bulk copies (cp.async.bulk, the TMA engine) issued one step ahead
-// by one thread of the group that consumes it, tracked by mbarriers:
-//     A   staged rows of the next item (+ the slot table of its tile if new)   armed after each scatter
-//     B   ELL term rows + descriptors of the next tile                         armed after the last ELL of a tile
-//     C   emit slots of the next tile                                          armed after the last emit of a tile
-//     full[2] / empty[2]   hand-over of the two value arrays between the groups
-// Every wait on A/B/C precedes a group barrier and every re-arm follows it, so no thread can still be waiting on
-// a phase when the next one completes.
+// Persistent kernel.  A work item is (tile t, row group g of R rows); items are numbered tile-major and every CTA
+// takes one contiguous run of them, so consecutive items of a CTA share the tile metadata, which stays in shared
+// memory.  All bulk traffic to and from global memory goes through the copy engine (cp.async.bulk, TMA), issued by
+// one thread, so the LSU pipes only ever see shared-memory work and its latency stays low:
+//     in   barrier A  staged rows of the next item (+ the slot table of its tile if new)   armed after each scatter
+//          barrier B  ELL term rows + descriptors of the next tile                         armed after the last ELL of a tile
+//          barrier C  emit slots of the next tile                                          armed after the last emit of a tile
+//     out  the tile's node-id interval is gathered into row-major staging chunks (two buffers) and written by bulk
+//          stores (bulk async-groups); only the few nodes outside the 16-byte aligned core use plain stores.
+// Every wait on A/B/C precedes a CTA barrier and every re-arm follows it, so no thread can still be waiting on a
+// phase when the next one completes.
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
     const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -334,39 +330,44 @@ template <typename VT, int R> struct RowVec {
 };
 
 constexpr int kTileThreads = 512;
+constexpr int kOutStageBytes = 16384;  // one output staging buffer (R rows x C nodes)
 // trace layout: [kTraceCtas][kTraceItems][kTraceEvents] SM-clock stamps
-constexpr int kTraceCtas = 512, kTraceItems = 32, kTraceEvents = 12;
+constexpr int kTraceCtas = 512, kTraceItems = 32, kTraceEvents = 24;
 #define GT_TRACE(ev)                                                                                         \
     do {                                                                                                     \
         if (P.trace && tid == 0 && blockIdx.x < kTraceCtas && k < kTraceItems)                                \
             P.trace[((size_t)blockIdx.x * kTraceItems + k) * kTraceEvents + (ev)] = clock64();               \
     } while (0)
-constexpr int kComputeThreads = 256;                          // warps 0..7
-constexpr int kEmitThreads = kTileThreads - kComputeThreads;  // warps 8..15
 
 // Shared-memory carve-up of tile_kernel (all sections 16-byte aligned).
 struct TileSmem {
-    size_t vals, vals_bytes, stage, p2, slots, terms, desc, bars, total;
+    size_t vals, stage, p2, slots, terms, desc, ostage, bars, total;
     __host__ __device__ TileSmem(const PlanView& P, int slot_bytes, int elem_bytes, int R) {
         size_t o = 0;
-        vals_bytes = (size_t)(P.SV + 4) * slot_bytes;                       // value slots + trash slot
-        vals = o;  o += 2 * vals_bytes;                                     // double-buffered between the groups
+        vals = o;  o += (size_t)(P.SV + 4) * slot_bytes;                    // value slots + trash slot
         stage = o; o += (size_t)R * P.max_tile_z * elem_bytes;              // staged rows of the next item
         p2 = o;    o += (size_t)P.max_tile_z * 2;                           // staged element -> value slot
         slots = o; o += (size_t)P.max_tile_nodes * 2;                       // node -> value slot (emit)
         terms = o; o += (size_t)P.max_tile_ell_rows * 64;                   // ELL term rows
         desc = o;  o += ((size_t)(P.max_tile_chunks + 2) * 8 + 15) & ~size_t(15); // ELL chunk descriptors (+ alignment slack)
-        bars = o;  o += 64;                                                 // seven mbarriers
+        ostage = o; o += 2 * (size_t)kOutStageBytes;                        // output staging, two buffers
+        bars = o;  o += 32;                                                 // three mbarriers
         total = o;
     }
 };
 
-__device__ __forceinline__ void mbar_arrive(uint64_t* b) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((unsigned)__cvta_generic_to_shared(b)) : "memory");
+// bulk store shared -> global (bulk async-group completion); bytes multiple of 16, both addresses 16-byte aligned
+__device__ __forceinline__ void bulk_s2g(void* gdst, const void* smem_src, unsigned bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst),
+                 "r"((unsigned)__cvta_generic_to_shared(smem_src)), "r"(bytes)
+                 : "memory");
 }
-template <int ID, int COUNT> __device__ __forceinline__ void group_sync() {
-    asm volatile("bar.sync %0, %1;" ::"n"(ID), "n"(COUNT) : "memory");
-}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all bulk stores of this thread have finished READING shared memory (the buffers may be rewritten)
+__device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// make this thread's shared-memory writes visible to the copy engine (async proxy)
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 template <typename VT, int R, int OP>
 __global__ void __launch_bounds__(kTileThreads, 2) tile_kernel(PlanView P, const VT* __restrict__ z, VT* __restrict__ out,
@@ -375,278 +376,268 @@ __global__ void __launch_bounds__(kTileThreads, 2) tile_kernel(PlanView P, const
     constexpr int B = (int)sizeof(VT) * R;  // bytes per slot
     static_assert(B == 4 || B == 8 || B == 16, "slot must be 4, 8 or 16 bytes");
     constexpr int SPC = 16 / B;             // slots per 16-byte chunk
+    constexpr int kWarps = kTileThreads / 32;
+    constexpr int C = kOutStageBytes / B;   // nodes per output staging buffer
+    constexpr int AL = 16 / (int)sizeof(VT);  // nodes per 16 bytes of an output row
+    constexpr int kIssueTid = kTileThreads - 32;          // lane 0 of the last warp issues the input fetches
+    constexpr int kStoreWarp0 = kWarps - R;               // lane 0 of warps kStoreWarp0 + r issues the stores of row r
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const TileSmem L(P, B, (int)sizeof(VT), R);
+    VT* vals = reinterpret_cast<VT*>(smem_raw + L.vals);
     VT* stage = reinterpret_cast<VT*>(smem_raw + L.stage);
     uint16_t* s_p2 = reinterpret_cast<uint16_t*>(smem_raw + L.p2);
     uint16_t* s_slots = reinterpret_cast<uint16_t*>(smem_raw + L.slots);
     uint16_t* s_terms = reinterpret_cast<uint16_t*>(smem_raw + L.terms);
     int2* s_desc = reinterpret_cast<int2*>(smem_raw + L.desc);
+    VT* ostage = reinterpret_cast<VT*>(smem_raw + L.ostage);  // [2][R][C]
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + L.bars);
-    uint64_t* barA = bars;          // rows (+ p2)
-    uint64_t* barB = bars + 1;      // terms + descriptors
-    uint64_t* barC = bars + 2;      // emit slots
-    uint64_t* full = bars + 3;      // [2] value array filled by the compute group
-    uint64_t* empty = bars + 5;     // [2] value array drained by the emit group
+    uint64_t* barA = bars;      // rows (+ p2)
+    uint64_t* barB = bars + 1;  // terms + descriptors
+    uint64_t* barC = bars + 2;  // emit slots
 
     const int T = P.T;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int RG = (n_rows + R - 1) / R;
     const int n_items = P.NT * RG;
     const int i0 = (int)((int64_t)blockIdx.x * n_items / gridDim.x);
     const int i1 = (int)((int64_t)(blockIdx.x + 1) * n_items / gridDim.x);
     if (i0 >= i1) return;
     const int zpitch = P.max_tile_z;
-    const int dbg = P.debug_stop;  // profiling aid: 3 = no emit stores, 9 = emit only (compute phases skipped)
+    const int dbg = P.debug_stop;  // profiling aid: 3 = no output, 9 = output only (compute phases skipped)
+    // bulk stores need 16-byte aligned rows; otherwise every node takes the plain-store path
+    const bool bulk_ok = ((ld_out * (int64_t)sizeof(VT)) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+    auto level_slot = [&](int k, int i) { return 2 * T - (T >> (k - 1)) + i; };  // level k >= 1, block i
 
-    if (threadIdx.x == 0) {
+    // Boundaries of the current tile (index 0..1) and the next one (1..2) in the four per-tile prefix arrays; the
+    // next tile's are loaded one tile ahead so that no fetch waits for them.
+    int zb[3], erb[3], ecb[3], nb3[3];
+    auto load_bound = [&](int t, int j) {
+        const int tt = min(t, P.NT);
+        zb[j] = __ldg(P.z_tile_off + tt); erb[j] = __ldg(P.ell_row_ptr + tt);
+        ecb[j] = __ldg(P.ell_chunk_ptr + tt); nb3[j] = __ldg(P.tile_node_lo + tt);
+    };
+
+    // ---- asynchronous fetches (thread 0) -----------------------------------------------------------------------
+    // Rows past the end of the batch alias the last valid row: they compute exactly what that row does, which keeps
+    // every loop free of row predicates; their output is not stored.
+    auto fetch_rows = [&](int g, int zlo, int zn, bool with_p2) {
+        const unsigned row_bytes = (unsigned)zn * (unsigned)sizeof(VT);
+        mbar_expect_tx(barA, R * row_bytes + (with_p2 ? (unsigned)zn * 2u : 0u));
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int row = min(g * R + r, n_rows - 1);
+            bulk_g2s(stage + (size_t)r * zpitch, z + (size_t)row * P.Zrow + zlo, row_bytes, barA);
+        }
+        if (with_p2) bulk_g2s(s_p2, P.p2_slot + zlo, (unsigned)zn * 2u, barA);
+    };
+    // ELL term rows and chunk descriptors (8 bytes each, copied from the 16-byte aligned pair at or below the first)
+    auto fetch_terms = [&](int er0, int er1, int ec0, int ec1) {
+        const int ea = ec0 & ~1;
+        const unsigned tb = (unsigned)(er1 - er0) * 64u, db = (unsigned)((ec1 - ea + 1) >> 1) * 16u;
+        mbar_expect_tx(barB, tb + db);
+        if (tb) bulk_g2s(s_terms, P.ell_terms + (size_t)er0 * 32, tb, barB);
+        if (db) bulk_g2s(s_desc, P.ell_desc + ea, db, barB);
+    };
+    // emit slots, staged from the 16-byte aligned start at or below the tile's first node
+    auto fetch_slots = [&](int n0, int n1) {
+        const int na = n0 & ~7;
+        const unsigned sb = (unsigned)((n1 - na + 7) >> 3) * 16u;
+        mbar_expect_tx(barC, sb);
+        bulk_g2s(s_slots, P.node_slot + na, sb, barC);
+    };
+
+    int t = i0 / RG, g = i0 - t * RG;
+    load_bound(t, 0); load_bound(t + 1, 1); load_bound(t + 2, 2);
+    if (tid == 0) {
         mbar_init(barA, 1); mbar_init(barB, 1); mbar_init(barC, 1);
-        mbar_init(full, kComputeThreads); mbar_init(full + 1, kComputeThreads);
-        mbar_init(empty, kEmitThreads); mbar_init(empty + 1, kEmitThreads);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        fetch_rows(g, zb[0], zb[1] - zb[0], true);
+        fetch_terms(erb[0], erb[1], ecb[0], ecb[1]);
+        fetch_slots(nb3[0], nb3[1]);
     }
-    __syncthreads();
+    __syncthreads();  // barriers initialised before anyone waits on them
 
-    if (threadIdx.x < kComputeThreads) {
-        // =========================== compute group ===========================================================
-        const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-        constexpr int kWarps = kComputeThreads / 32;
-        auto level_slot = [&](int k, int i) { return 2 * T - (T >> (k - 1)) + i; };  // level k >= 1, block i
-
-        // staged rows of item (t, g) (+ the tile's slot table).  Rows past the end of the batch alias the last valid
-        // row: they compute and store exactly what that row does, which keeps every loop free of row predicates.
-        auto fetch_rows = [&](int t, int g, bool with_p2) {
-            const int zlo = __ldg(P.z_tile_off + t), zn = __ldg(P.z_tile_off + t + 1) - zlo;
-            const unsigned row_bytes = (unsigned)zn * (unsigned)sizeof(VT);
-            mbar_expect_tx(barA, R * row_bytes + (with_p2 ? (unsigned)zn * 2u : 0u));
-#pragma unroll
-            for (int r = 0; r < R; ++r) {
-                const int row = min(g * R + r, n_rows - 1);
-                bulk_g2s(stage + (size_t)r * zpitch, z + (size_t)row * P.Zrow + zlo, row_bytes, barA);
-            }
-            if (with_p2) bulk_g2s(s_p2, P.p2_slot + zlo, (unsigned)zn * 2u, barA);
-        };
-        // ELL term rows and chunk descriptors (8 bytes each, copied from the 16-byte aligned pair at or below the
-        // first one)
-        auto fetch_terms = [&](int t) {
-            const int er0 = __ldg(P.ell_row_ptr + t), er1 = __ldg(P.ell_row_ptr + t + 1);
-            const int ec0 = __ldg(P.ell_chunk_ptr + t), ec1 = __ldg(P.ell_chunk_ptr + t + 1);
-            const int ea = ec0 & ~1;
-            const unsigned tb = (unsigned)(er1 - er0) * 64u, db = (unsigned)((ec1 - ea + 1) >> 1) * 16u;
-            mbar_expect_tx(barB, tb + db);
-            if (tb) bulk_g2s(s_terms, P.ell_terms + (size_t)er0 * 32, tb, barB);
-            if (db) bulk_g2s(s_desc, P.ell_desc + ea, db, barB);
-        };
-
-        int t = i0 / RG, g = i0 - t * RG;
-        if (tid == 0) { fetch_rows(t, g, true); fetch_terms(t); }
-        int zn4 = 0, ec0 = 0, nchunks = 0, nleaf = 0;
-        bool new_tile = true;
-        unsigned parB = 0;
-        for (int item = i0; item < i1; ++item) {
-            const int k = item - i0;
-            VT* vals = reinterpret_cast<VT*>(smem_raw + L.vals + (size_t)(k & 1) * L.vals_bytes);
-            if (new_tile) {
-                zn4 = (__ldg(P.z_tile_off + t + 1) - __ldg(P.z_tile_off + t)) >> 2;
-                ec0 = __ldg(P.ell_chunk_ptr + t); nchunks = __ldg(P.ell_chunk_ptr + t + 1) - ec0;
-                nleaf = (int)min((int64_t)T, P.V - (int64_t)t * T);
-            }
-            int tn = t, gn = g + 1;
-            if (gn == RG) { gn = 0; ++tn; }
-            const bool has_next = item + 1 < i1;
-            const bool next_new = has_next && tn != t;
-
-            // 1. staged rows -> DFS-ordered leaf slots (slot numbers in the table are already swizzled)
-            GT_TRACE(0);
-            mbar_wait(empty + (k & 1), ((unsigned)(k >> 1) & 1u) ^ 1u);  // the emit group has drained this value array
-            GT_TRACE(1);
-            mbar_wait(barA, (unsigned)k & 1u);
-            GT_TRACE(2);
-            if (dbg != 9) {
-                for (int q = tid; q < zn4; q += kComputeThreads) {
-                    const uint2 sl = *reinterpret_cast<const uint2*>(s_p2 + 4 * q);
-                    VT v[R][4];
-#pragma unroll
-                    for (int r = 0; r < R; ++r) load4<VT>(stage + (size_t)r * zpitch + 4 * q, v[r][0], v[r][1], v[r][2], v[r][3]);
-                    const unsigned s4[4] = {sl.x & 0xFFFFu, sl.x >> 16, sl.y & 0xFFFFu, sl.y >> 16};
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        RV x;
-#pragma unroll
-                        for (int r = 0; r < R; ++r) x.v[r] = v[r][e];
-                        x.store(vals + s4[e] * R);
-                    }
-                }
-                for (int i = nleaf + tid; i < T; i += kComputeThreads) RV::template ident<OP>().store(vals + swz<B>(i) * R);
-                if (tid == 0) RV::template ident<OP>().store(vals + swz<B>(2 * T - 1) * R);  // identity slot (ELL padding, spanning nodes)
-            }
-            group_sync<1, kComputeThreads>();
-            GT_TRACE(3);
-            // the staging buffer (and, on a tile change, the slot table) is free again: fetch the next item's rows
-            if (tid == 0) {
-                if (has_next) fetch_rows(tn, gn, next_new);
-                else mbar_expect_tx(barA, 0);
-            }
-            GT_TRACE(4);
-
-            // 2. pyramid of aligned blocks: level k block i at (swizzled) slot 2T - (T >> (k-1)) + i.
-            //    Lane u owns leaves 8u .. 8u+7: levels 1..3 in registers, 4..8 by warp shuffles (256 leaves per warp).
-            //    The swizzle makes the 16-byte chunk loads and the strided level stores bank-conflict free.
-            if (dbg != 9) {
-                for (int ub = warp * 32; ub < (T >> 3); ub += kWarps * 32) {
-                    const int u = ub + lane;
-                    RV x[8];
-#pragma unroll
-                    for (int ch = 0; ch < 8 / SPC; ++ch) {
-                        const int c = (8 * u) / SPC + ch;
-                        const int cc = c ^ ((c >> 3) & (B / 2 - 1));
-                        const float4 raw = *reinterpret_cast<const float4*>(reinterpret_cast<const unsigned char*>(vals) + (size_t)cc * 16);
-                        memcpy(&x[ch * SPC], &raw, 16);
-                    }
-                    RV a[4];
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        a[e] = RV::template combine<OP>(x[2 * e], x[2 * e + 1]);
-                        a[e].store(vals + swz<B>(level_slot(1, 4 * u + e)) * R);
-                    }
-                    const RV c0 = RV::template combine<OP>(a[0], a[1]), c1 = RV::template combine<OP>(a[2], a[3]);
-                    c0.store(vals + swz<B>(level_slot(2, 2 * u)) * R);
-                    c1.store(vals + swz<B>(level_slot(2, 2 * u + 1)) * R);
-                    RV y = RV::template combine<OP>(c0, c1);
-                    y.store(vals + swz<B>(level_slot(3, u)) * R);
-#pragma unroll
-                    for (int j = 1; j <= 5; ++j) {
-                        y = RV::template combine<OP>(y, y.shfl_down(1 << (j - 1)));
-                        if ((lane & ((1 << j) - 1)) == 0) y.store(vals + swz<B>(level_slot(3 + j, u >> j)) * R);
-                    }
-                }
-            }
-            GT_TRACE(5);
-            if (new_tile) { mbar_wait(barB, parB); parB ^= 1u; }  // ELL terms + descriptors of this tile
-            group_sync<1, kComputeThreads>();
-            GT_TRACE(6);
-
-            // 3. ranges that need more than one block: ELL chunks of 32 ranges, one warp per chunk, term rows read
-            //    from shared memory (k is a multiple of 4: the planner pads rows with the identity slot)
-            if (dbg != 9) {
-                const int2* dsc = s_desc + (ec0 & 1);
-                const int er0 = dsc[0].x;  // first chunk's row offset == the tile's first term row (unused if no chunk)
-                for (int c = warp; c < nchunks; c += kWarps) {
-                    const int2 d = dsc[c];
-                    const uint16_t* tp = s_terms + (d.x - er0) * 32 + lane;
-                    RV acc = RV::template ident<OP>();
-                    for (int kb = 0; kb < d.y; kb += 4) {
-                        int sl[4];
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) sl[e] = tp[(kb + e) * 32];
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) acc = RV::template combine<OP>(acc, RV::load(vals + sl[e] * R));
-                    }
-                    acc.store(vals + (2 * T + c * 32 + lane) * R);
-                }
-            }
-            GT_TRACE(7);
-            mbar_arrive(full + (k & 1));  // this thread's share of the value array is complete
-            if (next_new) {
-                group_sync<1, kComputeThreads>();  // everyone is done with this tile's terms
-                if (tid == 0) fetch_terms(tn);
-            }
-            new_tile = next_new;
-            t = tn; g = gn;
+    bool new_tile = true;
+    unsigned parBC = 0;
+    int pc0 = 0, pc1 = 0, my_pslot = 0, my_pidx = 0;
+    for (int item = i0; item < i1; ++item) {
+        const int k = item - i0;
+        if (new_tile) {  // this thread's spanning-node piece of the tile, requested a whole item before its first use
+            pc0 = __ldg(P.piece_ptr + t); pc1 = __ldg(P.piece_ptr + t + 1);
+            if (pc0 + tid < pc1) { my_pslot = __ldg(P.piece_slot + pc0 + tid); my_pidx = __ldg(P.piece_idx + pc0 + tid); }
         }
-    } else {
-        // =========================== emit group ==============================================================
-        const int tid = threadIdx.x - kComputeThreads;
-        // emit slots of a tile, staged from the 16-byte aligned start at or below its first node
-        auto fetch_slots = [&](int t) {
-            const int n0 = __ldg(P.tile_node_lo + t), n1 = __ldg(P.tile_node_lo + t + 1);
-            const int na = n0 & ~7;
-            const unsigned sb = (unsigned)((n1 - na + 7) >> 3) * 16u;
-            mbar_expect_tx(barC, sb);
-            bulk_g2s(s_slots, P.node_slot + na, sb, barC);
-        };
-        int t = i0 / RG, g = i0 - t * RG;
-        if (tid == 0) fetch_slots(t);
-        int n0 = 0, n1 = 0, pc0 = 0, pc1 = 0;
-        bool new_tile = true;
-        unsigned parC = 0;
-        for (int item = i0; item < i1; ++item) {
-            const int k = item - i0;
-            const VT* vals = reinterpret_cast<const VT*>(smem_raw + L.vals + (size_t)(k & 1) * L.vals_bytes);
-            if (new_tile) {
-                n0 = __ldg(P.tile_node_lo + t); n1 = __ldg(P.tile_node_lo + t + 1);
-                pc0 = __ldg(P.piece_ptr + t); pc1 = __ldg(P.piece_ptr + t + 1);
-                mbar_wait(barC, parC); parC ^= 1u;
-            }
-            int tn = t, gn = g + 1;
-            if (gn == RG) { gn = 0; ++tn; }
-            const bool next_new = item + 1 < i1 && tn != t;
+        int tn = t, gn = g + 1;
+        if (gn == RG) { gn = 0; ++tn; }
+        const bool has_next = item + 1 < i1;
+        const bool next_new = has_next && tn != t;
+        const int n0 = nb3[0], n1 = nb3[1];
 
+        // 1. staged rows -> DFS-ordered leaf slots (slot numbers in the table are already swizzled)
+        GT_TRACE(0);
+        mbar_wait(barA, (unsigned)k & 1u);
+        GT_TRACE(1);
+        if (dbg != 9) {
+            const int zn4 = (zb[1] - zb[0]) >> 2;
+            for (int q = tid; q < zn4; q += kTileThreads) {
+                const uint2 sl = *reinterpret_cast<const uint2*>(s_p2 + 4 * q);
+                VT v[R][4];
+#pragma unroll
+                for (int r = 0; r < R; ++r) load4<VT>(stage + (size_t)r * zpitch + 4 * q, v[r][0], v[r][1], v[r][2], v[r][3]);
+                const unsigned s4[4] = {sl.x & 0xFFFFu, sl.x >> 16, sl.y & 0xFFFFu, sl.y >> 16};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    RV x;
+#pragma unroll
+                    for (int r = 0; r < R; ++r) x.v[r] = v[r][e];
+                    x.store(vals + s4[e] * R);
+                }
+            }
+            const int nleaf = (int)min((int64_t)T, P.V - (int64_t)t * T);
+            for (int i = nleaf + tid; i < T; i += kTileThreads) RV::template ident<OP>().store(vals + swz<B>(i) * R);
+            if (tid == 0) RV::template ident<OP>().store(vals + swz<B>(2 * T - 1) * R);  // identity slot (ELL padding, spanning nodes)
+        }
+        __syncthreads();
+        GT_TRACE(2);
+        // the staging buffer (and, on a tile change, the slot table) is free again: fetch the next item's rows
+        // (issued by a warp that has no share of the pyramid, so nobody waits for the issue latency)
+        if (tid == kIssueTid) {
+            if (has_next) fetch_rows(gn, next_new ? zb[1] : zb[0], next_new ? zb[2] - zb[1] : zb[1] - zb[0], next_new);
+            else mbar_expect_tx(barA, 0);
+        }
+        GT_TRACE(3);
+
+        // 2. pyramid of aligned blocks: level k block i at (swizzled) slot 2T - (T >> (k-1)) + i.
+        //    Lane u owns leaves 8u .. 8u+7: levels 1..3 in registers, 4..8 by warp shuffles (256 leaves per warp).
+        //    The swizzle makes the 16-byte chunk loads and the strided level stores bank-conflict free.
+        if (dbg != 9) {
+            for (int ub = warp * 32; ub < (T >> 3); ub += kWarps * 32) {
+                const int u = ub + lane;
+                RV x[8];
+#pragma unroll
+                for (int ch = 0; ch < 8 / SPC; ++ch) {
+                    const int c = (8 * u) / SPC + ch;
+                    const int cc = c ^ ((c >> 3) & (B / 2 - 1));
+                    const float4 raw = *reinterpret_cast<const float4*>(reinterpret_cast<const unsigned char*>(vals) + (size_t)cc * 16);
+                    memcpy(&x[ch * SPC], &raw, 16);
+                }
+                RV a[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    a[e] = RV::template combine<OP>(x[2 * e], x[2 * e + 1]);
+                    a[e].store(vals + swz<B>(level_slot(1, 4 * u + e)) * R);
+                }
+                const RV c0 = RV::template combine<OP>(a[0], a[1]), c1 = RV::template combine<OP>(a[2], a[3]);
+                c0.store(vals + swz<B>(level_slot(2, 2 * u)) * R);
+                c1.store(vals + swz<B>(level_slot(2, 2 * u + 1)) * R);
+                RV y = RV::template combine<OP>(c0, c1);
+                y.store(vals + swz<B>(level_slot(3, u)) * R);
+#pragma unroll
+                for (int j = 1; j <= 5; ++j) {
+                    y = RV::template combine<OP>(y, y.shfl_down(1 << (j - 1)));
+                    if ((lane & ((1 << j) - 1)) == 0) y.store(vals + swz<B>(level_slot(3 + j, u >> j)) * R);
+                }
+            }
+        }
+        if (new_tile) mbar_wait(barB, parBC);  // ELL terms + descriptors of this tile
+        __syncthreads();
+        GT_TRACE(4);
+
+        // 3. ranges that need more than one block: ELL chunks of 32 ranges, one warp per chunk, term rows read from
+        //    shared memory (k is a multiple of 4: the planner pads rows with the identity slot)
+        if (dbg != 9) {
+            const int2* dsc = s_desc + (ecb[0] & 1);
+            const int nchunks = ecb[1] - ecb[0];
+            for (int c = warp; c < nchunks; c += kWarps) {
+                const int2 d = dsc[c];
+                const uint16_t* tp = s_terms + (d.x - erb[0]) * 32 + lane;
+                RV acc = RV::template ident<OP>();
+                for (int kb = 0; kb < d.y; kb += 4) {
+                    int sl[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) sl[e] = tp[(kb + e) * 32];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) acc = RV::template combine<OP>(acc, RV::load(vals + sl[e] * R));
+                }
+                acc.store(vals + (2 * T + c * 32 + lane) * R);
+            }
+        }
+        if (new_tile) { mbar_wait(barC, parBC); parBC ^= 1u; }  // emit slots of this tile
+        GT_TRACE(22);
+        // the previous item's output chunks have left both staging buffers (each issuing thread checks its own stores)
+        if (lane == 0 && warp >= kStoreWarp0) bulk_wait_read_all();
+        __syncthreads();
+        GT_TRACE(5);
+        if (tid == 0 && next_new) fetch_terms(erb[1], erb[2], ecb[1], ecb[2]);
+
+        // 4. output.  Core = the 16-byte aligned part [n0a, n1a) of the tile's node-id interval: gathered into
+        //    row-major staging chunks (lane = consecutive node id, so the slot reads of a warp cluster on a few
+        //    neighbouring slots -- unary chains broadcast -- and the staging writes are conflict-free), then
+        //    written by one bulk store per row and chunk.  Spanning nodes inside the interval carry the identity
+        //    slot: what is written for them here is overwritten by span_kernel.
+        if (dbg != 3) {
             const int b0 = g * R;
-            VT* orow[R];
+            const int nrows_here = min(R, n_rows - b0);
+            const uint16_t* sl_base = s_slots - (n0 & ~7);
+            const int n0a = bulk_ok ? min(n1, (n0 + AL - 1) & ~(AL - 1)) : n1;
+            const int n1a = bulk_ok ? max(n0a, n1 & ~(AL - 1)) : n1;
+            // nodes outside the aligned core, and the pieces of spanning nodes that overlap this tile (reduced by
+            // span_kernel, which runs next on the stream): plain stores
+            auto store_node = [&](int n) {
+                const RV x = RV::load(vals + (int)sl_base[n] * R);
 #pragma unroll
-            for (int r = 0; r < R; ++r) {
-                orow[r] = out + (size_t)min(b0 + r, n_rows - 1) * ld_out;
-                asm volatile("" : "+l"(orow[r]));  // keep the row pointers in registers (no rematerialisation per store)
+                for (int r = 0; r < R; ++r)
+                    if (r < nrows_here) out[(size_t)(b0 + r) * ld_out + n] = x.v[r];
+            };
+            for (int n = n0 + tid; n < n0a; n += kTileThreads) store_node(n);  // head (everything when !bulk_ok)
+            for (int n = n1a + tid; n < n1; n += kTileThreads) store_node(n);  // tail
+            for (int i = pc0 + tid; i < pc1; i += kTileThreads) {
+                const bool mine = i == pc0 + tid;
+                const RV x = RV::load(vals + (mine ? my_pslot : (int)__ldg(P.piece_slot + i)) * R);
+                const int idx = mine ? my_pidx : __ldg(P.piece_idx + i);
+#pragma unroll
+                for (int r = 0; r < R; ++r)
+                    if (r < nrows_here) part[(size_t)(b0 + r) * P.n_pieces + idx] = x.v[r];
             }
-            // 4. pieces of spanning nodes that overlap this tile (reduced by span_kernel, which runs next on the
-            //    stream).  The table entries are requested first and consumed after the emit loop.
-            const int pi = pc0 + tid;
-            int p_slot = 0, p_idx = 0;
-            if (pi < pc1) { p_slot = __ldg(P.piece_slot + pi); p_idx = __ldg(P.piece_idx + pi); }
-
-            GT_TRACE(8);
-            mbar_wait(full + (k & 1), (unsigned)(k >> 1) & 1u);  // the compute group has filled this value array
-            GT_TRACE(9);
-
-            // 5. emit the tile's node-id interval: lane = consecutive node id, so the slot reads of a warp cluster on
-            //    a few neighbouring slots (unary chains broadcast) and every store instruction writes 128 contiguous
-            //    bytes per row.  The sweep starts at the 128-byte line of row 0 that holds node n0, so with a row
-            //    stride that is a multiple of 32 elements every store instruction covers exactly one line.
-            //    Spanning nodes inside the interval carry the identity slot: what is written for them here is
-            //    overwritten by span_kernel.
-            if (dbg != 3) {
-                constexpr int U = 4;
-                const int na = n0 & ~7;
-                const int lead = (int)(((reinterpret_cast<uintptr_t>(orow[0]) / sizeof(VT)) + (unsigned)n0) & 31u);
-                const unsigned count = (unsigned)(n1 - n0);
-                const uint16_t* sl_base = s_slots - na;
-                const unsigned char* vbytes = reinterpret_cast<const unsigned char*>(vals);
-                for (int nb = n0 - lead + tid; nb < n1; nb += U * kEmitThreads) {
-                    VT* p[R];
+            GT_TRACE(6);
+            int buf = 0, ci = 0;
+            for (int cs = n0a; cs < n1a; cs += C, buf ^= 1, ++ci) {
+                const int cn = min(C, n1a - cs);
+                VT* ob = ostage + (size_t)buf * R * C;
+                for (int i = tid; i < cn; i += kTileThreads) {
+                    const RV x = RV::load(vals + (int)sl_base[cs + i] * R);
 #pragma unroll
-                    for (int r = 0; r < R; ++r) p[r] = orow[r] + nb;
-                    RV x[U];
-                    bool ok[U];
-#pragma unroll
-                    for (int u = 0; u < U; ++u) {
-                        const int n = nb + u * kEmitThreads;
-                        ok[u] = (unsigned)(n - n0) < count;
-                        if (ok[u]) x[u] = RV::load(reinterpret_cast<const VT*>(vbytes + (unsigned)sl_base[n] * (unsigned)B));
-                    }
-#pragma unroll
-                    for (int u = 0; u < U; ++u)
-                        if (ok[u]) {
-#pragma unroll
-                            for (int r = 0; r < R; ++r) __stcs(p[r] + u * kEmitThreads, x[u].v[r]);
-                        }
+                    for (int r = 0; r < R; ++r) ob[r * C + i] = x.v[r];
                 }
-                for (int i = pi; i < pc1; i += kEmitThreads) {
-                    if (i != pi) { p_slot = __ldg(P.piece_slot + i); p_idx = __ldg(P.piece_idx + i); }
-                    const RV x = RV::load(vals + p_slot * R);
-#pragma unroll
-                    for (int r = 0; r < R; ++r) part[(size_t)min(b0 + r, n_rows - 1) * P.n_pieces + p_idx] = x.v[r];
+                fence_async_smem();
+                if (ci < 4) GT_TRACE(7 + 4 * ci);
+                // the chunk after this one reuses the other buffer: its previous store must have been read out
+                if (lane == 0 && warp >= kStoreWarp0 && cs + C < n1a) bulk_wait_read_all();
+                if (ci < 4) GT_TRACE(8 + 4 * ci);
+                __syncthreads();
+                if (ci < 4) GT_TRACE(9 + 4 * ci);
+                if (lane == 0 && warp >= kStoreWarp0) {  // one row per issuing thread
+                    const int r = warp - kStoreWarp0;
+                    if (r < nrows_here)
+                        bulk_s2g(out + (size_t)(b0 + r) * ld_out + cs, ob + r * C, (unsigned)cn * (unsigned)sizeof(VT));
+                    bulk_commit();
                 }
+                if (ci < 4) GT_TRACE(10 + 4 * ci);
             }
-            GT_TRACE(10);
-            mbar_arrive(empty + (k & 1));  // this thread no longer reads the value array
-            if (next_new) {
-                group_sync<2, kEmitThreads>();  // everyone is done with this tile's emit slots
-                if (tid == 0) fetch_slots(tn);
-            }
-            new_tile = next_new;
-            t = tn; g = gn;
+            if (n1a <= n0a) __syncthreads();  // no chunk barrier ran: still separate this item's reads from the next scatter
+        } else {
+            __syncthreads();
         }
+        GT_TRACE(23);
+        if (tid == 0 && next_new) fetch_slots(nb3[1], nb3[2]);
+        if (next_new) {
+#pragma unroll
+            for (int j = 0; j < 2; ++j) { zb[j] = zb[j + 1]; erb[j] = erb[j + 1]; ecb[j] = ecb[j + 1]; nb3[j] = nb3[j + 1]; }
+            load_bound(tn + 1, 2);
+        }
+        new_tile = next_new;
+        t = tn; g = gn;
     }
+    if (lane == 0 && warp >= kStoreWarp0) bulk_wait_all();  // the output is complete in global memory before the CTA retires
 }
 
 // ---- phase 3: nodes whose leaf range crosses tiles, reduced from their per-tile pieces (fp64 for sums) ------------

@@ -1,9 +1,7 @@
 """Prints the timeline of tile_kernel's pipeline (GT_TRACE=1): per item, the SM-clock durations between the events
-stamped by the leader thread of the compute group (0..7) and of the emit group (8..10).
+stamped by thread 0.
 
-  compute: 0 start | 1 value array free (empty) | 2 rows landed (A) | 3 scatter done | 4 next fetch issued |
-           5 pyramid done | 6 terms ready + group barrier | 7 ELL done (full)
-  emit:    8 start | 9 value array full | 10 emit done (empty)
+  0 item start | 1 rows landed (A) | 2 scatter done | 3 next fetch issued | 4 pyramid done | 5 ELL done | 6 output staged + issued
 """
 import ctypes
 import os
@@ -36,8 +34,13 @@ eng.reduce(ws[0], ("sum",), out_sum=osum[0])
 torch.cuda.synchronize()
 _lib.lib.gt_debug_read_trace(eng._handle, 0, buf.ctypes.data, n, dims)
 tr = buf.reshape(dims[0], dims[1], dims[2]).astype(np.float64)
-names = ["wait empty", "wait rows(A)", "scatter+bar", "issue fetch", "pyramid", "wait terms+bar", "ELL"]
-valid = tr[:, :, 7] > 0
+ev = {"wait rows(A)": (0, 1), "scatter+bar": (1, 2), "issue fetch": (2, 3), "pyramid+bar": (3, 4), "ELL (own share)": (4, 22),
+      "wait_read+bar": (22, 5), "head+pieces": (5, 6),
+      "c0 gather": (6, 7), "c0 wait_read": (7, 8), "c0 bar": (8, 9), "c0 issue": (9, 10),
+      "c1 gather": (10, 11), "c1 wait_read": (11, 12), "c1 bar": (12, 13), "c1 issue": (13, 14),
+      "c2 gather": (14, 15), "c2 wait_read": (15, 16), "c2 bar": (16, 17), "c2 issue": (17, 18),
+      "item total": (0, 23)}
+valid = tr[:, :, 23] > 0
 print("CTAs with items:", int(valid.any(axis=1).sum()), " items traced:", int(valid.sum()))
 for first in (True, False):
     sel = valid.copy()
@@ -48,22 +51,12 @@ for first in (True, False):
     if not sel.any():
         continue
     print("first item of a CTA" if first else "later items")
-    for e, name in enumerate(names):
-        d = (tr[:, :, e + 1] - tr[:, :, e])[sel]
-        print(f"  compute {name:16s} mean {d.mean():8.0f}  p50 {np.median(d):8.0f}  p90 {np.percentile(d, 90):8.0f} cycles")
-    d = (tr[:, :, 7] - tr[:, :, 0])[sel]
-    print(f"  compute item total       mean {d.mean():8.0f}")
-    d = (tr[:, :, 9] - tr[:, :, 8])[sel]
-    print(f"  emit    wait full        mean {d.mean():8.0f}  p50 {np.median(d):8.0f}  p90 {np.percentile(d, 90):8.0f}")
-    d = (tr[:, :, 10] - tr[:, :, 9])[sel]
-    print(f"  emit    emit loop        mean {d.mean():8.0f}  p50 {np.median(d):8.0f}  p90 {np.percentile(d, 90):8.0f}")
-span = tr[:, :, 10].max(axis=1) - np.where(valid, tr[:, :, 0], np.inf).min(axis=1)
+    for name, (a, b) in ev.items():
+        ok = sel & (tr[:, :, a] > 0) & (tr[:, :, b] > 0)
+        if not ok.any():
+            continue
+        d = (tr[:, :, b] - tr[:, :, a])[ok]
+        print(f"  {name:16s} mean {d.mean():8.0f}  p50 {np.median(d):8.0f}  p90 {np.percentile(d, 90):8.0f} cycles  (n={ok.sum()})")
+span = tr[:, :, 23].max(axis=1) - np.where(valid, tr[:, :, 0], np.inf).min(axis=1)
 span = span[valid.any(axis=1)]
-print(f"CTA lifetime (first event -> last emit): mean {span.mean():.0f}  max {span.max():.0f} cycles")
-# one CTA in detail
-c = 10
-print("CTA 10 timeline (cycles since its first event):")
-t0 = tr[c, 0, 0]
-for k in range(dims[1]):
-    if tr[c, k, 7] > 0:
-        print("  item", k, " ".join(f"{int(x - t0):7d}" for x in tr[c, k, :11]))
+print(f"CTA lifetime (first event -> last output): mean {span.mean():.0f}  max {span.max():.0f} cycles")
