@@ -11,8 +11,11 @@ import sys
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
-LIB_NAME = "libgenlm_trie_b200.so"
+# GT_LIB_NAME / GT_NVCC_DEFINES: build (and load) an experimental variant next to the default library, e.g.
+#   GT_LIB_NAME=libgt_cw8.so GT_NVCC_DEFINES=-DGT_COMPUTE_WARPS=8 python genlm_backend_b200/build.py
+LIB_NAME = os.environ.get("GT_LIB_NAME", "libgenlm_trie_b200.so")
 LIB_PATH = os.path.join(PKG_DIR, LIB_NAME)
+EXTRA_DEFINES = os.environ.get("GT_NVCC_DEFINES", "").split()
 INCLUDE = os.path.join(os.path.dirname(PKG_DIR), "include")
 
 SOURCES = ["trie_builder.cpp", "trie_plan.cpp", "trie_kernels.cu", "sampler_kernels.cu"]
@@ -46,13 +49,13 @@ def build(force=False, verbose=False):
     if not force and not needs_build():
         return LIB_PATH
     nvcc = _nvcc()
-    objdir = os.path.join(PKG_DIR, "build")
+    objdir = os.path.join(PKG_DIR, "build", os.path.splitext(LIB_NAME)[0])
     os.makedirs(objdir, exist_ok=True)
     objs = []
     procs = []
     for src in SOURCES:
         obj = os.path.join(objdir, os.path.splitext(src)[0] + ".o")
-        cmd = [nvcc] + NVCC_FLAGS + ["-I", INCLUDE, "-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [nvcc] + NVCC_FLAGS + EXTRA_DEFINES + ["-I", INCLUDE, "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
             print(" ".join(cmd), flush=True)

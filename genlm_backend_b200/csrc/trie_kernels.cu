@@ -82,6 +82,25 @@ constexpr int OP_SUM = 1, OP_MAX = 2;
 constexpr size_t kMaxSmem = 200 * 1024;  // dynamic shared memory we are willing to ask for per CTA
 constexpr int kSegPad = 8;  // slack so a row segment can be stored at its global 16-byte phase
 
+// ---- programmatic dependent launch ---------------------------------------------------------------------
+// Consecutive kernels of one call (permute -> tile -> span -> tile -> span) are launched with the programmatic
+// stream-serialisation attribute: a kernel's launch set-up and prologue overlap the tail of its predecessor, and
+// pdl_wait() -- executed before the first access to memory another kernel of the chain touches -- blocks until the
+// predecessor grid has completed and flushed.  pdl_trigger() lets the successor's CTAs start launching.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 // ---- small device helpers -----------------------------------------------------------------------
 
 template <int OP, typename VT> __device__ __forceinline__ VT op_apply(VT a, VT b) {
@@ -185,6 +204,7 @@ __global__ void __launch_bounds__(kThreads) permute_kernel(PlanView P, const IN_
                                                            VT* __restrict__ z, int n_rows, int log_input) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     VT* seg = reinterpret_cast<VT*>(smem_raw);  // [R][Q + kSegPad]
+    pdl_wait();  // the previous call's tile kernels may still be reading z
     const int pitch = P.Q + kSegPad;
     const int s = blockIdx.x;
     const int b0 = blockIdx.y * R;
@@ -236,17 +256,21 @@ __global__ void __launch_bounds__(kThreads) permute_kernel(PlanView P, const IN_
 
 // ---- phase 2: per-tile pyramid, multi-term ranges, emit, spanning pieces -------------------------------------
 //
-// Persistent kernel.  A work item is (tile t, row group g of R rows); items are numbered tile-major and every CTA
-// takes one contiguous run of them, so consecutive items of a CTA share the tile metadata, which stays in shared
-// memory.  All bulk traffic to and from global memory goes through the copy engine (cp.async.bulk, TMA), issued by
-// one thread, so the LSU pipes only ever see shared-memory work and its latency stays low:
-//     in   barrier A  staged rows of the next item (+ the slot table of its tile if new)   armed after each scatter
-//          barrier B  ELL term rows + descriptors of the next tile                         armed after the last ELL of a tile
-//          barrier C  emit slots of the next tile                                          armed after the last emit of a tile
-//     out  the tile's node-id interval is gathered into row-major staging chunks (two buffers) and written by bulk
-//          stores (bulk async-groups); only the few nodes outside the 16-byte aligned core use plain stores.
-// Every wait on A/B/C precedes a CTA barrier and every re-arm follows it, so no thread can still be waiting on a
-// phase when the next one completes.
+// Persistent, warp-specialised kernel.  A work item is (tile t, row group g of R rows); items are numbered
+// tile-major and every CTA takes one contiguous run of them, so consecutive items of a CTA share the tile metadata,
+// which stays in shared memory.  The CTA is split into two groups that run one item apart over a double-buffered
+// value array:
+//     compute warps  staged rows -> leaf slots -> pyramid -> multi-term ranges           (fill  vals[item & 1])
+//     emit warps     node-id interval of the tile -> global memory, spanning-node pieces  (drain vals[item & 1])
+// so the output stores -- the HBM-bound part -- stream continuously while the next item is being built.
+// Everything read from global memory arrives by bulk copies (cp.async.bulk, the TMA engine) issued one step ahead
+// by one thread of the group that consumes it, tracked by mbarriers:
+//     A   staged rows of the next item (+ the slot table of its tile if new)   armed after each scatter
+//     B   ELL term rows + descriptors of the next tile                         armed after the last ELL of a tile
+//     C   emit slots of the next tile                                          armed after the last emit of a tile
+//     full[2] / empty[2]   hand-over of the two value arrays between the groups
+// Every wait on A/B/C precedes a group barrier and every re-arm follows it, so no thread can still be waiting on
+// a phase when the next one completes.
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
     const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -267,10 +291,13 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* b, unsigned bytes) {
 __device__ __forceinline__ void mbar_wait(uint64_t* b, unsigned parity) {
     const unsigned addr = (unsigned)__cvta_generic_to_shared(b);
     unsigned done;
-    do {  // try_wait suspends the thread in hardware for a bounded time; loop until the phase has completed
+    for (;;) {  // try_wait suspends the thread in hardware for a bounded time; back off between polls so that
+                // waiting warps do not take issue slots from the working ones
         asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
                      : "=r"(done) : "r"(addr), "r"(parity) : "memory");
-    } while (!done);
+        if (done) break;
+        __nanosleep(40);
+    }
 }
 // bytes: multiple of 16; both addresses 16-byte aligned
 __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, unsigned bytes, uint64_t* b) {
@@ -330,332 +357,424 @@ template <typename VT, int R> struct RowVec {
 };
 
 constexpr int kTileThreads = 512;
-constexpr int kOutStageBytes = 16384;  // one output staging buffer (R rows x C nodes)
 // trace layout: [kTraceCtas][kTraceItems][kTraceEvents] SM-clock stamps
-constexpr int kTraceCtas = 512, kTraceItems = 32, kTraceEvents = 24;
+constexpr int kTraceCtas = 512, kTraceItems = 32, kTraceEvents = 12;
 #define GT_TRACE(ev)                                                                                         \
     do {                                                                                                     \
         if (P.trace && tid == 0 && blockIdx.x < kTraceCtas && k < kTraceItems)                                \
             P.trace[((size_t)blockIdx.x * kTraceItems + k) * kTraceEvents + (ev)] = clock64();               \
     } while (0)
+#ifndef GT_COMPUTE_WARPS
+#define GT_COMPUTE_WARPS 12
+#endif
+constexpr int kComputeThreads = 32 * GT_COMPUTE_WARPS;        // warps 0 .. GT_COMPUTE_WARPS-1
+constexpr int kEmitThreads = kTileThreads - kComputeThreads;  // the remaining warps
 
 // Shared-memory carve-up of tile_kernel (all sections 16-byte aligned).
 struct TileSmem {
-    size_t vals, stage, p2, slots, terms, desc, ostage, bars, total;
+    size_t vals, vals_bytes, stage, p2, slots, terms, desc, bars, total;
     __host__ __device__ TileSmem(const PlanView& P, int slot_bytes, int elem_bytes, int R) {
         size_t o = 0;
-        vals = o;  o += (size_t)(P.SV + 4) * slot_bytes;                    // value slots + trash slot
+        vals_bytes = (size_t)(P.SV + 4) * slot_bytes;                       // value slots + trash slot
+        vals = o;  o += 2 * vals_bytes;                                     // double-buffered between the groups
         stage = o; o += (size_t)R * P.max_tile_z * elem_bytes;              // staged rows of the next item
         p2 = o;    o += (size_t)P.max_tile_z * 2;                           // staged element -> value slot
         slots = o; o += (size_t)P.max_tile_nodes * 2;                       // node -> value slot (emit)
         terms = o; o += (size_t)P.max_tile_ell_rows * 64;                   // ELL term rows
         desc = o;  o += ((size_t)(P.max_tile_chunks + 2) * 8 + 15) & ~size_t(15); // ELL chunk descriptors (+ alignment slack)
-        ostage = o; o += 2 * (size_t)kOutStageBytes;                        // output staging, two buffers
-        bars = o;  o += 32;                                                 // three mbarriers
+        bars = o;  o += 64;                                                 // seven mbarriers
         total = o;
     }
 };
 
-// bulk store shared -> global (bulk async-group completion); bytes multiple of 16, both addresses 16-byte aligned
-__device__ __forceinline__ void bulk_s2g(void* gdst, const void* smem_src, unsigned bytes) {
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst),
-                 "r"((unsigned)__cvta_generic_to_shared(smem_src)), "r"(bytes)
-                 : "memory");
+__device__ __forceinline__ void mbar_arrive(uint64_t* b) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((unsigned)__cvta_generic_to_shared(b)) : "memory");
 }
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-// all bulk stores of this thread have finished READING shared memory (the buffers may be rewritten)
-__device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-// make this thread's shared-memory writes visible to the copy engine (async proxy)
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+template <int ID, int COUNT> __device__ __forceinline__ void group_sync() {
+    asm volatile("bar.sync %0, %1;" ::"n"(ID), "n"(COUNT) : "memory");
+}
 
-template <typename VT, int R, int OP>
-__global__ void __launch_bounds__(kTileThreads, 2) tile_kernel(PlanView P, const VT* __restrict__ z, VT* __restrict__ out,
-                                                               int64_t ld_out, VT* __restrict__ part, int n_rows) {
+// What one launch works on: the staged rows and, per requested reduction, the output slab and the scratch for the
+// pieces of spanning nodes.  ops = GT_OP_SUM | GT_OP_MAX; with both, the two reductions of a (tile, row group) are
+// consecutive items that share one fetch of the staged rows.
+template <typename VT> struct TileArgs {
+    const VT* z;
+    VT* out_sum; VT* out_max;
+    VT* part_sum; VT* part_max;
+    int64_t ld_out;
+    int n_rows;
+    unsigned ops;
+};
+
+// ---- compute-group phases (OP is a compile-time parameter; the kernel branches once per phase) ----------------------
+
+// 1. staged rows -> DFS-ordered leaf slots (slot numbers in the table are already swizzled)
+template <typename VT, int R, int OP, int NTHREADS>
+__device__ __forceinline__ void phase_scatter(VT* vals, const VT* stage, const uint16_t* s_p2, int zpitch, int zn4, int nleaf,
+                                              int T, int tid) {
+    using RV = RowVec<VT, R>;
+    constexpr int B = (int)sizeof(VT) * R;
+    constexpr int U = R >= 4 ? 1 : 2;  // quads in flight per thread (a second one clamps to a duplicate of the last quad)
+    for (int qb = tid; qb < zn4; qb += U * NTHREADS) {
+        uint2 sl[U];
+        VT v[U][R][4];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int q = min(qb + u * NTHREADS, zn4 - 1);
+            sl[u] = *reinterpret_cast<const uint2*>(s_p2 + 4 * q);
+#pragma unroll
+            for (int r = 0; r < R; ++r) load4<VT>(stage + (size_t)r * zpitch + 4 * q, v[u][r][0], v[u][r][1], v[u][r][2], v[u][r][3]);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const unsigned s4[4] = {sl[u].x & 0xFFFFu, sl[u].x >> 16, sl[u].y & 0xFFFFu, sl[u].y >> 16};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                RV x;
+#pragma unroll
+                for (int r = 0; r < R; ++r) x.v[r] = v[u][r][e];
+                x.store(vals + s4[e] * R);
+            }
+        }
+    }
+    for (int i = nleaf + tid; i < T; i += NTHREADS) RV::template ident<OP>().store(vals + swz<B>(i) * R);
+    if (tid == 0) RV::template ident<OP>().store(vals + swz<B>(2 * T - 1) * R);  // identity slot (ELL padding, spanning nodes)
+}
+
+// 2. pyramid of aligned blocks: level k block i at (swizzled) slot 2T - (T >> (k-1)) + i.
+//    Lane u owns leaves 8u .. 8u+7: levels 1..3 in registers, 4..8 by warp shuffles (256 leaves per warp).
+//    The swizzle makes the 16-byte chunk loads and the strided level stores bank-conflict free.
+template <typename VT, int R, int OP, int NWARPS>
+__device__ __forceinline__ void phase_pyramid(VT* vals, int T, int warp, int lane) {
+    using RV = RowVec<VT, R>;
+    constexpr int B = (int)sizeof(VT) * R;
+    constexpr int SPC = 16 / B;  // slots per 16-byte chunk
+    auto level_slot = [&](int k, int i) { return 2 * T - (T >> (k - 1)) + i; };  // level k >= 1, block i
+    for (int ub = warp * 32; ub < (T >> 3); ub += NWARPS * 32) {
+        const int u = ub + lane;
+        RV x[8];
+#pragma unroll
+        for (int ch = 0; ch < 8 / SPC; ++ch) {
+            const int c = (8 * u) / SPC + ch;
+            const int cc = c ^ ((c >> 3) & (B / 2 - 1));
+            const float4 raw = *reinterpret_cast<const float4*>(reinterpret_cast<const unsigned char*>(vals) + (size_t)cc * 16);
+            memcpy(&x[ch * SPC], &raw, 16);
+        }
+        RV a[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            a[e] = RV::template combine<OP>(x[2 * e], x[2 * e + 1]);
+            a[e].store(vals + swz<B>(level_slot(1, 4 * u + e)) * R);
+        }
+        const RV c0 = RV::template combine<OP>(a[0], a[1]), c1 = RV::template combine<OP>(a[2], a[3]);
+        c0.store(vals + swz<B>(level_slot(2, 2 * u)) * R);
+        c1.store(vals + swz<B>(level_slot(2, 2 * u + 1)) * R);
+        RV y = RV::template combine<OP>(c0, c1);
+        y.store(vals + swz<B>(level_slot(3, u)) * R);
+#pragma unroll
+        for (int j = 1; j <= 5; ++j) {
+            y = RV::template combine<OP>(y, y.shfl_down(1 << (j - 1)));
+            if ((lane & ((1 << j) - 1)) == 0) y.store(vals + swz<B>(level_slot(3 + j, u >> j)) * R);
+        }
+    }
+}
+
+// 3. ranges that need more than one block: ELL chunks of 32 ranges, one warp per chunk, term rows read from shared
+//    memory (k is a multiple of 4: the planner pads rows with the identity slot).  Chunks are sorted by descending
+//    term count: rounds alternate direction so that the warps that drew the longest chunks of one round draw the
+//    shortest of the next.
+template <typename VT, int R, int OP, int NWARPS>
+__device__ __forceinline__ void phase_ell(VT* vals, const uint16_t* s_terms, const int2* dsc, int er0, int nchunks, int T,
+                                          int warp, int lane) {
+    using RV = RowVec<VT, R>;
+    for (int base = 0, rr = 0; base < nchunks; base += NWARPS, ++rr) {
+        const int c = base + ((rr & 1) ? NWARPS - 1 - warp : warp);
+        if (c >= nchunks) continue;
+        const int2 d = dsc[c];
+        const uint16_t* tp = s_terms + (d.x - er0) * 32 + lane;
+        RV acc = RV::template ident<OP>();
+        for (int kb = 0; kb < d.y; kb += 4) {
+            int sl[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) sl[e] = tp[(kb + e) * 32];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) acc = RV::template combine<OP>(acc, RV::load(vals + sl[e] * R));
+        }
+        acc.store(vals + (2 * T + c * 32 + lane) * R);
+    }
+}
+
+template <typename VT, int R>
+__global__ void __launch_bounds__(kTileThreads, 2) tile_kernel(PlanView P, TileArgs<VT> A) {
     using RV = RowVec<VT, R>;
     constexpr int B = (int)sizeof(VT) * R;  // bytes per slot
     static_assert(B == 4 || B == 8 || B == 16, "slot must be 4, 8 or 16 bytes");
-    constexpr int SPC = 16 / B;             // slots per 16-byte chunk
-    constexpr int kWarps = kTileThreads / 32;
-    constexpr int C = kOutStageBytes / B;   // nodes per output staging buffer
-    constexpr int AL = 16 / (int)sizeof(VT);  // nodes per 16 bytes of an output row
-    constexpr int kIssueTid = kTileThreads - 32;          // lane 0 of the last warp issues the input fetches
-    constexpr int kStoreWarp0 = kWarps - R;               // lane 0 of warps kStoreWarp0 + r issues the stores of row r
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const TileSmem L(P, B, (int)sizeof(VT), R);
-    VT* vals = reinterpret_cast<VT*>(smem_raw + L.vals);
     VT* stage = reinterpret_cast<VT*>(smem_raw + L.stage);
     uint16_t* s_p2 = reinterpret_cast<uint16_t*>(smem_raw + L.p2);
     uint16_t* s_slots = reinterpret_cast<uint16_t*>(smem_raw + L.slots);
     uint16_t* s_terms = reinterpret_cast<uint16_t*>(smem_raw + L.terms);
     int2* s_desc = reinterpret_cast<int2*>(smem_raw + L.desc);
-    VT* ostage = reinterpret_cast<VT*>(smem_raw + L.ostage);  // [2][R][C]
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + L.bars);
-    uint64_t* barA = bars;      // rows (+ p2)
-    uint64_t* barB = bars + 1;  // terms + descriptors
-    uint64_t* barC = bars + 2;  // emit slots
+    uint64_t* barA = bars;          // rows (+ p2)
+    uint64_t* barB = bars + 1;      // terms + descriptors
+    uint64_t* barC = bars + 2;      // emit slots
+    uint64_t* full = bars + 3;      // [2] value array filled by the compute group
+    uint64_t* empty = bars + 5;     // [2] value array drained by the emit group
 
     const int T = P.T;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n_rows = A.n_rows;
     const int RG = (n_rows + R - 1) / R;
-    const int n_items = P.NT * RG;
+    const int nops = (A.ops == (unsigned)(GT_OP_SUM | GT_OP_MAX)) ? 2 : 1;
+    const int first_op = (A.ops & GT_OP_SUM) ? OP_SUM : OP_MAX;
+    const int n_items = P.NT * RG * nops;  // item = (tile * RG + row group) * nops + j
     const int i0 = (int)((int64_t)blockIdx.x * n_items / gridDim.x);
     const int i1 = (int)((int64_t)(blockIdx.x + 1) * n_items / gridDim.x);
     if (i0 >= i1) return;
     const int zpitch = P.max_tile_z;
-    const int dbg = P.debug_stop;  // profiling aid: 3 = no output, 9 = output only (compute phases skipped)
-    // bulk stores need 16-byte aligned rows; otherwise every node takes the plain-store path
-    const bool bulk_ok = ((ld_out * (int64_t)sizeof(VT)) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
-    auto level_slot = [&](int k, int i) { return 2 * T - (T >> (k - 1)) + i; };  // level k >= 1, block i
+    const int dbg = P.debug_stop;  // profiling aid: 3 = no emit stores, 9 = emit only (compute phases skipped)
 
-    // Boundaries of the current tile (index 0..1) and the next one (1..2) in the four per-tile prefix arrays; the
-    // next tile's are loaded one tile ahead so that no fetch waits for them.
-    int zb[3], erb[3], ecb[3], nb3[3];
-    auto load_bound = [&](int t, int j) {
-        const int tt = min(t, P.NT);
-        zb[j] = __ldg(P.z_tile_off + tt); erb[j] = __ldg(P.ell_row_ptr + tt);
-        ecb[j] = __ldg(P.ell_chunk_ptr + tt); nb3[j] = __ldg(P.tile_node_lo + tt);
-    };
-
-    // ---- asynchronous fetches (thread 0) -----------------------------------------------------------------------
-    // Rows past the end of the batch alias the last valid row: they compute exactly what that row does, which keeps
-    // every loop free of row predicates; their output is not stored.
-    auto fetch_rows = [&](int g, int zlo, int zn, bool with_p2) {
-        const unsigned row_bytes = (unsigned)zn * (unsigned)sizeof(VT);
-        mbar_expect_tx(barA, R * row_bytes + (with_p2 ? (unsigned)zn * 2u : 0u));
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-            const int row = min(g * R + r, n_rows - 1);
-            bulk_g2s(stage + (size_t)r * zpitch, z + (size_t)row * P.Zrow + zlo, row_bytes, barA);
-        }
-        if (with_p2) bulk_g2s(s_p2, P.p2_slot + zlo, (unsigned)zn * 2u, barA);
-    };
-    // ELL term rows and chunk descriptors (8 bytes each, copied from the 16-byte aligned pair at or below the first)
-    auto fetch_terms = [&](int er0, int er1, int ec0, int ec1) {
-        const int ea = ec0 & ~1;
-        const unsigned tb = (unsigned)(er1 - er0) * 64u, db = (unsigned)((ec1 - ea + 1) >> 1) * 16u;
-        mbar_expect_tx(barB, tb + db);
-        if (tb) bulk_g2s(s_terms, P.ell_terms + (size_t)er0 * 32, tb, barB);
-        if (db) bulk_g2s(s_desc, P.ell_desc + ea, db, barB);
-    };
-    // emit slots, staged from the 16-byte aligned start at or below the tile's first node
-    auto fetch_slots = [&](int n0, int n1) {
-        const int na = n0 & ~7;
-        const unsigned sb = (unsigned)((n1 - na + 7) >> 3) * 16u;
-        mbar_expect_tx(barC, sb);
-        bulk_g2s(s_slots, P.node_slot + na, sb, barC);
-    };
-
-    int t = i0 / RG, g = i0 - t * RG;
-    load_bound(t, 0); load_bound(t + 1, 1); load_bound(t + 2, 2);
-    if (tid == 0) {
+    if (threadIdx.x == 0) {
         mbar_init(barA, 1); mbar_init(barB, 1); mbar_init(barC, 1);
+        mbar_init(full, kComputeThreads); mbar_init(full + 1, kComputeThreads);
+        mbar_init(empty, kEmitThreads); mbar_init(empty + 1, kEmitThreads);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        fetch_rows(g, zb[0], zb[1] - zb[0], true);
-        fetch_terms(erb[0], erb[1], ecb[0], ecb[1]);
-        fetch_slots(nb3[0], nb3[1]);
     }
-    __syncthreads();  // barriers initialised before anyone waits on them
+    pdl_wait();  // z comes from permute_kernel; the outputs may still be in use by the previous kernels of the chain
+    pdl_trigger();
+    __syncthreads();
 
-    bool new_tile = true;
-    unsigned parBC = 0;
-    int pc0 = 0, pc1 = 0, my_pslot = 0, my_pidx = 0;
-    for (int item = i0; item < i1; ++item) {
-        const int k = item - i0;
-        if (new_tile) {  // this thread's spanning-node piece of the tile, requested a whole item before its first use
-            pc0 = __ldg(P.piece_ptr + t); pc1 = __ldg(P.piece_ptr + t + 1);
-            if (pc0 + tid < pc1) { my_pslot = __ldg(P.piece_slot + pc0 + tid); my_pidx = __ldg(P.piece_idx + pc0 + tid); }
-        }
-        int tn = t, gn = g + 1;
-        if (gn == RG) { gn = 0; ++tn; }
-        const bool has_next = item + 1 < i1;
-        const bool next_new = has_next && tn != t;
-        const int n0 = nb3[0], n1 = nb3[1];
-
-        // 1. staged rows -> DFS-ordered leaf slots (slot numbers in the table are already swizzled)
-        GT_TRACE(0);
-        mbar_wait(barA, (unsigned)k & 1u);
-        GT_TRACE(1);
-        if (dbg != 9) {
-            const int zn4 = (zb[1] - zb[0]) >> 2;
-            for (int q = tid; q < zn4; q += kTileThreads) {
-                const uint2 sl = *reinterpret_cast<const uint2*>(s_p2 + 4 * q);
-                VT v[R][4];
+    if (threadIdx.x < kComputeThreads) {
+        // =========================== compute group ===========================================================
+        const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+        constexpr int kWarps = kComputeThreads / 32;
+        constexpr int kIssueTid = kComputeThreads - 32;  // lane 0 of the last compute warp issues the fetches: that
+                                                         // warp has no share of the pyramid, so nobody waits for it
+        // Boundaries of the current tile (index 0..1) and the next one (1..2) in the per-tile prefix arrays; the next
+        // tile's are loaded one tile ahead so that no fetch waits for them.
+        int zb[3], erb[3], ecb[3];
+        auto load_bound = [&](int t, int j) {
+            const int tt = min(t, P.NT);
+            zb[j] = __ldg(P.z_tile_off + tt); erb[j] = __ldg(P.ell_row_ptr + tt); ecb[j] = __ldg(P.ell_chunk_ptr + tt);
+        };
+        // staged rows of row group g (+ the tile's slot table).  Rows past the end of the batch alias the last valid
+        // row: they compute exactly what that row does, which keeps every loop free of row predicates.
+        auto fetch_rows = [&](int g, int zlo, int zn, bool with_p2) {
+            const unsigned row_bytes = (unsigned)zn * (unsigned)sizeof(VT);
+            mbar_expect_tx(barA, R * row_bytes + (with_p2 ? (unsigned)zn * 2u : 0u));
 #pragma unroll
-                for (int r = 0; r < R; ++r) load4<VT>(stage + (size_t)r * zpitch + 4 * q, v[r][0], v[r][1], v[r][2], v[r][3]);
-                const unsigned s4[4] = {sl.x & 0xFFFFu, sl.x >> 16, sl.y & 0xFFFFu, sl.y >> 16};
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    RV x;
-#pragma unroll
-                    for (int r = 0; r < R; ++r) x.v[r] = v[r][e];
-                    x.store(vals + s4[e] * R);
-                }
+            for (int r = 0; r < R; ++r) {
+                const int row = min(g * R + r, n_rows - 1);
+                bulk_g2s(stage + (size_t)r * zpitch, A.z + (size_t)row * P.Zrow + zlo, row_bytes, barA);
             }
+            if (with_p2) bulk_g2s(s_p2, P.p2_slot + zlo, (unsigned)zn * 2u, barA);
+        };
+        // ELL term rows and chunk descriptors (8 bytes each, copied from the 16-byte aligned pair at or below the
+        // first one)
+        auto fetch_terms = [&](int er0, int er1, int ec0, int ec1) {
+            const int ea = ec0 & ~1;
+            const unsigned tb = (unsigned)(er1 - er0) * 64u, db = (unsigned)((ec1 - ea + 1) >> 1) * 16u;
+            mbar_expect_tx(barB, tb + db);
+            if (tb) bulk_g2s(s_terms, P.ell_terms + (size_t)er0 * 32, tb, barB);
+            if (db) bulk_g2s(s_desc, P.ell_desc + ea, db, barB);
+        };
+
+        int tg = i0 / nops, j = i0 - tg * nops;  // (tile, row group) index and which reduction of it
+        int t = tg / RG, g = tg - t * RG;
+        load_bound(t, 0); load_bound(t + 1, 1); load_bound(t + 2, 2);
+        if (tid == kIssueTid) { fetch_rows(g, zb[0], zb[1] - zb[0], true); fetch_terms(erb[0], erb[1], ecb[0], ecb[1]); }
+        bool new_tile = true;
+        unsigned parB = 0;
+        for (int item = i0; item < i1; ++item) {
+            const int k = item - i0;
+            VT* vals = reinterpret_cast<VT*>(smem_raw + L.vals + (size_t)(k & 1) * L.vals_bytes);
+            const bool is_sum = (j == 0 ? first_op : OP_MAX) == OP_SUM;
+            // the item after this one
+            int jn = j + 1, tn = t, gn = g;
+            if (jn == nops) { jn = 0; if (++gn == RG) { gn = 0; ++tn; } }
+            const bool has_next = item + 1 < i1;
+            const bool next_rows = has_next && jn == 0;   // the next item needs other staged rows
+            const bool next_new = has_next && tn != t;    // ... of another tile
+            const int zn4 = (zb[1] - zb[0]) >> 2, nchunks = ecb[1] - ecb[0];
             const int nleaf = (int)min((int64_t)T, P.V - (int64_t)t * T);
-            for (int i = nleaf + tid; i < T; i += kTileThreads) RV::template ident<OP>().store(vals + swz<B>(i) * R);
-            if (tid == 0) RV::template ident<OP>().store(vals + swz<B>(2 * T - 1) * R);  // identity slot (ELL padding, spanning nodes)
-        }
-        __syncthreads();
-        GT_TRACE(2);
-        // the staging buffer (and, on a tile change, the slot table) is free again: fetch the next item's rows
-        // (issued by a warp that has no share of the pyramid, so nobody waits for the issue latency)
-        if (tid == kIssueTid) {
-            if (has_next) fetch_rows(gn, next_new ? zb[1] : zb[0], next_new ? zb[2] - zb[1] : zb[1] - zb[0], next_new);
-            else mbar_expect_tx(barA, 0);
-        }
-        GT_TRACE(3);
 
-        // 2. pyramid of aligned blocks: level k block i at (swizzled) slot 2T - (T >> (k-1)) + i.
-        //    Lane u owns leaves 8u .. 8u+7: levels 1..3 in registers, 4..8 by warp shuffles (256 leaves per warp).
-        //    The swizzle makes the 16-byte chunk loads and the strided level stores bank-conflict free.
-        if (dbg != 9) {
-            for (int ub = warp * 32; ub < (T >> 3); ub += kWarps * 32) {
-                const int u = ub + lane;
-                RV x[8];
-#pragma unroll
-                for (int ch = 0; ch < 8 / SPC; ++ch) {
-                    const int c = (8 * u) / SPC + ch;
-                    const int cc = c ^ ((c >> 3) & (B / 2 - 1));
-                    const float4 raw = *reinterpret_cast<const float4*>(reinterpret_cast<const unsigned char*>(vals) + (size_t)cc * 16);
-                    memcpy(&x[ch * SPC], &raw, 16);
-                }
-                RV a[4];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    a[e] = RV::template combine<OP>(x[2 * e], x[2 * e + 1]);
-                    a[e].store(vals + swz<B>(level_slot(1, 4 * u + e)) * R);
-                }
-                const RV c0 = RV::template combine<OP>(a[0], a[1]), c1 = RV::template combine<OP>(a[2], a[3]);
-                c0.store(vals + swz<B>(level_slot(2, 2 * u)) * R);
-                c1.store(vals + swz<B>(level_slot(2, 2 * u + 1)) * R);
-                RV y = RV::template combine<OP>(c0, c1);
-                y.store(vals + swz<B>(level_slot(3, u)) * R);
-#pragma unroll
-                for (int j = 1; j <= 5; ++j) {
-                    y = RV::template combine<OP>(y, y.shfl_down(1 << (j - 1)));
-                    if ((lane & ((1 << j) - 1)) == 0) y.store(vals + swz<B>(level_slot(3 + j, u >> j)) * R);
-                }
+            GT_TRACE(0);
+            mbar_wait(empty + (k & 1), ((unsigned)(k >> 1) & 1u) ^ 1u);  // the emit group has drained this value array
+            GT_TRACE(1);
+            mbar_wait(barA, (unsigned)k & 1u);
+            GT_TRACE(2);
+            if (dbg != 9) {
+                if (is_sum) phase_scatter<VT, R, OP_SUM, kComputeThreads>(vals, stage, s_p2, zpitch, zn4, nleaf, T, tid);
+                else phase_scatter<VT, R, OP_MAX, kComputeThreads>(vals, stage, s_p2, zpitch, zn4, nleaf, T, tid);
             }
-        }
-        if (new_tile) mbar_wait(barB, parBC);  // ELL terms + descriptors of this tile
-        __syncthreads();
-        GT_TRACE(4);
-
-        // 3. ranges that need more than one block: ELL chunks of 32 ranges, one warp per chunk, term rows read from
-        //    shared memory (k is a multiple of 4: the planner pads rows with the identity slot)
-        if (dbg != 9) {
-            const int2* dsc = s_desc + (ecb[0] & 1);
-            const int nchunks = ecb[1] - ecb[0];
-            for (int c = warp; c < nchunks; c += kWarps) {
-                const int2 d = dsc[c];
-                const uint16_t* tp = s_terms + (d.x - erb[0]) * 32 + lane;
-                RV acc = RV::template ident<OP>();
-                for (int kb = 0; kb < d.y; kb += 4) {
-                    int sl[4];
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) sl[e] = tp[(kb + e) * 32];
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) acc = RV::template combine<OP>(acc, RV::load(vals + sl[e] * R));
-                }
-                acc.store(vals + (2 * T + c * 32 + lane) * R);
+            group_sync<1, kComputeThreads>();
+            GT_TRACE(3);
+            // the staging buffer (and, on a tile change, the slot table) is free again: fetch the next item's rows,
+            // unless it is the other reduction of the same rows (the barrier is armed once per item either way)
+            if (tid == kIssueTid) {
+                if (next_rows) fetch_rows(gn, next_new ? zb[1] : zb[0], next_new ? zb[2] - zb[1] : zb[1] - zb[0], next_new);
+                else mbar_expect_tx(barA, 0);
             }
-        }
-        if (new_tile) { mbar_wait(barC, parBC); parBC ^= 1u; }  // emit slots of this tile
-        GT_TRACE(22);
-        // the previous item's output chunks have left both staging buffers (each issuing thread checks its own stores)
-        if (lane == 0 && warp >= kStoreWarp0) bulk_wait_read_all();
-        __syncthreads();
-        GT_TRACE(5);
-        if (tid == 0 && next_new) fetch_terms(erb[1], erb[2], ecb[1], ecb[2]);
-
-        // 4. output.  Core = the 16-byte aligned part [n0a, n1a) of the tile's node-id interval: gathered into
-        //    row-major staging chunks (lane = consecutive node id, so the slot reads of a warp cluster on a few
-        //    neighbouring slots -- unary chains broadcast -- and the staging writes are conflict-free), then
-        //    written by one bulk store per row and chunk.  Spanning nodes inside the interval carry the identity
-        //    slot: what is written for them here is overwritten by span_kernel.
-        if (dbg != 3) {
-            const int b0 = g * R;
-            const int nrows_here = min(R, n_rows - b0);
-            const uint16_t* sl_base = s_slots - (n0 & ~7);
-            const int n0a = bulk_ok ? min(n1, (n0 + AL - 1) & ~(AL - 1)) : n1;
-            const int n1a = bulk_ok ? max(n0a, n1 & ~(AL - 1)) : n1;
-            // nodes outside the aligned core, and the pieces of spanning nodes that overlap this tile (reduced by
-            // span_kernel, which runs next on the stream): plain stores
-            auto store_node = [&](int n) {
-                const RV x = RV::load(vals + (int)sl_base[n] * R);
-#pragma unroll
-                for (int r = 0; r < R; ++r)
-                    if (r < nrows_here) out[(size_t)(b0 + r) * ld_out + n] = x.v[r];
-            };
-            for (int n = n0 + tid; n < n0a; n += kTileThreads) store_node(n);  // head (everything when !bulk_ok)
-            for (int n = n1a + tid; n < n1; n += kTileThreads) store_node(n);  // tail
-            for (int i = pc0 + tid; i < pc1; i += kTileThreads) {
-                const bool mine = i == pc0 + tid;
-                const RV x = RV::load(vals + (mine ? my_pslot : (int)__ldg(P.piece_slot + i)) * R);
-                const int idx = mine ? my_pidx : __ldg(P.piece_idx + i);
-#pragma unroll
-                for (int r = 0; r < R; ++r)
-                    if (r < nrows_here) part[(size_t)(b0 + r) * P.n_pieces + idx] = x.v[r];
+            GT_TRACE(4);
+            if (dbg != 9) {
+                if (is_sum) phase_pyramid<VT, R, OP_SUM, kWarps>(vals, T, warp, lane);
+                else phase_pyramid<VT, R, OP_MAX, kWarps>(vals, T, warp, lane);
             }
+            GT_TRACE(5);
+            if (new_tile) { mbar_wait(barB, parB); parB ^= 1u; }  // ELL terms + descriptors of this tile
+            group_sync<1, kComputeThreads>();
             GT_TRACE(6);
-            int buf = 0, ci = 0;
-            for (int cs = n0a; cs < n1a; cs += C, buf ^= 1, ++ci) {
-                const int cn = min(C, n1a - cs);
-                VT* ob = ostage + (size_t)buf * R * C;
-                for (int i = tid; i < cn; i += kTileThreads) {
-                    const RV x = RV::load(vals + (int)sl_base[cs + i] * R);
-#pragma unroll
-                    for (int r = 0; r < R; ++r) ob[r * C + i] = x.v[r];
-                }
-                fence_async_smem();
-                if (ci < 4) GT_TRACE(7 + 4 * ci);
-                // the chunk after this one reuses the other buffer: its previous store must have been read out
-                if (lane == 0 && warp >= kStoreWarp0 && cs + C < n1a) bulk_wait_read_all();
-                if (ci < 4) GT_TRACE(8 + 4 * ci);
-                __syncthreads();
-                if (ci < 4) GT_TRACE(9 + 4 * ci);
-                if (lane == 0 && warp >= kStoreWarp0) {  // one row per issuing thread
-                    const int r = warp - kStoreWarp0;
-                    if (r < nrows_here)
-                        bulk_s2g(out + (size_t)(b0 + r) * ld_out + cs, ob + r * C, (unsigned)cn * (unsigned)sizeof(VT));
-                    bulk_commit();
-                }
-                if (ci < 4) GT_TRACE(10 + 4 * ci);
+            if (dbg != 9) {
+                const int2* dsc = s_desc + (ecb[0] & 1);
+                if (is_sum) phase_ell<VT, R, OP_SUM, kWarps>(vals, s_terms, dsc, erb[0], nchunks, T, warp, lane);
+                else phase_ell<VT, R, OP_MAX, kWarps>(vals, s_terms, dsc, erb[0], nchunks, T, warp, lane);
             }
-            if (n1a <= n0a) __syncthreads();  // no chunk barrier ran: still separate this item's reads from the next scatter
-        } else {
-            __syncthreads();
-        }
-        GT_TRACE(23);
-        if (tid == 0 && next_new) fetch_slots(nb3[1], nb3[2]);
-        if (next_new) {
+            GT_TRACE(7);
+            mbar_arrive(full + (k & 1));  // this thread's share of the value array is complete
+            if (next_new) {
+                group_sync<1, kComputeThreads>();  // everyone is done with this tile's terms
+                if (tid == kIssueTid) fetch_terms(erb[1], erb[2], ecb[1], ecb[2]);
 #pragma unroll
-            for (int j = 0; j < 2; ++j) { zb[j] = zb[j + 1]; erb[j] = erb[j + 1]; ecb[j] = ecb[j + 1]; nb3[j] = nb3[j + 1]; }
-            load_bound(tn + 1, 2);
+                for (int q = 0; q < 2; ++q) { zb[q] = zb[q + 1]; erb[q] = erb[q + 1]; ecb[q] = ecb[q + 1]; }
+                load_bound(tn + 1, 2);
+            }
+            new_tile = next_new;
+            t = tn; g = gn; j = jn;
         }
-        new_tile = next_new;
-        t = tn; g = gn;
+    } else {
+        // =========================== emit group ==============================================================
+        const int tid = threadIdx.x - kComputeThreads;
+        // emit slots of a tile, staged from the 16-byte aligned start at or below its first node
+        auto fetch_slots = [&](int n0, int n1) {
+            const int na = n0 & ~7;
+            const unsigned sb = (unsigned)((n1 - na + 7) >> 3) * 16u;
+            mbar_expect_tx(barC, sb);
+            bulk_g2s(s_slots, P.node_slot + na, sb, barC);
+        };
+        int tg = i0 / nops, j = i0 - tg * nops;
+        int t = tg / RG, g = tg - t * RG;
+        int nb3[3];  // node-id boundaries of this tile and the next (loaded one tile ahead)
+#pragma unroll
+        for (int q = 0; q < 3; ++q) nb3[q] = __ldg(P.tile_node_lo + min(t + q, P.NT));
+        if (tid == 0) fetch_slots(nb3[0], nb3[1]);
+        int pc0 = 0, pc1 = 0, my_pslot = 0, my_pidx = 0;
+        bool new_tile = true;
+        unsigned parC = 0;
+        for (int item = i0; item < i1; ++item) {
+            const int k = item - i0;
+            const VT* vals = reinterpret_cast<const VT*>(smem_raw + L.vals + (size_t)(k & 1) * L.vals_bytes);
+            const bool is_sum = (j == 0 ? first_op : OP_MAX) == OP_SUM;
+            VT* out = is_sum ? A.out_sum : A.out_max;
+            VT* part = is_sum ? A.part_sum : A.part_max;
+            const int n0 = nb3[0], n1 = nb3[1];
+            if (new_tile) {
+                // this thread's spanning-node piece of the tile, requested long before its first use
+                pc0 = __ldg(P.piece_ptr + t); pc1 = __ldg(P.piece_ptr + t + 1);
+                if (pc0 + tid < pc1) { my_pslot = __ldg(P.piece_slot + pc0 + tid); my_pidx = __ldg(P.piece_idx + pc0 + tid); }
+                mbar_wait(barC, parC); parC ^= 1u;
+            }
+            int jn = j + 1, tn = t, gn = g;
+            if (jn == nops) { jn = 0; if (++gn == RG) { gn = 0; ++tn; } }
+            const bool next_new = item + 1 < i1 && tn != t;
+
+            const int b0 = g * R;
+            VT* orow[R];
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                orow[r] = out + (size_t)min(b0 + r, n_rows - 1) * A.ld_out;
+                asm volatile("" : "+l"(orow[r]));  // keep the row pointers in registers (no rematerialisation per store)
+            }
+            GT_TRACE(8);
+            mbar_wait(full + (k & 1), (unsigned)(k >> 1) & 1u);  // the compute group has filled this value array
+            GT_TRACE(9);
+
+            // 4. emit the tile's node-id interval: lane = consecutive node id, so the slot reads of a warp cluster on
+            //    a few neighbouring slots (unary chains broadcast) and every store instruction writes 128 contiguous
+            //    bytes per row.  The sweep starts at the 128-byte line of row 0 that holds node n0, so with a row
+            //    stride that is a multiple of 32 elements every store instruction covers exactly one line.
+            //    Spanning nodes inside the interval carry the identity slot: what is written for them here is
+            //    overwritten by span_kernel.
+            if (dbg != 3) {
+                constexpr int U = 4;
+                const int na = n0 & ~7;
+                const int lead = (int)(((reinterpret_cast<uintptr_t>(orow[0]) / sizeof(VT)) + (unsigned)n0) & 31u);
+                const unsigned count = (unsigned)(n1 - n0);
+                const uint16_t* sl_base = s_slots - na;
+                const unsigned char* vbytes = reinterpret_cast<const unsigned char*>(vals);
+                for (int nb = n0 - lead + tid; nb < n1; nb += U * kEmitThreads) {
+                    VT* p[R];
+#pragma unroll
+                    for (int r = 0; r < R; ++r) p[r] = orow[r] + nb;
+                    RV x[U];
+                    bool ok[U];
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        const int n = nb + u * kEmitThreads;
+                        ok[u] = (unsigned)(n - n0) < count;
+                        if (ok[u]) x[u] = RV::load(reinterpret_cast<const VT*>(vbytes + (unsigned)sl_base[n] * (unsigned)B));
+                    }
+#pragma unroll
+                    for (int u = 0; u < U; ++u)
+                        if (ok[u]) {
+#pragma unroll
+                            for (int r = 0; r < R; ++r) __stcs(p[r] + u * kEmitThreads, x[u].v[r]);
+                        }
+                }
+                // 5. pieces of spanning nodes that overlap this tile (reduced by span_kernel, which runs next on the stream)
+                for (int i = pc0 + tid; i < pc1; i += kEmitThreads) {
+                    const bool mine = i == pc0 + tid;
+                    const RV x = RV::load(vals + (mine ? my_pslot : (int)__ldg(P.piece_slot + i)) * R);
+                    const int idx = mine ? my_pidx : __ldg(P.piece_idx + i);
+#pragma unroll
+                    for (int r = 0; r < R; ++r) part[(size_t)min(b0 + r, n_rows - 1) * P.n_pieces + idx] = x.v[r];
+                }
+            }
+            GT_TRACE(10);
+            mbar_arrive(empty + (k & 1));  // this thread no longer reads the value array
+            if (next_new) {
+                group_sync<2, kEmitThreads>();  // everyone is done with this tile's emit slots
+                if (tid == 0) fetch_slots(nb3[1], nb3[2]);
+                nb3[0] = nb3[1]; nb3[1] = nb3[2];
+                nb3[2] = __ldg(P.tile_node_lo + min(tn + 2, P.NT));
+            }
+            new_tile = next_new;
+            t = tn; g = gn; j = jn;
+        }
     }
-    if (lane == 0 && warp >= kStoreWarp0) bulk_wait_all();  // the output is complete in global memory before the CTA retires
 }
 
 // ---- phase 3: nodes whose leaf range crosses tiles, reduced from their per-tile pieces (fp64 for sums) ------------
 // One thread per (spanning node, row); consecutive lanes take consecutive spanning nodes of one row, whose pieces
 // are adjacent in `part`.  Runs after tile_kernel in stream order and overwrites the placeholder it emitted.
-template <typename VT, int OP>
-__global__ void __launch_bounds__(256) span_kernel(PlanView P, const VT* __restrict__ part, VT* __restrict__ out,
-                                                   int64_t ld_out, int n_rows) {
+// blockIdx.z selects the reduction when both were requested.
+template <typename VT>
+__global__ void __launch_bounds__(256) span_kernel(PlanView P, TileArgs<VT> A) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    pdl_wait();  // pieces and placeholders come from tile_kernel
+    pdl_trigger();
     if (k >= P.n_span) return;
+    const bool is_sum = (A.ops & GT_OP_SUM) && blockIdx.z == 0;
+    const VT* part = is_sum ? A.part_sum : A.part_max;
+    VT* out = is_sum ? A.out_sum : A.out_max;
     const int q0 = __ldg(P.span_pp + k), q1 = __ldg(P.span_pp + k + 1), node = __ldg(P.span_node + k);
-    using AT = typename std::conditional<OP == OP_SUM, double, VT>::type;
-    for (int b = blockIdx.y; b < n_rows; b += gridDim.y) {
+    for (int b = blockIdx.y; b < A.n_rows; b += gridDim.y) {
         const VT* pr = part + (size_t)b * P.n_pieces;
-        AT acc = op_ident<OP, AT>();
-#pragma unroll 8
-        for (int q = q0; q < q1; ++q) acc = op_apply<OP, AT>(acc, (AT)pr[q]);
-        out[(size_t)b * ld_out + node] = q1 > q0 ? (VT)acc : VT(0);
+        VT res = VT(0);
+        if (q1 > q0) {
+            if (is_sum) {
+                double acc = 0.0;
+#pragma unroll 4
+                for (int q = q0; q < q1; ++q) acc += (double)pr[q];
+                res = (VT)acc;
+            } else {
+                VT acc = -std::numeric_limits<VT>::infinity();
+#pragma unroll 4
+                for (int q = q0; q < q1; ++q) acc = fmax(acc, pr[q]);
+                res = acc;
+            }
+        }
+        out[(size_t)b * A.ld_out + node] = res;
     }
 }
 
@@ -764,18 +883,20 @@ template <typename K> static cudaError_t allow_smem(K kernel, size_t bytes) {
     return allow_smem_impl(reinterpret_cast<const void*>(kernel), bytes);
 }
 
-// Scratch layout for one chunk of `rows` rows: z [rows][Zrow] VT | part [rows][n_pieces] VT
+// Scratch layout for one chunk of `rows` rows: z [rows][Zrow] VT | part_sum [rows][n_pieces] VT | part_max likewise
 template <typename VT> struct Scratch {
-    VT* z; VT* part;
+    VT* z; VT* part_sum; VT* part_max;
+    static size_t pad(size_t b) { return (b + 255) & ~size_t(255); }
     Scratch(const PlanView& v, void* base, int64_t rows) {
         char* p = static_cast<char*>(base);
         z = reinterpret_cast<VT*>(p);
-        p += (((size_t)rows * v.Zrow * sizeof(VT)) + 255) & ~size_t(255);
-        part = reinterpret_cast<VT*>(p);
+        p += pad((size_t)rows * v.Zrow * sizeof(VT));
+        part_sum = reinterpret_cast<VT*>(p);
+        p += pad((size_t)rows * v.n_pieces * sizeof(VT));
+        part_max = reinterpret_cast<VT*>(p);
     }
     static size_t total(const PlanView& v, int64_t rows) {
-        return ((((size_t)rows * v.Zrow * sizeof(VT)) + 255) & ~size_t(255)) +
-               ((((size_t)rows * v.n_pieces * sizeof(VT)) + 255) & ~size_t(255));
+        return pad((size_t)rows * v.Zrow * sizeof(VT)) + 2 * pad((size_t)rows * v.n_pieces * sizeof(VT));
     }
 };
 
@@ -785,9 +906,8 @@ static int launch_permute(const PlanView& v, const void* ws, int64_t ld_ws, cons
     const size_t smem = permute_smem<VT, R>(v);
     GT_CUDA(allow_smem(permute_kernel<VT, IN_T, R>, smem));
     dim3 grid((unsigned)v.NS, (unsigned)((rows + R - 1) / R));
-    permute_kernel<VT, IN_T, R><<<grid, kThreads, smem, st>>>(v, static_cast<const IN_T*>(ws), ld_ws, sc.z, rows,
-                                                             log_input ? 1 : 0);
-    GT_CUDA(cudaGetLastError());
+    GT_CUDA(launch_pdl(permute_kernel<VT, IN_T, R>, grid, dim3(kThreads), smem, st, v, static_cast<const IN_T*>(ws), ld_ws,
+                       sc.z, rows, log_input ? 1 : 0));
     return GT_OK;
 }
 
@@ -821,10 +941,12 @@ static int sm_count() {
     return n;
 }
 
-template <typename VT, int R, int OP>
-static int launch_tile(const PlanView& v, const Scratch<VT>& sc, VT* out, int64_t ld_out, int rows, cudaStream_t st) {
+template <typename VT, int R>
+static int launch_tile(const PlanView& v, const Scratch<VT>& sc, VT* out_sum, VT* out_max, int64_t ld_out, int rows,
+                       unsigned ops, unsigned phases, cudaStream_t st) {
     if (v.NT == 0) {  // empty vocabulary: the root is the only node and has no mass
-        GT_CUDA(cudaMemset2DAsync(out, (size_t)ld_out * sizeof(VT), 0, (size_t)v.N * sizeof(VT), (size_t)rows, st));
+        for (VT* out : {out_sum, out_max})
+            if (out) GT_CUDA(cudaMemset2DAsync(out, (size_t)ld_out * sizeof(VT), 0, (size_t)v.N * sizeof(VT), (size_t)rows, st));
         return GT_OK;
     }
     const size_t smem = tile_smem<VT, R>(v);
@@ -832,17 +954,19 @@ static int launch_tile(const PlanView& v, const Scratch<VT>& sc, VT* out, int64_
         set_error("tile plan needs %zu bytes of shared memory per CTA (limit 232448): use a smaller tile or fewer rows per CTA", smem);
         return GT_ERR_LIMIT;
     }
-    GT_CUDA(allow_smem(tile_kernel<VT, R, OP>, smem));
-    // persistent grid: one CTA per resident slot, each takes a contiguous run of (tile, row group) items
-    const int64_t items = (int64_t)v.NT * ((rows + R - 1) / R);
-    const int slots = sm_count() * resident_ctas(reinterpret_cast<const void*>(tile_kernel<VT, R, OP>), kTileThreads, smem);
+    GT_CUDA(allow_smem(tile_kernel<VT, R>, smem));
+    TileArgs<VT> A;
+    A.z = sc.z; A.out_sum = out_sum; A.out_max = out_max; A.part_sum = sc.part_sum; A.part_max = sc.part_max;
+    A.ld_out = ld_out; A.n_rows = rows; A.ops = ops;
+    const int nops = (ops == (unsigned)(GT_OP_SUM | GT_OP_MAX)) ? 2 : 1;
+    // persistent grid: one CTA per resident slot, each takes a contiguous run of (tile, row group, reduction) items
+    const int64_t items = (int64_t)v.NT * ((rows + R - 1) / R) * nops;
+    const int slots = sm_count() * resident_ctas(reinterpret_cast<const void*>(tile_kernel<VT, R>), kTileThreads, smem);
     const unsigned grid = (unsigned)std::min<int64_t>(items, slots);
-    tile_kernel<VT, R, OP><<<grid, kTileThreads, smem, st>>>(v, sc.z, out, ld_out, sc.part, rows);
-    GT_CUDA(cudaGetLastError());
-    if (v.n_span > 0) {
-        dim3 sgrid((unsigned)((v.n_span + 255) / 256), (unsigned)std::min(rows, 4096));
-        span_kernel<VT, OP><<<sgrid, 256, 0, st>>>(v, sc.part, out, ld_out, rows);
-        GT_CUDA(cudaGetLastError());
+    if (phases & GT_FLAG_PHASE_TILE) GT_CUDA(launch_pdl(tile_kernel<VT, R>, dim3(grid), dim3(kTileThreads), smem, st, v, A));
+    if (v.n_span > 0 && (phases & GT_FLAG_PHASE_SPAN)) {
+        dim3 sgrid((unsigned)((v.n_span + 255) / 256), (unsigned)std::min(rows, 4096), (unsigned)nops);
+        GT_CUDA(launch_pdl(span_kernel<VT>, sgrid, dim3(256), 0, st, v, A));
     }
     return GT_OK;
 }
@@ -853,7 +977,7 @@ static int reduce_typed(const PlanView& v, const void* ws, int in_type, int64_t 
                         size_t workspace_bytes, cudaStream_t st) {
     // rows per chunk: what the caller's scratch can stage, rounded down to whole row groups when it holds at least
     // one (a partial row group is legal: the kernels alias the missing rows to the last valid one)
-    const size_t per_row = (size_t)(v.Zrow + v.n_pieces) * sizeof(VT);
+    const size_t per_row = (size_t)(v.Zrow + 2 * v.n_pieces) * sizeof(VT);
     int64_t chunk = std::min<int64_t>(n_rows, 32768);
     if (Scratch<VT>::total(v, chunk) > workspace_bytes) {
         chunk = std::min<int64_t>(chunk, (int64_t)(workspace_bytes / std::max<size_t>(per_row, 1)));
@@ -888,12 +1012,10 @@ static int reduce_typed(const PlanView& v, const void* ws, int in_type, int64_t 
 #undef GT_PERMUTE
             if (rc != GT_OK) return rc;
         }
-        if ((ops & GT_OP_SUM) && (phases & GT_FLAG_PHASE_TILE)) {
-            rc = launch_tile<VT, R, OP_SUM>(v, sc, static_cast<VT*>(out_sum) + (size_t)r0 * ld_out, ld_out, rows, st);
-            if (rc != GT_OK) return rc;
-        }
-        if ((ops & GT_OP_MAX) && (phases & GT_FLAG_PHASE_TILE)) {
-            rc = launch_tile<VT, R, OP_MAX>(v, sc, static_cast<VT*>(out_max) + (size_t)r0 * ld_out, ld_out, rows, st);
+        if (phases & (GT_FLAG_PHASE_TILE | GT_FLAG_PHASE_SPAN)) {
+            rc = launch_tile<VT, R>(v, sc, (ops & GT_OP_SUM) ? static_cast<VT*>(out_sum) + (size_t)r0 * ld_out : nullptr,
+                                    (ops & GT_OP_MAX) ? static_cast<VT*>(out_max) + (size_t)r0 * ld_out : nullptr, ld_out, rows,
+                                    ops, phases, st);
             if (rc != GT_OK) return rc;
         }
     }

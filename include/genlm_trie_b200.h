@@ -124,10 +124,11 @@ size_t gt_workspace_bytes(const gt_trie* t, int64_t max_rows);
 
 #define GT_FLAG_LOG_INPUT 1u /* rows hold log-weights: exp() is fused into the load (-inf -> 0) */
 /* Profiling aids: restrict a call to some phases (default: all).  Used by bench.py to time one kernel in
- * isolation with CUDA events; results are only complete when both phases have run in order. */
+ * isolation with CUDA events; results are only complete when all phases have run in order. */
 #define GT_FLAG_PHASE_PERMUTE 0x100u
-#define GT_FLAG_PHASE_TILE 0x200u /* tile kernel + the small spanning-node kernel that follows it */
-#define GT_FLAG_PHASE_MASK 0x300u
+#define GT_FLAG_PHASE_TILE 0x200u /* tile kernel */
+#define GT_FLAG_PHASE_SPAN 0x400u /* the small spanning-node kernel that follows it */
+#define GT_FLAG_PHASE_MASK 0x700u
 
 /* Input / output element types. */
 #define GT_F32 0

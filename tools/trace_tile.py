@@ -1,7 +1,8 @@
 """Prints the timeline of tile_kernel's pipeline (GT_TRACE=1): per item, the SM-clock durations between the events
 stamped by thread 0.
 
-  0 item start | 1 rows landed (A) | 2 scatter done | 3 next fetch issued | 4 pyramid done | 5 ELL done | 6 output staged + issued
+  compute group leader: 0 start | 1 value array free | 2 rows landed | 3 scatter done | 4 (fetch issued) | 5 pyramid done |
+  6 terms ready + barrier | 7 ELL done;   emit group leader: 8 start | 9 value array full | 10 emit done
 """
 import ctypes
 import os
@@ -34,13 +35,10 @@ eng.reduce(ws[0], ("sum",), out_sum=osum[0])
 torch.cuda.synchronize()
 _lib.lib.gt_debug_read_trace(eng._handle, 0, buf.ctypes.data, n, dims)
 tr = buf.reshape(dims[0], dims[1], dims[2]).astype(np.float64)
-ev = {"wait rows(A)": (0, 1), "scatter+bar": (1, 2), "issue fetch": (2, 3), "pyramid+bar": (3, 4), "ELL (own share)": (4, 22),
-      "wait_read+bar": (22, 5), "head+pieces": (5, 6),
-      "c0 gather": (6, 7), "c0 wait_read": (7, 8), "c0 bar": (8, 9), "c0 issue": (9, 10),
-      "c1 gather": (10, 11), "c1 wait_read": (11, 12), "c1 bar": (12, 13), "c1 issue": (13, 14),
-      "c2 gather": (14, 15), "c2 wait_read": (15, 16), "c2 bar": (16, 17), "c2 issue": (17, 18),
-      "item total": (0, 23)}
-valid = tr[:, :, 23] > 0
+ev = {"C wait empty": (0, 1), "C wait rows(A)": (1, 2), "C scatter+bar": (2, 3), "C issue fetch": (3, 4), "C pyramid": (4, 5),
+      "C wait terms+bar": (5, 6), "C ELL": (6, 7), "C item total": (0, 7),
+      "E wait full": (8, 9), "E emit loop": (9, 10)}
+valid = tr[:, :, 7] > 0
 print("CTAs with items:", int(valid.any(axis=1).sum()), " items traced:", int(valid.sum()))
 for first in (True, False):
     sel = valid.copy()
@@ -56,7 +54,13 @@ for first in (True, False):
         if not ok.any():
             continue
         d = (tr[:, :, b] - tr[:, :, a])[ok]
-        print(f"  {name:16s} mean {d.mean():8.0f}  p50 {np.median(d):8.0f}  p90 {np.percentile(d, 90):8.0f} cycles  (n={ok.sum()})")
-span = tr[:, :, 23].max(axis=1) - np.where(valid, tr[:, :, 0], np.inf).min(axis=1)
+        print(f"  {name:18s} mean {d.mean():8.0f}  p50 {np.median(d):8.0f}  p90 {np.percentile(d, 90):8.0f} cycles  (n={ok.sum()})")
+span = tr[:, :, 10].max(axis=1) - np.where(valid, tr[:, :, 0], np.inf).min(axis=1)
 span = span[valid.any(axis=1)]
-print(f"CTA lifetime (first event -> last output): mean {span.mean():.0f}  max {span.max():.0f} cycles")
+print(f"CTA lifetime (first event -> last emit): mean {span.mean():.0f}  max {span.max():.0f} cycles")
+c = 10
+print("CTA 10 timeline (cycles since its first event):")
+t0 = tr[c, 0, 0]
+for k in range(dims[1]):
+    if tr[c, k, 7] > 0:
+        print("  item", k, " ".join(f"{int(x - t0):7d}" for x in tr[c, k, :11]))
