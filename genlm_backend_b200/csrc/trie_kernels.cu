@@ -33,7 +33,7 @@ namespace gt {
 
 struct PlanView {
     int32_t T, logT, Q, NT, NS, SV;  // SV = value slots per tile in shared memory
-    int32_t R, max_tile_nodes, max_tile_ell_rows, max_tile_chunks, max_tile_z;
+    int32_t R, max_tile_nodes, max_tile_ell_rows, max_tile_chunks, max_tile_z, max_seg_recs;
     int64_t V, N, Zrow;
     const int32_t* p1_chunk_ptr; const int4* p1_rec;
     const int32_t* z_tile_off; const uint16_t* p2_slot;
@@ -356,6 +356,94 @@ template <typename VT, int R> struct RowVec {
     }
 };
 
+// ---- phase 1, bulk-copy variant: persistent CTAs, rows fetched by the copy engine one item ahead -------------------
+// Used when every row segment is 16-byte aligned (row stride and row length multiples of 16 bytes).  An item is
+// (segment s, group of RP rows); items are numbered segment-major and every CTA takes one contiguous run, so the
+// segment's records stay in shared memory across consecutive items.  Rows land in shared memory in their input type
+// (two stages); conversion / exp happens in the gather.
+template <typename VT, typename IN_T, int RP>
+__global__ void __launch_bounds__(kThreads, 2) permute_bulk_kernel(PlanView P, const IN_T* __restrict__ ws, int64_t ld_ws,
+                                                                   VT* __restrict__ z, int n_rows, int log_input) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int Q = P.Q;
+    IN_T* stage = reinterpret_cast<IN_T*>(smem_raw);                                       // [2][RP][Q]
+    int4* s_rec = reinterpret_cast<int4*>(smem_raw + (size_t)2 * RP * Q * sizeof(IN_T));   // [max_seg_recs]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(s_rec) + (size_t)P.max_seg_recs * 16);
+    uint64_t* full = bars;        // [2] rows of a stage have landed
+    uint64_t* rec_bar = bars + 2; // records of the current segment have landed
+
+    const int tid = threadIdx.x;
+    const int RGp = (n_rows + RP - 1) / RP;
+    const int n_items = P.NS * RGp;
+    const int i0 = (int)((int64_t)blockIdx.x * n_items / gridDim.x);
+    const int i1 = (int)((int64_t)(blockIdx.x + 1) * n_items / gridDim.x);
+    if (i0 >= i1) return;
+    const bool lg = log_input != 0;
+
+    auto seg_len = [&](int s) { return (int)min((int64_t)Q, P.V - (int64_t)s * Q); };
+    auto fetch_rows = [&](int s, int rg, int st) {  // thread 0
+        const int nrows = min(RP, n_rows - rg * RP);
+        const unsigned bytes = (unsigned)seg_len(s) * (unsigned)sizeof(IN_T);
+        mbar_expect_tx(full + st, (unsigned)nrows * bytes);
+        for (int r = 0; r < nrows; ++r)
+            bulk_g2s(stage + ((size_t)st * RP + r) * Q, ws + (size_t)(rg * RP + r) * ld_ws + (size_t)s * Q, bytes, full + st);
+    };
+    auto fetch_recs = [&](int c0, int c1) {  // thread 0
+        mbar_expect_tx(rec_bar, (unsigned)(c1 - c0) * 16u);
+        if (c1 > c0) bulk_g2s(s_rec, P.p1_rec + c0, (unsigned)(c1 - c0) * 16u, rec_bar);
+    };
+
+    int s = i0 / RGp, rg = i0 - s * RGp;
+    int c0 = __ldg(P.p1_chunk_ptr + s), c1 = __ldg(P.p1_chunk_ptr + s + 1), c2 = __ldg(P.p1_chunk_ptr + min(s + 2, P.NS));
+    if (tid == 0) {
+        mbar_init(full, 1); mbar_init(full + 1, 1); mbar_init(rec_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        fetch_recs(c0, c1);  // plan metadata: may run ahead of the previous kernel's completion
+    }
+    pdl_wait();  // the previous call's tile kernel may still be reading z; ws may come from a kernel of the caller
+    if (tid == 0) fetch_rows(s, rg, 0);
+    __syncthreads();
+
+    bool new_seg = true;
+    unsigned par_rec = 0;
+    for (int item = i0; item < i1; ++item) {
+        const int k = item - i0, st = k & 1;
+        int sn = s, rgn = rg + 1;
+        if (rgn == RGp) { rgn = 0; ++sn; }
+        const bool has_next = item + 1 < i1;
+        if (tid == 0 && has_next) fetch_rows(sn, rgn, st ^ 1);  // the other stage was released by the barrier below
+        if (new_seg) { mbar_wait(rec_bar, par_rec); par_rec ^= 1u; }
+        mbar_wait(full + st, (unsigned)(k >> 1) & 1u);
+
+        const int nrows = min(RP, n_rows - rg * RP);
+        const IN_T* sr0 = stage + (size_t)st * RP * Q;
+        const int nrec = c1 - c0;
+        for (int i = tid; i < nrec; i += kThreads) {
+            const int4 rec = s_rec[i];
+            const unsigned s0 = (unsigned)rec.y & 0xFFFFu, s1 = (unsigned)rec.y >> 16;
+            const unsigned s2 = (unsigned)rec.z & 0xFFFFu, s3 = (unsigned)rec.z >> 16;
+#pragma unroll
+            for (int r = 0; r < RP; ++r) {
+                if (r < nrows) {
+                    const IN_T* sr = sr0 + (size_t)r * Q;
+                    const VT a = s0 != 0xFFFFu ? convert_in<VT, IN_T>(sr[s0], lg) : VT(0);
+                    const VT b = s1 != 0xFFFFu ? convert_in<VT, IN_T>(sr[s1], lg) : VT(0);
+                    const VT c = s2 != 0xFFFFu ? convert_in<VT, IN_T>(sr[s2], lg) : VT(0);
+                    const VT d = s3 != 0xFFFFu ? convert_in<VT, IN_T>(sr[s3], lg) : VT(0);
+                    store4<VT>(z + (size_t)(rg * RP + r) * P.Zrow + rec.x, a, b, c, d);
+                }
+            }
+        }
+        __syncthreads();  // this stage (and, on a segment change, the record buffer) may be overwritten
+        new_seg = has_next && sn != s;
+        if (new_seg) {
+            c0 = c1; c1 = c2; c2 = __ldg(P.p1_chunk_ptr + min(sn + 2, P.NS));
+            if (tid == 0) fetch_recs(c0, c1);
+        }
+        s = sn; rg = rgn;
+    }
+}
+
 constexpr int kTileThreads = 512;
 // trace layout: [kTraceCtas][kTraceItems][kTraceEvents] SM-clock stamps
 constexpr int kTraceCtas = 512, kTraceItems = 32, kTraceEvents = 12;
@@ -365,7 +453,7 @@ constexpr int kTraceCtas = 512, kTraceItems = 32, kTraceEvents = 12;
             P.trace[((size_t)blockIdx.x * kTraceItems + k) * kTraceEvents + (ev)] = clock64();               \
     } while (0)
 #ifndef GT_COMPUTE_WARPS
-#define GT_COMPUTE_WARPS 12
+#define GT_COMPUTE_WARPS 8
 #endif
 constexpr int kComputeThreads = 32 * GT_COMPUTE_WARPS;        // warps 0 .. GT_COMPUTE_WARPS-1
 constexpr int kEmitThreads = kTileThreads - kComputeThreads;  // the remaining warps
@@ -541,9 +629,7 @@ __global__ void __launch_bounds__(kTileThreads, 2) tile_kernel(PlanView P, TileA
         mbar_init(empty, kEmitThreads); mbar_init(empty + 1, kEmitThreads);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    pdl_wait();  // z comes from permute_kernel; the outputs may still be in use by the previous kernels of the chain
-    pdl_trigger();
-    __syncthreads();
+    __syncthreads();  // barriers initialised before anyone uses them
 
     if (threadIdx.x < kComputeThreads) {
         // =========================== compute group ===========================================================
@@ -583,7 +669,11 @@ __global__ void __launch_bounds__(kTileThreads, 2) tile_kernel(PlanView P, TileA
         int tg = i0 / nops, j = i0 - tg * nops;  // (tile, row group) index and which reduction of it
         int t = tg / RG, g = tg - t * RG;
         load_bound(t, 0); load_bound(t + 1, 1); load_bound(t + 2, 2);
-        if (tid == kIssueTid) { fetch_rows(g, zb[0], zb[1] - zb[0], true); fetch_terms(erb[0], erb[1], ecb[0], ecb[1]); }
+        // plan metadata may be fetched ahead of the previous kernel's completion; the staged rows may not
+        if (tid == kIssueTid) fetch_terms(erb[0], erb[1], ecb[0], ecb[1]);
+        pdl_wait();  // z comes from permute_kernel
+        pdl_trigger();
+        if (tid == kIssueTid) fetch_rows(g, zb[0], zb[1] - zb[0], true);
         bool new_tile = true;
         unsigned parB = 0;
         for (int item = i0; item < i1; ++item) {
@@ -658,6 +748,7 @@ __global__ void __launch_bounds__(kTileThreads, 2) tile_kernel(PlanView P, TileA
 #pragma unroll
         for (int q = 0; q < 3; ++q) nb3[q] = __ldg(P.tile_node_lo + min(t + q, P.NT));
         if (tid == 0) fetch_slots(nb3[0], nb3[1]);
+        pdl_wait();  // the outputs and piece buffers may still be in use by the previous kernels of the chain
         int pc0 = 0, pc1 = 0, my_pslot = 0, my_pidx = 0;
         bool new_tile = true;
         unsigned parC = 0;
@@ -751,13 +842,16 @@ __global__ void __launch_bounds__(kTileThreads, 2) tile_kernel(PlanView P, TileA
 template <typename VT>
 __global__ void __launch_bounds__(256) span_kernel(PlanView P, TileArgs<VT> A) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = k < P.n_span;
+    // plan metadata first: these loads may run ahead of the tile kernel's completion
+    const int q0 = live ? __ldg(P.span_pp + k) : 0, q1 = live ? __ldg(P.span_pp + k + 1) : 0;
+    const int node = live ? __ldg(P.span_node + k) : 0;
     pdl_wait();  // pieces and placeholders come from tile_kernel
     pdl_trigger();
-    if (k >= P.n_span) return;
+    if (!live) return;
     const bool is_sum = (A.ops & GT_OP_SUM) && blockIdx.z == 0;
     const VT* part = is_sum ? A.part_sum : A.part_max;
     VT* out = is_sum ? A.out_sum : A.out_max;
-    const int q0 = __ldg(P.span_pp + k), q1 = __ldg(P.span_pp + k + 1), node = __ldg(P.span_node + k);
     for (int b = blockIdx.y; b < A.n_rows; b += gridDim.y) {
         const VT* pr = part + (size_t)b * P.n_pieces;
         VT res = VT(0);
@@ -839,6 +933,8 @@ static DevicePlan* upload_plan(const Layout& L, const Plan& P, int device) {
     v.ell_terms = (const uint16_t*)(base + o_ell_terms); v.ell_row_ptr = (const int32_t*)(base + o_ell_row_ptr);
     v.R = P.R; v.max_tile_nodes = P.max_tile_nodes; v.max_tile_ell_rows = P.max_tile_ell_rows;
     v.max_tile_chunks = P.max_tile_chunks; v.max_tile_z = P.max_tile_z;
+    v.max_seg_recs = 0;
+    for (size_t i = 0; i + 1 < P.p1_chunk_ptr.size(); ++i) v.max_seg_recs = std::max(v.max_seg_recs, P.p1_chunk_ptr[i + 1] - P.p1_chunk_ptr[i]);
     v.tile_node_lo = (const int32_t*)(base + o_tile_node_lo); v.node_slot = (const uint16_t*)(base + o_node_slot);
     v.piece_ptr = (const int32_t*)(base + o_piece_ptr); v.piece_slot = (const uint16_t*)(base + o_piece_slot);
     v.piece_idx = (const int32_t*)(base + o_piece_idx);
@@ -900,17 +996,6 @@ template <typename VT> struct Scratch {
     }
 };
 
-template <typename VT, typename IN_T, int R>
-static int launch_permute(const PlanView& v, const void* ws, int64_t ld_ws, const Scratch<VT>& sc, int rows,
-                          bool log_input, cudaStream_t st) {
-    const size_t smem = permute_smem<VT, R>(v);
-    GT_CUDA(allow_smem(permute_kernel<VT, IN_T, R>, smem));
-    dim3 grid((unsigned)v.NS, (unsigned)((rows + R - 1) / R));
-    GT_CUDA(launch_pdl(permute_kernel<VT, IN_T, R>, grid, dim3(kThreads), smem, st, v, static_cast<const IN_T*>(ws), ld_ws,
-                       sc.z, rows, log_input ? 1 : 0));
-    return GT_OK;
-}
-
 // Resident CTAs per SM of a kernel at a given dynamic shared-memory size (cached: the query is not free).
 static int resident_ctas(const void* kernel, int threads, size_t smem) {
     static std::mutex mu;
@@ -939,6 +1024,38 @@ static int sm_count() {
     cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
     cache[dev] = n;
     return n;
+}
+
+template <typename IN_T, int RP> static size_t permute_bulk_smem(const PlanView& v) {
+    return (size_t)2 * RP * v.Q * sizeof(IN_T) + (size_t)v.max_seg_recs * 16 + 32;
+}
+// rows must be 16-byte aligned segment by segment for the copy engine
+template <typename IN_T> static bool permute_bulk_ok(const PlanView& v, const void* ws, int64_t ld_ws) {
+    return (reinterpret_cast<uintptr_t>(ws) & 15) == 0 && ((ld_ws * (int64_t)sizeof(IN_T)) & 15) == 0 &&
+           ((v.V * (int64_t)sizeof(IN_T)) & 15) == 0 && (((int64_t)v.Q * (int64_t)sizeof(IN_T)) & 15) == 0;
+}
+template <typename VT, typename IN_T, int RP>
+static int launch_permute_bulk(const PlanView& v, const void* ws, int64_t ld_ws, const Scratch<VT>& sc, int rows,
+                               bool log_input, cudaStream_t st) {
+    const size_t smem = permute_bulk_smem<IN_T, RP>(v);
+    GT_CUDA(allow_smem(permute_bulk_kernel<VT, IN_T, RP>, smem));
+    const int64_t items = (int64_t)v.NS * ((rows + RP - 1) / RP);
+    const int slots = sm_count() * resident_ctas(reinterpret_cast<const void*>(permute_bulk_kernel<VT, IN_T, RP>), kThreads, smem);
+    const unsigned grid = (unsigned)std::min<int64_t>(items, slots);
+    GT_CUDA(launch_pdl(permute_bulk_kernel<VT, IN_T, RP>, dim3(grid), dim3(kThreads), smem, st, v, static_cast<const IN_T*>(ws),
+                       ld_ws, sc.z, rows, log_input ? 1 : 0));
+    return GT_OK;
+}
+
+template <typename VT, typename IN_T, int R>
+static int launch_permute(const PlanView& v, const void* ws, int64_t ld_ws, const Scratch<VT>& sc, int rows,
+                          bool log_input, cudaStream_t st) {
+    const size_t smem = permute_smem<VT, R>(v);
+    GT_CUDA(allow_smem(permute_kernel<VT, IN_T, R>, smem));
+    dim3 grid((unsigned)v.NS, (unsigned)((rows + R - 1) / R));
+    GT_CUDA(launch_pdl(permute_kernel<VT, IN_T, R>, grid, dim3(kThreads), smem, st, v, static_cast<const IN_T*>(ws), ld_ws,
+                       sc.z, rows, log_input ? 1 : 0));
+    return GT_OK;
 }
 
 template <typename VT, int R>
@@ -1000,8 +1117,11 @@ static int reduce_typed(const PlanView& v, const void* ws, int in_type, int64_t 
             // rows per CTA in the permute phase: R unless the segment buffer would not fit in shared memory
             constexpr int RP = sizeof(VT) == 4 ? 2 : 1;  // rows per CTA of the permute kernel
             const bool wide = permute_smem<VT, RP>(v) <= kMaxSmem;
-#define GT_PERMUTE(IN_T) (wide ? launch_permute<VT, IN_T, RP>(v, wsr, ld_ws, sc, rows, log_input, st) \
-                               : launch_permute<VT, IN_T, 1>(v, wsr, ld_ws, sc, rows, log_input, st))
+            const bool use_bulk = getenv("GT_NO_BULK_PERMUTE") == nullptr;
+#define GT_PERMUTE(IN_T) ((use_bulk && permute_bulk_ok<IN_T>(v, wsr, ld_ws) && permute_bulk_smem<IN_T, 2>(v) <= 110 * 1024) \
+                              ? launch_permute_bulk<VT, IN_T, 2>(v, wsr, ld_ws, sc, rows, log_input, st)                      \
+                          : wide ? launch_permute<VT, IN_T, RP>(v, wsr, ld_ws, sc, rows, log_input, st)                     \
+                                 : launch_permute<VT, IN_T, 1>(v, wsr, ld_ws, sc, rows, log_input, st))
             switch (in_type) {
                 case GT_F32: rc = GT_PERMUTE(float); break;
                 case GT_F64: rc = GT_PERMUTE(double); break;
