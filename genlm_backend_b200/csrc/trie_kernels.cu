@@ -361,16 +361,16 @@ template <typename VT, int R> struct RowVec {
 // (segment s, group of RP rows); items are numbered segment-major and every CTA takes one contiguous run, so the
 // segment's records stay in shared memory across consecutive items.  Rows land in shared memory in their input type
 // (two stages); conversion / exp happens in the gather.
-template <typename VT, typename IN_T, int RP>
+template <typename VT, typename IN_T, int RP, int NST>
 __global__ void __launch_bounds__(kThreads, 2) permute_bulk_kernel(PlanView P, const IN_T* __restrict__ ws, int64_t ld_ws,
                                                                    VT* __restrict__ z, int n_rows, int log_input) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int Q = P.Q;
-    IN_T* stage = reinterpret_cast<IN_T*>(smem_raw);                                       // [2][RP][Q]
-    int4* s_rec = reinterpret_cast<int4*>(smem_raw + (size_t)2 * RP * Q * sizeof(IN_T));   // [max_seg_recs]
+    IN_T* stage = reinterpret_cast<IN_T*>(smem_raw);                                         // [NST][RP][Q]
+    int4* s_rec = reinterpret_cast<int4*>(smem_raw + (size_t)NST * RP * Q * sizeof(IN_T));   // [max_seg_recs]
     uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(s_rec) + (size_t)P.max_seg_recs * 16);
-    uint64_t* full = bars;        // [2] rows of a stage have landed
-    uint64_t* rec_bar = bars + 2; // records of the current segment have landed
+    uint64_t* full = bars;          // [NST] rows of a stage have landed
+    uint64_t* rec_bar = bars + NST; // records of the current segment have landed
 
     const int tid = threadIdx.x;
     const int RGp = (n_rows + RP - 1) / RP;
@@ -396,24 +396,33 @@ __global__ void __launch_bounds__(kThreads, 2) permute_bulk_kernel(PlanView P, c
     int s = i0 / RGp, rg = i0 - s * RGp;
     int c0 = __ldg(P.p1_chunk_ptr + s), c1 = __ldg(P.p1_chunk_ptr + s + 1), c2 = __ldg(P.p1_chunk_ptr + min(s + 2, P.NS));
     if (tid == 0) {
-        mbar_init(full, 1); mbar_init(full + 1, 1); mbar_init(rec_bar, 1);
+        for (int i = 0; i < NST; ++i) mbar_init(full + i, 1);
+        mbar_init(rec_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         fetch_recs(c0, c1);  // plan metadata: may run ahead of the previous kernel's completion
     }
     pdl_wait();  // the previous call's tile kernel may still be reading z; ws may come from a kernel of the caller
-    if (tid == 0) fetch_rows(s, rg, 0);
+    // item position -> (segment, row group), for the thread that issues the fetches NST-1 items ahead
+    int fs = s, frg = rg, fitem = i0;
+    auto fetch_advance = [&]() {
+        if (fitem < i1) fetch_rows(fs, frg, (fitem - i0) % NST);
+        ++fitem;
+        if (++frg == RGp) { frg = 0; ++fs; }
+    };
+    if (tid == 0)
+        for (int i = 0; i < NST - 1; ++i) fetch_advance();
     __syncthreads();
 
     bool new_seg = true;
     unsigned par_rec = 0;
     for (int item = i0; item < i1; ++item) {
-        const int k = item - i0, st = k & 1;
+        const int k = item - i0, st = k % NST;
         int sn = s, rgn = rg + 1;
         if (rgn == RGp) { rgn = 0; ++sn; }
         const bool has_next = item + 1 < i1;
-        if (tid == 0 && has_next) fetch_rows(sn, rgn, st ^ 1);  // the other stage was released by the barrier below
+        if (tid == 0) fetch_advance();  // item k + NST - 1: its stage was released by the barrier at the end of item k - 1
         if (new_seg) { mbar_wait(rec_bar, par_rec); par_rec ^= 1u; }
-        mbar_wait(full + st, (unsigned)(k >> 1) & 1u);
+        mbar_wait(full + st, (unsigned)(k / NST) & 1u);
 
         const int nrows = min(RP, n_rows - rg * RP);
         const IN_T* sr0 = stage + (size_t)st * RP * Q;
@@ -1026,23 +1035,23 @@ static int sm_count() {
     return n;
 }
 
-template <typename IN_T, int RP> static size_t permute_bulk_smem(const PlanView& v) {
-    return (size_t)2 * RP * v.Q * sizeof(IN_T) + (size_t)v.max_seg_recs * 16 + 32;
+template <typename IN_T, int RP, int NST> static size_t permute_bulk_smem(const PlanView& v) {
+    return (size_t)NST * RP * v.Q * sizeof(IN_T) + (size_t)v.max_seg_recs * 16 + 8 * (NST + 1);
 }
 // rows must be 16-byte aligned segment by segment for the copy engine
 template <typename IN_T> static bool permute_bulk_ok(const PlanView& v, const void* ws, int64_t ld_ws) {
     return (reinterpret_cast<uintptr_t>(ws) & 15) == 0 && ((ld_ws * (int64_t)sizeof(IN_T)) & 15) == 0 &&
            ((v.V * (int64_t)sizeof(IN_T)) & 15) == 0 && (((int64_t)v.Q * (int64_t)sizeof(IN_T)) & 15) == 0;
 }
-template <typename VT, typename IN_T, int RP>
+template <typename VT, typename IN_T, int RP, int NST>
 static int launch_permute_bulk(const PlanView& v, const void* ws, int64_t ld_ws, const Scratch<VT>& sc, int rows,
                                bool log_input, cudaStream_t st) {
-    const size_t smem = permute_bulk_smem<IN_T, RP>(v);
-    GT_CUDA(allow_smem(permute_bulk_kernel<VT, IN_T, RP>, smem));
+    const size_t smem = permute_bulk_smem<IN_T, RP, NST>(v);
+    GT_CUDA(allow_smem(permute_bulk_kernel<VT, IN_T, RP, NST>, smem));
     const int64_t items = (int64_t)v.NS * ((rows + RP - 1) / RP);
-    const int slots = sm_count() * resident_ctas(reinterpret_cast<const void*>(permute_bulk_kernel<VT, IN_T, RP>), kThreads, smem);
+    const int slots = sm_count() * resident_ctas(reinterpret_cast<const void*>(permute_bulk_kernel<VT, IN_T, RP, NST>), kThreads, smem);
     const unsigned grid = (unsigned)std::min<int64_t>(items, slots);
-    GT_CUDA(launch_pdl(permute_bulk_kernel<VT, IN_T, RP>, dim3(grid), dim3(kThreads), smem, st, v, static_cast<const IN_T*>(ws),
+    GT_CUDA(launch_pdl(permute_bulk_kernel<VT, IN_T, RP, NST>, dim3(grid), dim3(kThreads), smem, st, v, static_cast<const IN_T*>(ws),
                        ld_ws, sc.z, rows, log_input ? 1 : 0));
     return GT_OK;
 }
@@ -1118,8 +1127,14 @@ static int reduce_typed(const PlanView& v, const void* ws, int in_type, int64_t 
             constexpr int RP = sizeof(VT) == 4 ? 2 : 1;  // rows per CTA of the permute kernel
             const bool wide = permute_smem<VT, RP>(v) <= kMaxSmem;
             const bool use_bulk = getenv("GT_NO_BULK_PERMUTE") == nullptr;
-#define GT_PERMUTE(IN_T) ((use_bulk && permute_bulk_ok<IN_T>(v, wsr, ld_ws) && permute_bulk_smem<IN_T, 2>(v) <= 110 * 1024) \
-                              ? launch_permute_bulk<VT, IN_T, 2>(v, wsr, ld_ws, sc, rows, log_input, st)                      \
+#ifndef GT_PB_RP
+#define GT_PB_RP 2
+#endif
+#ifndef GT_PB_NST
+#define GT_PB_NST 2
+#endif
+#define GT_PERMUTE(IN_T) ((use_bulk && permute_bulk_ok<IN_T>(v, wsr, ld_ws) && permute_bulk_smem<IN_T, GT_PB_RP, GT_PB_NST>(v) <= 113 * 1024) \
+                              ? launch_permute_bulk<VT, IN_T, GT_PB_RP, GT_PB_NST>(v, wsr, ld_ws, sc, rows, log_input, st)      \
                           : wide ? launch_permute<VT, IN_T, RP>(v, wsr, ld_ws, sc, rows, log_input, st)                     \
                                  : launch_permute<VT, IN_T, 1>(v, wsr, ld_ws, sc, rows, log_input, st))
             switch (in_type) {

@@ -15,6 +15,7 @@ import torch
 
 from .base import TokenCharacterTrie
 from ._engine import require_cuda
+from ..sharding import row_blocks
 
 # rows per pipelined slice of the host->device->host path
 _PIPE_ROWS = 32
@@ -131,11 +132,9 @@ class ParallelTokenCharacterTrie(TokenCharacterTrie):
         outs = {op: torch.empty((B, ld), dtype=torch.float32, pin_memory=True) for op in ops}
         if B == 0:
             return {op: o.numpy()[:, :N] for op, o in outs.items()}
-        per = (B + len(devices) - 1) // len(devices)
         used = []
         keep = []
-        for di, index in enumerate(devices):
-            lo, hi = di * per, min(B, (di + 1) * per)
+        for index, (lo, hi) in zip(devices, row_blocks(B, len(devices))):
             if lo >= hi:
                 continue
             dev = torch.device("cuda", index)
