@@ -48,6 +48,7 @@ def parse_args():
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 10)")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sampler", action="store_true", help="skip the secondary sampler-kernel measurement")
     return ap.parse_args()
 
 
@@ -174,6 +175,43 @@ class ClockSampler(threading.Thread):
             return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0}
         return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_mhz,
                 "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ---- secondary measurement: the SMC row op (BASELINE.json configs[3], per-GPU share) ---------------------------------
+def sampler_metrics(dev, vocab, peak, rows=512, iters=20):
+    """Fused masked logsumexp + categorical draw over `rows` x `vocab` fp32 log-probabilities with a per-row bool mask
+    (one particle per row).  Device time from a CUDA graph rotating over two logit buffers larger than L2."""
+    import torch
+
+    from genlm_backend_b200 import smc
+
+    gen = torch.Generator(device=dev).manual_seed(0)
+    sets = [torch.log_softmax(torch.randn(rows, vocab, device=dev, generator=gen), dim=-1) for _ in range(2)]
+    masks = [torch.rand(rows, vocab, device=dev, generator=gen) < 0.5 for _ in range(2)]
+    out = {}
+    for name, mk in (("shared_f32_mask", lambda k: masks[0][0].float().log()), ("per_row_bool_mask", lambda k: masks[k])):
+        ms_ = [mk(0), mk(1)]
+        for i in range(3):
+            smc.masked_logsumexp_sample(sets[i % 2], ms_[i % 2], seed=i)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for k in range(2):
+                smc.masked_logsumexp_sample(sets[k], ms_[k], seed=k)
+        g.replay()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(iters):
+            g.replay()
+        b.record()
+        torch.cuda.synchronize()
+        sec = a.elapsed_time(b) / (2 * iters) / 1e3
+        bytes_per_row = 4 * vocab + (vocab if name == "per_row_bool_mask" else 0) + 8
+        out[name] = {"rows_per_s": rows / sec, "us_per_launch": sec * 1e6, "achieved_GBps": rows * bytes_per_row / sec / 1e9,
+                     "frac_of_hbm_peak": rows * bytes_per_row / sec / 1e9 / peak}
+    return {"kernel": "lse_sample_kernel<float>", "rows": rows, "vocab": vocab, "bound": "hbm",
+            "bytes_per_row": "4V (+V for a per-row bool mask) + 8", **out}
 
 
 # ---- our arm -------------------------------------------------------------------------------------------------------
@@ -324,9 +362,15 @@ def run_ours(args):
         return
 
     peak, peak_src = peaks()
-    bytes_per_dist = 4 * V + 4 * N
-    achieved = B * bytes_per_dist / (ms_tile / 1e3) / 1e9
-    path_achieved = B * (4 * V + 8 * N) * K / (ms_total / 1e3) / 1e9
+    bytes_one = B * (4 * V + 4 * N)    # one reduction: rows in, one node array out
+    bytes_both = B * (4 * V + 8 * N)   # both reductions from one launch (the step's tile_kernel launch)
+    achieved = bytes_both / (ms_tile_both / 1e3) / 1e9
+    path_achieved = bytes_both * K / (ms_total / 1e3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if os.path.exists(tpath) and V == 128256 and B == 64:
+        with open(tpath) as f:
+            traffic = json.load(f)["traffic_bytes_per_launch"]
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -346,10 +390,13 @@ def run_ours(args):
         },
         "gpu_launches": launches_per_step * K,
         "roofline": {
-            "bound": "hbm", "kernel": "tile_kernel<float,4> (weight_sum alone)", "achieved": achieved, "peak": peak, "unit": "GB/s",
-            "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-            "bytes_per_launch": B * bytes_per_dist, "ms_per_launch": ms_tile,
-            "note": "algorithmic bytes = (4V + 4N) per distribution x batch; kernel timed alone with CUDA events",
+            "bound": "hbm", "kernel": "tile_kernel<float,4> (both reductions of the step in one launch)", "achieved": achieved,
+            "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+            "bytes_per_launch": bytes_both, "ms_per_launch": ms_tile_both,
+            "one_reduction": {"bytes_per_launch": bytes_one, "ms_per_launch": ms_tile,
+                              "achieved": bytes_one / (ms_tile / 1e3) / 1e9, "frac": bytes_one / (ms_tile / 1e3) / 1e9 / peak},
+            "note": "algorithmic bytes = (4V + 8N) per distribution x batch; kernel timed alone with CUDA events from a CUDA graph "
+                    "rotating over the buffer sets; traffic = dram read+write of one launch from the ncu capture under profiles/",
         },
         "path_roofline": {
             "achieved": path_achieved, "peak": peak, "unit": "GB/s", "frac": path_achieved / peak,
@@ -359,6 +406,8 @@ def run_ours(args):
                       "span_both": ms_span_both, "sum_op_all_phases": ms_sum_op},
         "clocks": clocks.summary(),
     }
+    if world == 1 and not args.no_sampler:
+        line["sampler"] = sampler_metrics(dev, V, peak)
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_rate(args, trie._layout, trie.idx_to_leaf)
     print(json.dumps(line), flush=True)

@@ -22,6 +22,14 @@ namespace gt {
 constexpr int kSThreads = 512;
 constexpr float kLog2e = 1.4426950408889634f;
 
+// 2^x for x <= 0 (flush-to-zero below 2^-126: such terms vanish against the row maximum anyway): one MUFU, without
+// the range scaling of exp2f()
+__device__ __forceinline__ float fast_exp2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 struct SampleArgs {
     const void* logp; int64_t ld_logp; int64_t V; int n_rows;
     const void* mask; int mask_kind; int64_t mask_ld;
@@ -48,51 +56,82 @@ template <> __device__ __forceinline__ float elem_to_float<__half>(__half x) { r
 template <> __device__ __forceinline__ float elem_to_float<__nv_bfloat16>(__nv_bfloat16 x) { return __bfloat162float(x); }
 
 // Per-row view: groups of EPV elements aligned to 16 bytes in global memory.
-template <typename IN_T> struct RowView {
+template <typename IN_T, int MK> struct RowView {
     static constexpr int EPV = 16 / (int)sizeof(IN_T);
     const IN_T* row;        // first element of the row
     int phase;              // element offset of `row` inside its 16-byte line
     int V;
-    const void* mrow; int mask_kind; bool mask_vec;
+    const void* mrow; bool mask_vec;
+    static constexpr int mask_kind = MK;  // compile-time: no per-element dispatch
     float inv_temp;
 
     __device__ __forceinline__ int n_groups() const { return (phase + V + EPV - 1) / EPV; }
 
     __device__ __forceinline__ float mask_apply(float x, int i) const {
-        if (mask_kind == GT_MASK_ADD_F32) return x + static_cast<const float*>(mrow)[i];
-        if (mask_kind == GT_MASK_BOOL_U8) return static_cast<const uint8_t*>(mrow)[i] ? x : -INFINITY;
-        if (mask_kind == GT_MASK_BITS_U32) return (static_cast<const uint32_t*>(mrow)[i >> 5] >> (i & 31)) & 1u ? x : -INFINITY;
-        return x;
+        if constexpr (MK == GT_MASK_ADD_F32) return x + __ldg(static_cast<const float*>(mrow) + i);
+        else if constexpr (MK == GT_MASK_BOOL_U8) return __ldg(static_cast<const uint8_t*>(mrow) + i) ? x : -INFINITY;
+        else if constexpr (MK == GT_MASK_BITS_U32) return (__ldg(static_cast<const uint32_t*>(mrow) + (i >> 5)) >> (i & 31)) & 1u ? x : -INFINITY;
+        else return x;
     }
 
-    // x[k] = masked, temperature-scaled value of element (g*EPV - phase + k), -inf outside the row.
-    __device__ __forceinline__ void fetch(int g, float x[EPV]) const {
+    // A group is "interior" when all of its EPV elements lie inside the row: then it is one aligned 16-byte load.
+    __device__ __forceinline__ bool interior(int g) const {
         const int i0 = g * EPV - phase;
-        if (i0 >= 0 && i0 + EPV <= V) {
-            uint4 raw;
-            asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
-                         : "=r"(raw.x), "=r"(raw.y), "=r"(raw.z), "=r"(raw.w) : "l"(row + i0));
-            const IN_T* e = reinterpret_cast<const IN_T*>(&raw);
-#pragma unroll
-            for (int k = 0; k < EPV; ++k) x[k] = elem_to_float<IN_T>(e[k]) * inv_temp;
-            if (mask_kind == GT_MASK_ADD_F32 && mask_vec) {
-                const float4* m4 = reinterpret_cast<const float4*>(static_cast<const float*>(mrow) + i0);
-#pragma unroll
-                for (int q = 0; q < EPV / 4; ++q) {
-                    const float4 m = __ldg(m4 + q);
-                    x[4 * q] += m.x; x[4 * q + 1] += m.y; x[4 * q + 2] += m.z; x[4 * q + 3] += m.w;
-                }
-            } else if (mask_kind != GT_MASK_NONE) {
-#pragma unroll
-                for (int k = 0; k < EPV; ++k) x[k] = mask_apply(x[k], i0 + k);
-            }
-        } else {
-#pragma unroll
-            for (int k = 0; k < EPV; ++k) {
-                const int i = i0 + k;
-                x[k] = (i >= 0 && i < V) ? mask_apply(elem_to_float<IN_T>(row[i]) * inv_temp, i) : -INFINITY;
+        return i0 >= 0 && i0 + EPV <= V;
+    }
+    // What is requested ahead of its use for one interior group: the 16 bytes of the row and, for a byte mask, the
+    // EPV mask bytes (a per-row mask streams from HBM just like the row).
+    struct Raw { uint4 v; uint32_t m0, m1; };
+    __device__ __forceinline__ Raw issue(int g) const {
+        Raw r;
+        const int i0 = g * EPV - phase;
+        asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                     : "=r"(r.v.x), "=r"(r.v.y), "=r"(r.v.z), "=r"(r.v.w) : "l"(row + i0));
+        r.m0 = r.m1 = 0;
+        if (MK == GT_MASK_BOOL_U8 && mask_vec) {
+            const uint8_t* mp = static_cast<const uint8_t*>(mrow) + i0;
+            if constexpr (EPV <= 4) {
+                r.m0 = __ldg(reinterpret_cast<const uint32_t*>(mp));
+            } else {
+                const uint2 t = __ldg(reinterpret_cast<const uint2*>(mp));
+                r.m0 = t.x; r.m1 = t.y;
             }
         }
+        return r;
+    }
+    // x[k] = masked, temperature-scaled value of element (g*EPV - phase + k) from an issued load
+    __device__ __forceinline__ void finish(int g, const Raw& raw, float x[EPV]) const {
+        const int i0 = g * EPV - phase;
+        const IN_T* e = reinterpret_cast<const IN_T*>(&raw.v);
+#pragma unroll
+        for (int k = 0; k < EPV; ++k) x[k] = elem_to_float<IN_T>(e[k]) * inv_temp;
+        if (MK == GT_MASK_ADD_F32 && mask_vec) {
+            const float4* m4 = reinterpret_cast<const float4*>(static_cast<const float*>(mrow) + i0);
+#pragma unroll
+            for (int q = 0; q < EPV / 4; ++q) {
+                const float4 m = __ldg(m4 + q);
+                x[4 * q] += m.x; x[4 * q + 1] += m.y; x[4 * q + 2] += m.z; x[4 * q + 3] += m.w;
+            }
+        } else if (MK == GT_MASK_BOOL_U8 && mask_vec) {
+#pragma unroll
+            for (int k = 0; k < EPV; ++k) x[k] = (((k < 4 ? raw.m0 : raw.m1) >> (8 * (k & 3))) & 0xFFu) ? x[k] : -INFINITY;
+        } else if (MK != GT_MASK_NONE) {
+#pragma unroll
+            for (int k = 0; k < EPV; ++k) x[k] = mask_apply(x[k], i0 + k);
+        }
+    }
+    // edge groups (first / last of an unaligned row): element-wise, -inf outside the row
+    __device__ __forceinline__ void fetch_edge(int g, float x[EPV]) const {
+        const int i0 = g * EPV - phase;
+#pragma unroll
+        for (int k = 0; k < EPV; ++k) {
+            const int i = i0 + k;
+            x[k] = (i >= 0 && i < V) ? mask_apply(elem_to_float<IN_T>(row[i]) * inv_temp, i) : -INFINITY;
+        }
+    }
+    __device__ __forceinline__ void fetch(int g, float x[EPV]) const {
+        if (interior(g)) finish(g, issue(g), x);
+        else fetch_edge(g, x);
     }
 };
 
@@ -133,9 +172,9 @@ __device__ __forceinline__ void warp_find(const double* arr, int n, double targe
     }
 }
 
-template <typename IN_T>
-__global__ void __launch_bounds__(kSThreads) lse_sample_kernel(SampleArgs A) {
-    constexpr int EPV = RowView<IN_T>::EPV;
+template <typename IN_T, int MK>
+__global__ void __launch_bounds__(kSThreads, 2) lse_sample_kernel(SampleArgs A) {
+    constexpr int EPV = RowView<IN_T, MK>::EPV;
     __shared__ double s_mass[kSThreads];
     __shared__ float s_wmax[kSThreads / 32];
     __shared__ float s_M;
@@ -144,38 +183,58 @@ __global__ void __launch_bounds__(kSThreads) lse_sample_kernel(SampleArgs A) {
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int b = blockIdx.x; b < A.n_rows; b += gridDim.x) {
-        RowView<IN_T> rv;
+        RowView<IN_T, MK> rv;
         rv.row = static_cast<const IN_T*>(A.logp) + (size_t)b * A.ld_logp;
         rv.phase = (int)((reinterpret_cast<uintptr_t>(rv.row) & 15) / sizeof(IN_T));
-        rv.V = (int)A.V; rv.mask_kind = A.mask_kind; rv.inv_temp = A.inv_temp;
+        rv.V = (int)A.V; rv.inv_temp = A.inv_temp;
         rv.mrow = nullptr; rv.mask_vec = false;
-        if (A.mask_kind == GT_MASK_ADD_F32) {
+        if (MK == GT_MASK_ADD_F32) {
             const float* m = static_cast<const float*>(A.mask) + (size_t)b * A.mask_ld;
             rv.mrow = m;
             // group g starts at element g*EPV - phase: its mask address is 16-byte aligned iff the mask row
             // has the same phase (mod 4 floats) as the group grid
             rv.mask_vec = EPV >= 4 && ((((reinterpret_cast<uintptr_t>(m) >> 2) + 4u - (unsigned)(rv.phase & 3)) & 3u) == 0);
-        } else if (A.mask_kind == GT_MASK_BOOL_U8) {
-            rv.mrow = static_cast<const uint8_t*>(A.mask) + (size_t)b * A.mask_ld;
-        } else if (A.mask_kind == GT_MASK_BITS_U32) {
+        } else if (MK == GT_MASK_BOOL_U8) {
+            const uint8_t* m = static_cast<const uint8_t*>(A.mask) + (size_t)b * A.mask_ld;
+            rv.mrow = m;
+            // group g starts at element g*EPV - phase: its EPV mask bytes are one aligned word iff (m - phase) is
+            // aligned to EPV bytes; fp64 rows (EPV = 2) keep the per-element path
+            rv.mask_vec = EPV >= 4 && (((reinterpret_cast<uintptr_t>(m) + (uintptr_t)EPV - (uintptr_t)(rv.phase % EPV)) % (uintptr_t)EPV) == 0);
+        } else if (MK == GT_MASK_BITS_U32) {
             rv.mrow = static_cast<const uint32_t*>(A.mask) + (size_t)b * A.mask_ld;
         }
         const int ng = rv.n_groups();
 
         // ---- pass 1: online (max, sum exp) per thread ------------------------------------------------
+        // Software pipelined: the 16-byte loads of the next U groups are in flight while the current U groups are
+        // reduced, so every thread keeps U loads outstanding all the time.
         float m = -INFINITY, s = 0.f;
         constexpr int U = EPV >= 8 ? 2 : 4;  // independent 16-byte groups in flight per thread
+        typename RowView<IN_T, MK>::Raw raw[U];
+        bool inner[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int g = tid + u * kSThreads;
+            inner[u] = g < ng && rv.interior(g);
+            if (inner[u]) raw[u] = rv.issue(g);
+        }
         for (int gb = tid; gb < ng; gb += U * kSThreads) {
             float x[U][EPV];
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 const int g = gb + u * kSThreads;
-                if (g < ng) {
-                    rv.fetch(g, x[u]);
+                if (inner[u]) {
+                    rv.finish(g, raw[u], x[u]);
+                } else if (g < ng) {
+                    rv.fetch_edge(g, x[u]);
                 } else {
 #pragma unroll
                     for (int k = 0; k < EPV; ++k) x[u][k] = -INFINITY;
                 }
+                // the register set is free again: request this thread's group of the next round right away
+                const int gn = g + U * kSThreads;
+                inner[u] = gn < ng && rv.interior(gn);
+                if (inner[u]) raw[u] = rv.issue(gn);
             }
             float gm = x[0][0];
 #pragma unroll
@@ -183,7 +242,7 @@ __global__ void __launch_bounds__(kSThreads) lse_sample_kernel(SampleArgs A) {
 #pragma unroll
                 for (int k = 0; k < EPV; ++k) gm = fmaxf(gm, x[u][k]);
             if (gm > m) {  // rare once the running max has settled
-                s *= exp2f((m - gm) * kLog2e);  // m = -inf: s is still 0
+                s *= fast_exp2((m - gm) * kLog2e);  // m = -inf: s is still 0
                 m = gm;
             }
             if (m > -INFINITY) {
@@ -191,7 +250,7 @@ __global__ void __launch_bounds__(kSThreads) lse_sample_kernel(SampleArgs A) {
 #pragma unroll
                 for (int u = 0; u < U; ++u)
 #pragma unroll
-                    for (int k = 0; k < EPV; ++k) s += exp2f(fmaf(x[u][k], kLog2e, -ml));
+                    for (int k = 0; k < EPV; ++k) s += fast_exp2(fmaf(x[u][k], kLog2e, -ml));
             }
         }
         // A NaN element poisons s (fmaxf ignores it, so m stays finite): logZ becomes NaN, tok = -1.
@@ -248,7 +307,7 @@ __global__ void __launch_bounds__(kSThreads) lse_sample_kernel(SampleArgs A) {
             rv.fetch(g, x);
             const float ml = M * kLog2e;
 #pragma unroll
-            for (int k = 0; k < EPV; ++k) { x[k] = exp2f(fmaf(x[k], kLog2e, -ml)); local += (double)x[k]; }
+            for (int k = 0; k < EPV; ++k) { x[k] = fast_exp2(fmaf(x[k], kLog2e, -ml)); local += (double)x[k]; }
         } else {
 #pragma unroll
             for (int k = 0; k < EPV; ++k) x[k] = 0.f;
@@ -285,15 +344,23 @@ __global__ void __launch_bounds__(kSThreads) lse_sample_kernel(SampleArgs A) {
     }
 }
 
-template <typename IN_T> static int launch_sampler(const SampleArgs& A, cudaStream_t st) {
+template <typename IN_T, int MK> static int launch_sampler_mk(const SampleArgs& A, cudaStream_t st) {
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int grid = A.n_rows < sms * 8 ? A.n_rows : sms * 8;
-    lse_sample_kernel<IN_T><<<grid, kSThreads, 0, st>>>(A);
+    lse_sample_kernel<IN_T, MK><<<grid, kSThreads, 0, st>>>(A);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { set_error("lse_sample launch failed: %s", cudaGetErrorString(e)); return GT_ERR_CUDA; }
     return GT_OK;
+}
+template <typename IN_T> static int launch_sampler(const SampleArgs& A, cudaStream_t st) {
+    switch (A.mask_kind) {
+        case GT_MASK_NONE: return launch_sampler_mk<IN_T, GT_MASK_NONE>(A, st);
+        case GT_MASK_ADD_F32: return launch_sampler_mk<IN_T, GT_MASK_ADD_F32>(A, st);
+        case GT_MASK_BOOL_U8: return launch_sampler_mk<IN_T, GT_MASK_BOOL_U8>(A, st);
+        default: return launch_sampler_mk<IN_T, GT_MASK_BITS_U32>(A, st);
+    }
 }
 
 }  // namespace gt

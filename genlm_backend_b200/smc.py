@@ -27,7 +27,7 @@ def _mask_args(mask, B, V, device):
         mask = torch.as_tensor(mask)
     mask = mask.to(device)
     if mask.dtype == torch.bool:
-        kind, m = _lib.GT_MASK_BOOL_U8, mask.to(torch.uint8)
+        kind, m = _lib.GT_MASK_BOOL_U8, mask.view(torch.uint8)  # same bytes: no conversion pass
     elif mask.dtype == torch.uint8:
         kind, m = _lib.GT_MASK_BOOL_U8, mask
     elif mask.dtype == torch.int32 and mask.shape[-1] == (V + 31) // 32:

@@ -14,7 +14,7 @@ if "--" in args:
 for spec in args:
     T, Q, R = spec.split(",")
     env = dict(os.environ, GT_TILE_LEAVES=T, GT_SEG_POSITIONS=Q, GT_ROWS_PER_CTA=R)
-    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--no-cpu-baseline", "--e2e-steps", "2"] + extra,
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--no-cpu-baseline", "--no-sampler", "--e2e-steps", "2"] + extra,
                          env=env, capture_output=True, text=True)
     try:
         line = json.loads(out.stdout.strip().splitlines()[-1])
