@@ -14,6 +14,7 @@
 #include <cuda_bf16.h>
 
 #include <cstdint>
+#include <type_traits>
 
 #include "trie_internal.h"
 
@@ -56,6 +57,12 @@ template <> __device__ __forceinline__ float elem_to_float<__half>(__half x) { r
 template <> __device__ __forceinline__ float elem_to_float<__nv_bfloat16>(__nv_bfloat16 x) { return __bfloat162float(x); }
 
 // Per-row view: groups of EPV elements aligned to 16 bytes in global memory.
+//
+// Values are handled in "working units" that cost the fewest instructions per element: with an additive mask
+// y = logp * inv_temp + mask (one FFMA) and exponentials are 2^(y * log2e - ...); otherwise y is the raw log-prob
+// (masked-out elements replaced by -inf) and the temperature is folded into the exponent scale SC = inv_temp * log2e,
+// which is legal because inv_temp > 0 preserves the maximum.  unit() converts a working-unit value back to
+// temperature-scaled natural-log units.
 template <typename IN_T, int MK> struct RowView {
     static constexpr int EPV = 16 / (int)sizeof(IN_T);
     const IN_T* row;        // first element of the row
@@ -66,12 +73,15 @@ template <typename IN_T, int MK> struct RowView {
     float inv_temp;
 
     __device__ __forceinline__ int n_groups() const { return (phase + V + EPV - 1) / EPV; }
+    __device__ __forceinline__ float scale() const { return MK == GT_MASK_ADD_F32 ? kLog2e : inv_temp * kLog2e; }
+    __device__ __forceinline__ float unit() const { return MK == GT_MASK_ADD_F32 ? 1.f : inv_temp; }
 
-    __device__ __forceinline__ float mask_apply(float x, int i) const {
-        if constexpr (MK == GT_MASK_ADD_F32) return x + __ldg(static_cast<const float*>(mrow) + i);
-        else if constexpr (MK == GT_MASK_BOOL_U8) return __ldg(static_cast<const uint8_t*>(mrow) + i) ? x : -INFINITY;
-        else if constexpr (MK == GT_MASK_BITS_U32) return (__ldg(static_cast<const uint32_t*>(mrow) + (i >> 5)) >> (i & 31)) & 1u ? x : -INFINITY;
-        else return x;
+    // working-unit value of element i (scalar path: edge groups and masks that do not line up with the row's groups)
+    __device__ __forceinline__ float mask_apply(float e, int i) const {
+        if constexpr (MK == GT_MASK_ADD_F32) return fmaf(e, inv_temp, __ldg(static_cast<const float*>(mrow) + i));
+        else if constexpr (MK == GT_MASK_BOOL_U8) return __ldg(static_cast<const uint8_t*>(mrow) + i) ? e : -INFINITY;
+        else if constexpr (MK == GT_MASK_BITS_U32) return (__ldg(static_cast<const uint32_t*>(mrow) + (i >> 5)) >> (i & 31)) & 1u ? e : -INFINITY;
+        else return e;
     }
 
     // A group is "interior" when all of its EPV elements lie inside the row: then it is one aligned 16-byte load.
@@ -79,61 +89,129 @@ template <typename IN_T, int MK> struct RowView {
         const int i0 = g * EPV - phase;
         return i0 >= 0 && i0 + EPV <= V;
     }
-    // What is requested ahead of its use for one interior group: the 16 bytes of the row and, for a byte mask, the
-    // EPV mask bytes (a per-row mask streams from HBM just like the row).
-    struct Raw { uint4 v; uint32_t m0, m1; };
-    __device__ __forceinline__ Raw issue(int g) const {
+    // What is requested ahead of its use for one interior group: the 16 bytes of the row and the group's share of the
+    // mask -- 16/32 bytes of an additive mask, EPV bytes of a byte mask, one or two words of a bit mask.  issue() only
+    // requests: nothing here may consume a loaded value, or the requests of a round would serialise on each other.
+    // A Cursor holds the addresses of one interior group; the groups a thread visits are a fixed number of groups
+    // apart, so the loads of a round are the cursor plus compile-time offsets and advancing is a few pointer adds.
+    struct Raw { uint4 v; uint4 ma, mb; uint32_t m0, m1; };
+    struct Cursor {
+        const IN_T* p; const unsigned char* mp;
+        int i0;      // element index of the group's first element
+        int sh;      // bit mask: position of that element's bit in its word (the same for every group of a thread)
+        bool strad;  // bit mask: the group's bits continue in the next word (unaligned rows only)
+    };
+    __device__ __forceinline__ Cursor cursor(int g) const {
+        Cursor c;
+        c.i0 = g * EPV - phase;
+        c.p = row + c.i0;
+        c.sh = c.i0 & 31; c.strad = c.sh + EPV > 32;
+        if (MK == GT_MASK_ADD_F32) c.mp = reinterpret_cast<const unsigned char*>(static_cast<const float*>(mrow) + c.i0);
+        else if (MK == GT_MASK_BOOL_U8) c.mp = static_cast<const unsigned char*>(mrow) + c.i0;
+        else if (MK == GT_MASK_BITS_U32) c.mp = reinterpret_cast<const unsigned char*>(static_cast<const uint32_t*>(mrow) + (c.i0 >> 5));
+        else c.mp = nullptr;
+        return c;
+    }
+    // dg groups further on (dg * EPV is a multiple of 32 wherever this is used with a bit mask)
+    __device__ __forceinline__ void advance(Cursor& c, int dg) const {
+        const int de = dg * EPV;
+        c.i0 += de; c.p += de;
+        if (MK == GT_MASK_ADD_F32) c.mp += (size_t)de * 4;
+        else if (MK == GT_MASK_BOOL_U8) c.mp += de;
+        else if (MK == GT_MASK_BITS_U32) c.mp += de >> 3;
+    }
+    // the group dg groups after the cursor
+    template <bool VEC> __device__ __forceinline__ Raw issue(const Cursor& c, int dg) const {
         Raw r;
-        const int i0 = g * EPV - phase;
+        const int de = dg * EPV;
         asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
-                     : "=r"(r.v.x), "=r"(r.v.y), "=r"(r.v.z), "=r"(r.v.w) : "l"(row + i0));
+                     : "=r"(r.v.x), "=r"(r.v.y), "=r"(r.v.z), "=r"(r.v.w) : "l"(c.p + de));
         r.m0 = r.m1 = 0;
-        if (MK == GT_MASK_BOOL_U8 && mask_vec) {
-            const uint8_t* mp = static_cast<const uint8_t*>(mrow) + i0;
+        r.ma = r.mb = make_uint4(0, 0, 0, 0);
+        if (MK == GT_MASK_ADD_F32 && VEC) {
+            const uint4* m4 = reinterpret_cast<const uint4*>(c.mp + (size_t)de * 4);
+            r.ma = __ldg(m4);
+            if constexpr (EPV >= 8) r.mb = __ldg(m4 + 1);
+        } else if (MK == GT_MASK_BOOL_U8 && VEC) {
+            const unsigned char* mp = c.mp + de;
             if constexpr (EPV <= 4) {
                 r.m0 = __ldg(reinterpret_cast<const uint32_t*>(mp));
             } else {
                 const uint2 t = __ldg(reinterpret_cast<const uint2*>(mp));
                 r.m0 = t.x; r.m1 = t.y;
             }
+        } else if (MK == GT_MASK_BITS_U32) {
+            // the word that holds the group's first bit and, when the group straddles, the next one (which exists:
+            // the group is interior)
+            const uint32_t* mw = reinterpret_cast<const uint32_t*>(c.mp + (de >> 3));
+            r.m0 = __ldg(mw);
+            if (c.strad) r.m1 = __ldg(mw + 1);
         }
         return r;
     }
-    // x[k] = masked, temperature-scaled value of element (g*EPV - phase + k) from an issued load
-    __device__ __forceinline__ void finish(int g, const Raw& raw, float x[EPV]) const {
-        const int i0 = g * EPV - phase;
+    // y[k] = working-unit value of element k of the group dg groups after the cursor, from an issued load
+    template <bool VEC> __device__ __forceinline__ void finish(const Cursor& c, int dg, const Raw& raw, float y[EPV]) const {
         const IN_T* e = reinterpret_cast<const IN_T*>(&raw.v);
 #pragma unroll
-        for (int k = 0; k < EPV; ++k) x[k] = elem_to_float<IN_T>(e[k]) * inv_temp;
-        if (MK == GT_MASK_ADD_F32 && mask_vec) {
-            const float4* m4 = reinterpret_cast<const float4*>(static_cast<const float*>(mrow) + i0);
+        for (int k = 0; k < EPV; ++k) y[k] = elem_to_float<IN_T>(e[k]);
+        if (MK == GT_MASK_ADD_F32 && VEC) {
+            const float* ma = reinterpret_cast<const float*>(&raw.ma);
+            const float* mb = reinterpret_cast<const float*>(&raw.mb);
 #pragma unroll
-            for (int q = 0; q < EPV / 4; ++q) {
-                const float4 m = __ldg(m4 + q);
-                x[4 * q] += m.x; x[4 * q + 1] += m.y; x[4 * q + 2] += m.z; x[4 * q + 3] += m.w;
-            }
-        } else if (MK == GT_MASK_BOOL_U8 && mask_vec) {
+            for (int k = 0; k < EPV; ++k) y[k] = fmaf(y[k], inv_temp, k < 4 ? ma[k & 3] : mb[k & 3]);
+        } else if (MK == GT_MASK_BOOL_U8 && VEC) {
 #pragma unroll
-            for (int k = 0; k < EPV; ++k) x[k] = (((k < 4 ? raw.m0 : raw.m1) >> (8 * (k & 3))) & 0xFFu) ? x[k] : -INFINITY;
+            for (int k = 0; k < EPV; ++k) y[k] = ((k < 4 ? raw.m0 : raw.m1) & (0xFFu << (8 * (k & 3)))) ? y[k] : -INFINITY;
+        } else if (MK == GT_MASK_BITS_U32) {
+            const uint32_t bits = __funnelshift_r(raw.m0, raw.m1, c.sh);  // m1 = 0 when the group does not straddle
+#pragma unroll
+            for (int k = 0; k < EPV; ++k) y[k] = (bits & (1u << k)) ? y[k] : -INFINITY;
         } else if (MK != GT_MASK_NONE) {
+            const int i0 = c.i0 + dg * EPV;
 #pragma unroll
-            for (int k = 0; k < EPV; ++k) x[k] = mask_apply(x[k], i0 + k);
+            for (int k = 0; k < EPV; ++k) y[k] = mask_apply(y[k], i0 + k);
         }
     }
     // edge groups (first / last of an unaligned row): element-wise, -inf outside the row
-    __device__ __forceinline__ void fetch_edge(int g, float x[EPV]) const {
+    __device__ __forceinline__ void fetch_edge(int g, float y[EPV]) const {
         const int i0 = g * EPV - phase;
 #pragma unroll
         for (int k = 0; k < EPV; ++k) {
             const int i = i0 + k;
-            x[k] = (i >= 0 && i < V) ? mask_apply(elem_to_float<IN_T>(row[i]) * inv_temp, i) : -INFINITY;
+            y[k] = (i >= 0 && i < V) ? mask_apply(elem_to_float<IN_T>(row[i]), i) : -INFINITY;
         }
     }
-    __device__ __forceinline__ void fetch(int g, float x[EPV]) const {
-        if (interior(g)) finish(g, issue(g), x);
-        else fetch_edge(g, x);
+    __device__ __forceinline__ void fetch(int g, float y[EPV]) const {
+        if (interior(g)) {
+            const Cursor c = cursor(g);
+            if (mask_vec) finish<true>(c, 0, issue<true>(c, 0), y);
+            else finish<false>(c, 0, issue<false>(c, 0), y);
+        }
+        else fetch_edge(g, y);
     }
 };
+
+// Online (max, sum of 2^((y - max) * SC)) update with N more values.
+template <int N> __device__ __forceinline__ void online_update(const float (&y)[N], float SC, float& m, float& s) {
+    float gm = y[0];
+#pragma unroll
+    for (int k = 1; k < N; ++k) gm = fmaxf(gm, y[k]);
+    if (gm > m) {  // rare once the running max has settled
+        s *= fast_exp2((m - gm) * SC);  // m = -inf: s is still 0
+        m = gm;
+    }
+    if (m > -INFINITY) {
+        const float ms = -m * SC;
+        float t[N];
+#pragma unroll
+        for (int k = 0; k < N; ++k) t[k] = fast_exp2(fmaf(y[k], SC, ms));
+#pragma unroll
+        for (int w = 1; w < N; w <<= 1)  // pairwise: a short dependency chain
+#pragma unroll
+            for (int k = 0; k + w < N; k += 2 * w) t[k] += t[k + w];
+        s += t[0];
+    }
+}
 
 // Warp-wide search over arr[0..n) (shared memory).  target >= 0: first index whose inclusive prefix sum
 // exceeds target.  target < 0, or rounding pushed target past the total: the last index with positive
@@ -206,51 +284,66 @@ __global__ void __launch_bounds__(kSThreads, 2) lse_sample_kernel(SampleArgs A) 
         const int ng = rv.n_groups();
 
         // ---- pass 1: online (max, sum exp) per thread ------------------------------------------------
-        // Software pipelined: the 16-byte loads of the next U groups are in flight while the current U groups are
-        // reduced, so every thread keeps U loads outstanding all the time.
+        // Thread t owns groups t, t + 512, ...  Its interior groups are streamed in rounds of U with no per-group
+        // checks: the 16-byte loads (+ mask words) of the next round are requested while the current round is reduced,
+        // so every thread keeps 64 bytes of the row in flight.  What is left (fewer than U interior groups, and the
+        // one or two edge groups of an unaligned row) is handled group by group afterwards.
+        const float SC = rv.scale();
         float m = -INFINITY, s = 0.f;
-        constexpr int U = EPV >= 8 ? 2 : 4;  // independent 16-byte groups in flight per thread
-        typename RowView<IN_T, MK>::Raw raw[U];
-        bool inner[U];
+        constexpr int U = (EPV >= 8 || MK == GT_MASK_ADD_F32) ? 2 : 4;
+        const int g_lo = rv.phase ? 1 : 0, g_hi = (rv.phase + rv.V) / EPV;  // interior groups: [g_lo, g_hi)
+        const int g0 = tid < g_lo ? tid + kSThreads : tid;
+        const int cnt = g0 < g_hi ? (g_hi - 1 - g0) / kSThreads + 1 : 0;
+        const int rounds = cnt / U;
+        auto stream = [&](auto vec_tag) {  // vec_tag: the mask lines up with the row's groups (vector mask loads)
+            constexpr bool VEC = decltype(vec_tag)::value;
+            typename RowView<IN_T, MK>::Raw raw[U];
+            typename RowView<IN_T, MK>::Cursor c = rv.cursor(g0);
+            if (rounds > 0) {
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int g = tid + u * kSThreads;
-            inner[u] = g < ng && rv.interior(g);
-            if (inner[u]) raw[u] = rv.issue(g);
-        }
-        for (int gb = tid; gb < ng; gb += U * kSThreads) {
-            float x[U][EPV];
+                for (int u = 0; u < U; ++u) raw[u] = rv.template issue<VEC>(c, u * kSThreads);
+            }
+            for (int r = 0; r < rounds; ++r) {
+                const bool more = r + 1 < rounds;
+                // the (max, sum) update runs over UH groups at a time: all of the round's values at once is the
+                // cheapest, half a round keeps the byte-mask variant inside the register budget of 2 CTAs per SM
+                constexpr int UH = (MK == GT_MASK_BOOL_U8 && U == 4) ? 2 : U;
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int g = gb + u * kSThreads;
-                if (inner[u]) {
-                    rv.finish(g, raw[u], x[u]);
-                } else if (g < ng) {
-                    rv.fetch_edge(g, x[u]);
-                } else {
+                for (int h = 0; h < U; h += UH) {
+                    float y[UH * EPV];
 #pragma unroll
-                    for (int k = 0; k < EPV; ++k) x[u][k] = -INFINITY;
+                    for (int uu = 0; uu < UH; ++uu) {
+                        const int u = h + uu;
+                        float yu[EPV];
+                        rv.template finish<VEC>(c, u * kSThreads, raw[u], yu);
+#pragma unroll
+                        for (int k = 0; k < EPV; ++k) y[uu * EPV + k] = yu[k];
+                        // the register set is free again: request this thread's group of the next round right away
+                        if (more) raw[u] = rv.template issue<VEC>(c, (U + u) * kSThreads);
+                    }
+                    online_update<UH * EPV>(y, SC, m, s);
                 }
-                // the register set is free again: request this thread's group of the next round right away
-                const int gn = g + U * kSThreads;
-                inner[u] = gn < ng && rv.interior(gn);
-                if (inner[u]) raw[u] = rv.issue(gn);
+                rv.advance(c, U * kSThreads);
             }
-            float gm = x[0][0];
-#pragma unroll
-            for (int u = 0; u < U; ++u)
-#pragma unroll
-                for (int k = 0; k < EPV; ++k) gm = fmaxf(gm, x[u][k]);
-            if (gm > m) {  // rare once the running max has settled
-                s *= fast_exp2((m - gm) * kLog2e);  // m = -inf: s is still 0
-                m = gm;
+            for (int i = rounds * U; i < cnt; ++i) {
+                float y[EPV];
+                rv.template finish<VEC>(c, 0, rv.template issue<VEC>(c, 0), y);
+                rv.advance(c, kSThreads);
+                online_update<EPV>(y, SC, m, s);
             }
-            if (m > -INFINITY) {
-                const float ml = m * kLog2e;
-#pragma unroll
-                for (int u = 0; u < U; ++u)
-#pragma unroll
-                    for (int k = 0; k < EPV; ++k) s += fast_exp2(fmaf(x[u][k], kLog2e, -ml));
+        };
+        if (MK == GT_MASK_NONE || MK == GT_MASK_BITS_U32 || rv.mask_vec) stream(std::true_type{});
+        else stream(std::false_type{});
+        {
+            if (g_lo == 1 && tid == 0) {
+                float y[EPV];
+                rv.fetch_edge(0, y);
+                online_update<EPV>(y, SC, m, s);
+            }
+            if (g_hi < ng && g_hi >= g_lo && tid == g_hi % kSThreads) {
+                float y[EPV];
+                rv.fetch_edge(g_hi, y);
+                online_update<EPV>(y, SC, m, s);
             }
         }
         // A NaN element poisons s (fmaxf ignores it, so m stays finite): logZ becomes NaN, tok = -1.
@@ -268,7 +361,7 @@ __global__ void __launch_bounds__(kSThreads, 2) lse_sample_kernel(SampleArgs A) 
         }
         __syncthreads();
         const float M = s_M;
-        s_mass[tid] = (m > -INFINITY) ? (double)s * exp2((double)(m - M) * (double)kLog2e) : 0.0;
+        s_mass[tid] = (m > -INFINITY) ? (double)s * exp2((double)(m - M) * (double)SC) : 0.0;
         __syncthreads();
 
         if (warp == 0) {
@@ -287,7 +380,7 @@ __global__ void __launch_bounds__(kSThreads, 2) lse_sample_kernel(SampleArgs A) 
             if (lane == 0) {
                 s_pick = pick;
                 s_resid = before < 0.0 ? -1.0 : u * tot - before;
-                A.logZ[b] = (M == -INFINITY) ? -INFINITY : (float)((double)M + log(tot));
+                A.logZ[b] = (M == -INFINITY) ? -INFINITY : (float)((double)M * (double)rv.unit() + log(tot));
             }
         }
         __syncthreads();
@@ -305,9 +398,9 @@ __global__ void __launch_bounds__(kSThreads, 2) lse_sample_kernel(SampleArgs A) 
         double local = 0.0;
         if (g < ng) {
             rv.fetch(g, x);
-            const float ml = M * kLog2e;
+            const float ms = -M * SC;
 #pragma unroll
-            for (int k = 0; k < EPV; ++k) { x[k] = fast_exp2(fmaf(x[k], kLog2e, -ml)); local += (double)x[k]; }
+            for (int k = 0; k < EPV; ++k) { x[k] = fast_exp2(fmaf(x[k], SC, ms)); local += (double)x[k]; }
         } else {
 #pragma unroll
             for (int k = 0; k < EPV; ++k) x[k] = 0.f;

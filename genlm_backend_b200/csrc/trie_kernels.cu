@@ -846,38 +846,59 @@ __global__ void __launch_bounds__(kTileThreads, 2) tile_kernel(PlanView P, TileA
 
 // ---- phase 3: nodes whose leaf range crosses tiles, reduced from their per-tile pieces (fp64 for sums) ------------
 // One thread per (spanning node, row); consecutive lanes take consecutive spanning nodes of one row, whose pieces
-// are adjacent in `part`.  Runs after tile_kernel in stream order and overwrites the placeholder it emitted.
+// are adjacent in `part`.  Most spanning nodes have two or three pieces, which a thread loads all at once; the few
+// with many (the root has one per tile) are reduced by the whole warp, 32 pieces per step, so that no thread walks a
+// long chain of dependent loads.  Runs after tile_kernel in stream order and overwrites the placeholder it emitted.
 // blockIdx.z selects the reduction when both were requested.
+constexpr int kSpanInline = 8;  // pieces a thread reduces by itself
+
+template <typename VT, bool SUM> __device__ __forceinline__ VT span_reduce(const VT* __restrict__ pr, int q0, int q1, int lane) {
+    using AT = std::conditional_t<SUM, double, VT>;  // sums across tiles accumulate in fp64; max is exact
+    const AT ident = SUM ? AT(0) : -std::numeric_limits<AT>::infinity();
+    const int cnt = q1 - q0;
+    AT acc = ident;
+    if (cnt <= kSpanInline) {
+        VT v[kSpanInline];
+#pragma unroll
+        for (int i = 0; i < kSpanInline; ++i) v[i] = i < cnt ? pr[q0 + i] : (VT)ident;  // independent loads
+#pragma unroll
+        for (int i = 0; i < kSpanInline; ++i) acc = SUM ? acc + (AT)v[i] : (AT)fmax((VT)acc, v[i]);
+    }
+    // nodes with many pieces, one at a time, by the whole warp (fixed order: results do not depend on the launch)
+    unsigned heavy = __ballot_sync(0xffffffffu, cnt > kSpanInline);
+    while (heavy) {
+        const int src = __ffs(heavy) - 1;
+        heavy &= heavy - 1;
+        const int h0 = __shfl_sync(0xffffffffu, q0, src), h1 = __shfl_sync(0xffffffffu, q1, src);
+        AT a = ident;
+        for (int q = h0 + lane; q < h1; q += 32) a = SUM ? a + (AT)pr[q] : (AT)fmax((VT)a, pr[q]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const AT y = __shfl_xor_sync(0xffffffffu, a, o);
+            a = SUM ? a + y : (AT)fmax((VT)a, (VT)y);
+        }
+        if (lane == src) acc = a;
+    }
+    return cnt > 0 ? (VT)acc : VT(0);  // an empty range (root of an empty vocabulary) has no mass
+}
+
 template <typename VT>
 __global__ void __launch_bounds__(256) span_kernel(PlanView P, TileArgs<VT> A) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
     const bool live = k < P.n_span;
     // plan metadata first: these loads may run ahead of the tile kernel's completion
     const int q0 = live ? __ldg(P.span_pp + k) : 0, q1 = live ? __ldg(P.span_pp + k + 1) : 0;
     const int node = live ? __ldg(P.span_node + k) : 0;
     pdl_wait();  // pieces and placeholders come from tile_kernel
     pdl_trigger();
-    if (!live) return;
     const bool is_sum = (A.ops & GT_OP_SUM) && blockIdx.z == 0;
     const VT* part = is_sum ? A.part_sum : A.part_max;
     VT* out = is_sum ? A.out_sum : A.out_max;
-    for (int b = blockIdx.y; b < A.n_rows; b += gridDim.y) {
+    for (int b = blockIdx.y; b < A.n_rows; b += gridDim.y) {  // whole warps stay together: dead lanes have no pieces
         const VT* pr = part + (size_t)b * P.n_pieces;
-        VT res = VT(0);
-        if (q1 > q0) {
-            if (is_sum) {
-                double acc = 0.0;
-#pragma unroll 4
-                for (int q = q0; q < q1; ++q) acc += (double)pr[q];
-                res = (VT)acc;
-            } else {
-                VT acc = -std::numeric_limits<VT>::infinity();
-#pragma unroll 4
-                for (int q = q0; q < q1; ++q) acc = fmax(acc, pr[q]);
-                res = acc;
-            }
-        }
-        out[(size_t)b * A.ld_out + node] = res;
+        const VT res = is_sum ? span_reduce<VT, true>(pr, q0, q1, lane) : span_reduce<VT, false>(pr, q0, q1, lane);
+        if (live) out[(size_t)b * A.ld_out + node] = res;
     }
 }
 

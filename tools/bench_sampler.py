@@ -20,8 +20,22 @@ sets = [torch.log_softmax(torch.randn(B, V, device="cuda"), dim=-1) for _ in ran
 shared = (torch.rand(V, device="cuda") < 0.5).float().log()
 per_row = (torch.rand(B, V, device="cuda") < 0.5).float().log()
 bool_mask = torch.rand(V, device="cuda") < 0.5
+bool_rows = torch.rand(B, V, device="cuda") < 0.5
+
+
+def pack_bits(keep):
+    """bool [..., V] -> int32 [..., ceil(V/32)] keep-bitmask (bit i of word w = element 32*w + i)"""
+    pad = (-keep.shape[-1]) % 32
+    k = torch.nn.functional.pad(keep, (0, pad)).view(*keep.shape[:-1], -1, 32).to(torch.int64)
+    w = (k << torch.arange(32, device=keep.device, dtype=torch.int64)).sum(-1)
+    return torch.where(w >= 2**31, w - 2**32, w).to(torch.int32)
+
+
+W = (V + 31) // 32
 cases = {"no mask": (None, 4 * V), "shared additive fp32 mask": (shared, 4 * V), "shared bool mask": (bool_mask, 4 * V),
-         "per-row additive fp32 mask": (per_row, 8 * V)}
+         "shared bit mask": (pack_bits(bool_mask), 4 * V),
+         "per-row additive fp32 mask": (per_row, 8 * V), "per-row bool mask": (bool_rows, 5 * V),
+         "per-row bit mask": (pack_bits(bool_rows), 4 * V + 4 * W)}
 for dtype in (torch.float32, torch.bfloat16):
     data = [s.to(dtype) for s in sets]
     for name, (mask, bytes_per_row) in cases.items():

@@ -1,7 +1,7 @@
 """Condenses an Nsight Compute report (.ncu-rep, read here without a GPU) into the text summary kept under profiles/:
 key raw metrics per kernel launch, warp-stall totals, and the hottest SASS instructions by stall samples.
 
-    python tools/ncu_summary.py gpurun_out/prof_tile.ncu-rep > profiles/r01_tile_kernel_ncu.txt
+    python tools/ncu_summary.py gpurun_out/prof_tile.ncu-rep [launch index ...] > profiles/r01_tile_kernel_ncu.txt
 """
 import csv
 import re
@@ -9,6 +9,7 @@ import subprocess
 import sys
 
 rep = sys.argv[1]
+SASS_OF = [int(a) for a in sys.argv[2:]] or [0]  # which launches get the SASS view (default: the first)
 WANT = re.compile(
     r"^(gpu__time_duration\.sum|dram__bytes_read\.sum|dram__bytes_write\.sum|dram__throughput\.avg\.pct_of_peak_sustained_elapsed|"
     r"lts__t_bytes\.sum|lts__throughput\.avg\.pct_of_peak_sustained_elapsed|l1tex__throughput\.avg\.pct_of_peak_sustained_elapsed|"
@@ -43,7 +44,7 @@ for r in rows:
         hdr = r
     elif cur is not None and hdr is not None and len(r) == len(hdr):
         cur["data"].append(r)
-for kinfo in kernels[:1]:
+for kinfo in [kernels[i] for i in SASS_OF if i < len(kernels)]:
     data = kinfo["data"]
     si, ii, sc = hdr.index("# Samples"), hdr.index("Instructions Executed"), hdr.index("Source")
     tot = sum(int(r[si]) for r in data) or 1
