@@ -41,6 +41,8 @@ struct PlanView {
     const int32_t* tile_node_lo; const uint16_t* node_slot;
     const int32_t* piece_ptr; const uint16_t* piece_slot; const int32_t* piece_idx;
     int32_t n_span, n_pieces; const int32_t* span_node; const int32_t* span_pp;
+    const int32_t* leaf_rank;  // [V] DFS rank of each item's leaf (inverse of Layout::perm)
+    const int32_t* node_lo; const int32_t* node_hi;  // [N] DFS leaf range of every node
     int32_t debug_stop;  // profiling aid (GT_DEBUG_STOP): 0 = normal; 3 = tile_kernel skips the emit stores; 9 = emit only
     long long* trace;    // profiling aid (GT_TRACE=1): per (CTA, item) SM-clock stamps of the pipeline events, else null
 };
@@ -922,6 +924,9 @@ static DevicePlan* upload_plan(const Layout& L, const Plan& P, int device) {
     const size_t o_tile_node_lo = ADDV(P.tile_node_lo), o_node_slot = ADDV(P.node_slot);
     const size_t o_piece_ptr = ADDV(P.piece_ptr), o_piece_slot = ADDV(P.piece_slot), o_piece_idx = ADDV(P.piece_idx);
     const size_t o_span_node = ADDV(P.span_node), o_span_pp = ADDV(P.span_pp);
+    std::vector<int32_t> leaf_rank((size_t)L.V);
+    for (int64_t r = 0; r < L.V; ++r) leaf_rank[(size_t)L.perm[(size_t)r]] = (int32_t)r;
+    const size_t o_leaf_rank = ADDV(leaf_rank), o_node_lo = ADDV(L.lo), o_node_hi = ADDV(L.hi);
 #undef ADDV
     total += 256;
 
@@ -970,6 +975,8 @@ static DevicePlan* upload_plan(const Layout& L, const Plan& P, int device) {
     v.piece_idx = (const int32_t*)(base + o_piece_idx);
     v.n_span = (int32_t)P.span_node.size(); v.n_pieces = P.n_pieces;
     v.span_node = (const int32_t*)(base + o_span_node); v.span_pp = (const int32_t*)(base + o_span_pp);
+    v.leaf_rank = (const int32_t*)(base + o_leaf_rank);
+    v.node_lo = (const int32_t*)(base + o_node_lo); v.node_hi = (const int32_t*)(base + o_node_hi);
     { const char* e = getenv("GT_DEBUG_STOP"); v.debug_stop = e && *e ? atoi(e) : 0; }
     v.trace = nullptr;
     if (const char* e = getenv("GT_TRACE")) {
@@ -1178,6 +1185,61 @@ static int reduce_typed(const PlanView& v, const void* ws, int in_type, int64_t 
     return GT_OK;
 }
 
+// ---- read-outs that keep the [B, N] slab on the GPU ---------------------------------------
+//
+// gather: the caller of the mass path reads a handful of nodes per row (the children of the node a particle stands
+// on), so only out[b, k] = mass[b, ids[b, k]] has to cross PCIe.  One thread per (row, k); rows on blockIdx.y.
+template <typename VT>
+__global__ void __launch_bounds__(256) gather_nodes_kernel(const VT* __restrict__ mass, int64_t ld_mass, int n_rows, int64_t N,
+                                                           const int32_t* __restrict__ ids, int n_ids, int64_t ids_ld,
+                                                           const int32_t* __restrict__ norm, int log_out,
+                                                           VT* __restrict__ out, int64_t ld_out) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_ids) return;
+    for (int b = blockIdx.y; b < n_rows; b += gridDim.y) {
+        const VT* row = mass + (size_t)b * ld_mass;
+        const int id = __ldg(ids + (size_t)b * ids_ld + k);
+        VT v = (id >= 0 && id < N) ? row[id] : VT(0);
+        if (norm) {
+            const int z = __ldg(norm + b);
+            const VT d = (z >= 0 && z < N) ? row[z] : VT(0);
+            v = log_out ? (VT)(log((double)v) - log((double)d)) : v / d;
+        } else if (log_out) {
+            v = (VT)log((double)v);
+        }
+        out[(size_t)b * ld_out + k] = v;
+    }
+}
+
+// token mask: bit i of row b is set iff item i's leaf lies in the subtree of nodes[b], i.e. iff the reference's
+// reachability matrix has M[i, nodes[b]] = 1 (parallel.py:33-64).  With leaves in DFS order that is one range test
+// on the leaf's DFS rank, so a warp produces one mask word per ballot; kMaskRows rows share every rank load.
+constexpr int kMaskThreads = 512, kMaskRows = 16;
+__global__ void __launch_bounds__(kMaskThreads) subtree_mask_kernel(PlanView P, const int32_t* __restrict__ nodes, int n_rows,
+                                                                    uint32_t* __restrict__ bits, int64_t ld_bits) {
+    __shared__ int s_lo[kMaskRows];
+    __shared__ unsigned s_len[kMaskRows];
+    const int b0 = blockIdx.y * kMaskRows;
+    if (threadIdx.x < kMaskRows) {
+        const int b = b0 + threadIdx.x;
+        int lo = 0; unsigned len = 0;
+        if (b < n_rows) {
+            const int n = __ldg(nodes + b);
+            if (n >= 0 && n < P.N) { lo = __ldg(P.node_lo + n); len = (unsigned)(__ldg(P.node_hi + n) - lo); }
+        }
+        s_lo[threadIdx.x] = lo; s_len[threadIdx.x] = len;
+    }
+    const int64_t i = (int64_t)blockIdx.x * kMaskThreads + threadIdx.x;
+    const int r = i < P.V ? __ldg(P.leaf_rank + i) : -1;  // -1: fails every range test
+    __syncthreads();
+    const int64_t w = i >> 5;
+    const int rows = min(kMaskRows, n_rows - b0);
+    for (int q = 0; q < rows; ++q) {
+        const unsigned word = __ballot_sync(0xffffffffu, r >= 0 && (unsigned)(r - s_lo[q]) < s_len[q]);
+        if ((threadIdx.x & 31) == 0 && w < ld_bits) bits[(size_t)(b0 + q) * ld_bits + w] = word;
+    }
+}
+
 }  // namespace gt
 
 extern "C" {
@@ -1273,6 +1335,48 @@ int gt_weight_reduce(const gt_trie* t, const void* ws, int in_type, int64_t n_ro
 #undef GT_REDUCE
     gt::set_error("gt_weight_reduce: output type must be GT_F32 or GT_F64");
     return GT_ERR_ARG;
+}
+
+int gt_gather_nodes(const void* mass, int type, int64_t n_rows, int64_t n_nodes, int64_t ld_mass, const int32_t* node_ids,
+                    int64_t n_ids, int64_t ids_ld, const int32_t* norm_node, unsigned flags, void* out, int64_t ld_out,
+                    gt_stream stream) {
+    if (n_rows < 0 || n_ids < 0 || n_nodes < 0 || ld_mass < n_nodes || ld_out < n_ids || ids_ld < 0 || (flags & ~(unsigned)GT_GATHER_LOG)) {
+        gt::set_error("gt_gather_nodes: bad size / stride / flags"); return GT_ERR_ARG;
+    }
+    if (n_rows == 0 || n_ids == 0) return GT_OK;
+    if (!mass || !node_ids || !out) { gt::set_error("gt_gather_nodes: null data pointer"); return GT_ERR_ARG; }
+    if (n_rows > INT32_MAX || n_ids > INT32_MAX) { gt::set_error("gt_gather_nodes: too many rows / ids"); return GT_ERR_LIMIT; }
+    if (type != GT_F32 && type != GT_F64) { gt::set_error("gt_gather_nodes: type must be GT_F32 or GT_F64"); return GT_ERR_ARG; }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    dim3 grid((unsigned)((n_ids + 255) / 256), (unsigned)std::min<int64_t>(n_rows, 32768));
+    const int lg = (flags & GT_GATHER_LOG) ? 1 : 0;
+    if (type == GT_F32)
+        gt::gather_nodes_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(mass), ld_mass, (int)n_rows, n_nodes, node_ids,
+                                                            (int)n_ids, ids_ld, norm_node, lg, static_cast<float*>(out), ld_out);
+    else
+        gt::gather_nodes_kernel<double><<<grid, 256, 0, st>>>(static_cast<const double*>(mass), ld_mass, (int)n_rows, n_nodes, node_ids,
+                                                             (int)n_ids, ids_ld, norm_node, lg, static_cast<double*>(out), ld_out);
+    GT_CUDA(cudaGetLastError());
+    return GT_OK;
+}
+
+int gt_subtree_token_mask(const gt_trie* t, const int32_t* nodes, int64_t n_rows, uint32_t* mask_bits, int64_t mask_ld,
+                          gt_stream stream) {
+    if (!t) { gt::set_error("gt_subtree_token_mask: null trie"); return GT_ERR_ARG; }
+    const int64_t words = (t->layout.V + 31) / 32;
+    if (n_rows < 0 || mask_ld < words) { gt::set_error("gt_subtree_token_mask: bad n_rows / mask_ld (need >= %lld words)", (long long)words); return GT_ERR_ARG; }
+    if (n_rows == 0 || words == 0) return GT_OK;
+    if (!nodes || !mask_bits) { gt::set_error("gt_subtree_token_mask: null data pointer"); return GT_ERR_ARG; }
+    if (n_rows > (int64_t)65535 * gt::kMaskRows) { gt::set_error("gt_subtree_token_mask: too many rows"); return GT_ERR_LIMIT; }
+    int device = -1;
+    GT_CUDA(cudaGetDevice(&device));
+    auto it = t->dev.find(device);
+    if (it == t->dev.end()) { gt::set_error("trie metadata is not resident on device %d (call gt_upload)", device); return GT_ERR_STATE; }
+    // the grid covers whole mask words: ceil(V/32) of them, kMaskThreads/32 per CTA
+    dim3 grid((unsigned)((words * 32 + gt::kMaskThreads - 1) / gt::kMaskThreads), (unsigned)((n_rows + gt::kMaskRows - 1) / gt::kMaskRows));
+    gt::subtree_mask_kernel<<<grid, gt::kMaskThreads, 0, static_cast<cudaStream_t>(stream)>>>(it->second->view, nodes, (int)n_rows, mask_bits, mask_ld);
+    GT_CUDA(cudaGetLastError());
+    return GT_OK;
 }
 
 }  // extern "C"

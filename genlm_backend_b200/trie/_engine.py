@@ -175,3 +175,64 @@ class TrieEngine:
                 "gt_weight_reduce",
             )
         return out_sum, out_max
+
+    # ---- read-outs that keep the [B, N] slab on the GPU --------------------------------------------------------
+    def gather_nodes(self, mass, node_ids, normalizer=None, log=False):
+        """``out[b, k] = mass[b, node_ids[b, k]]`` (``node_ids`` 1-D: shared by all rows), optionally divided by
+        ``mass[b, normalizer[b]]`` and / or returned as logs.  Everything stays on ``mass``'s device."""
+        require_cuda()
+        if not (isinstance(mass, torch.Tensor) and mass.is_cuda and mass.dim() == 2 and mass.dtype in _OUT_TYPES):
+            raise ValueError("mass must be a 2-D float32 / float64 CUDA tensor")
+        if mass.shape[1] != self.N:
+            raise AssertionError([mass.shape[1], self.N])
+        if mass.shape[1] > 1 and mass.stride(1) != 1:
+            mass = mass.contiguous()
+        B, dev = mass.shape[0], mass.device
+        ids = torch.as_tensor(node_ids).to(device=dev, dtype=torch.int32)
+        if ids.dim() == 1:
+            ids, ids_ld = ids.contiguous(), 0
+        elif ids.dim() == 2 and ids.shape[0] == B:
+            ids = ids.contiguous()
+            ids_ld = ids.shape[1]
+        else:
+            raise ValueError("node_ids must be [K] or [B, K]")
+        K = ids.shape[-1]
+        norm = None
+        if normalizer is not None:
+            norm = torch.as_tensor(normalizer).to(device=dev, dtype=torch.int32)
+            norm = norm.expand(B).contiguous() if norm.dim() == 0 else norm.contiguous()
+            if norm.shape != (B,):
+                raise ValueError("normalizer must be a node id or one node id per row")
+        out = torch.empty((B, K), dtype=mass.dtype, device=dev)
+        if B and K:
+            with torch.cuda.device(dev.index):
+                check(
+                    lib.gt_gather_nodes(
+                        mass.data_ptr(), _OUT_TYPES[mass.dtype], B, self.N, mass.stride(0) if B > 1 else self.N,
+                        ids.data_ptr(), K, ids_ld, norm.data_ptr() if norm is not None else None,
+                        _lib.GT_GATHER_LOG if log else 0, out.data_ptr(), K, torch.cuda.current_stream(dev.index).cuda_stream,
+                    ),
+                    "gt_gather_nodes",
+                )
+        return out
+
+    def subtree_token_mask(self, nodes, device=None):
+        """Keep-bitmask ``int32[B, ceil(V/32)]`` of the tokens under each node (bit ``i % 32`` of word ``i // 32``):
+        the layout ``smc.masked_logsumexp_sample`` takes as a bit mask."""
+        require_cuda()
+        nodes = torch.as_tensor(nodes)
+        if device is None:
+            device = nodes.device if nodes.is_cuda else torch.device("cuda", torch.cuda.current_device())
+        device = torch.device(device)
+        nodes = nodes.to(device=device, dtype=torch.int32).reshape(-1).contiguous()
+        B, W = nodes.shape[0], (self.V + 31) // 32
+        self.ensure_device(device.index)
+        bits = torch.empty((B, W), dtype=torch.int32, device=device)
+        if B and W:
+            with torch.cuda.device(device.index):
+                check(
+                    lib.gt_subtree_token_mask(self._handle, nodes.data_ptr(), B, bits.data_ptr(), W,
+                                              torch.cuda.current_stream(device.index).cuda_stream),
+                    "gt_subtree_token_mask",
+                )
+        return bits

@@ -111,6 +111,30 @@ class ParallelTokenCharacterTrie(TokenCharacterTrie):
     def batch_weight_max_tensor(self, ws, log_input=False, out=None):
         return self.batch_weight_tensor(ws, ("max",), log_input=log_input, out_max=out)[1]
 
+    def gather_nodes(self, mass, node_ids, normalizer=None, log=False):
+        """Read a few nodes per row out of a device-resident ``[B, N]`` mass slab (a ``*_tensor`` result):
+        ``out[b, k] = mass[b, node_ids[b, k]]``; with ``normalizer`` (a node id per row) the value is divided by
+        that node's mass, with ``log=True`` logs are returned.  The result is a ``[B, K]`` device tensor, so only
+        ``B * K`` values ever cross PCIe instead of the whole slab (``parallel.py:103,145``)."""
+        return self._engine.gather_nodes(mass, node_ids, normalizer=normalizer, log=log)
+
+    def batch_weight_sum_at(self, ws, node_ids, normalizer=None, log=False, log_input=False):
+        """``batch_weight_sum(ws)[b, node_ids[b, k]]`` as a ``[B, K]`` float32 numpy array, without moving the
+        ``[B, N]`` slab to the host."""
+        sums = self.batch_weight_sum_tensor(ws, log_input=log_input)
+        return self.gather_nodes(sums, node_ids, normalizer=normalizer, log=log).cpu().numpy()
+
+    def batch_weight_max_at(self, ws, node_ids, log=False, log_input=False):
+        """``batch_weight_max(ws)[b, node_ids[b, k]]`` as a ``[B, K]`` float32 numpy array."""
+        maxes = self.batch_weight_max_tensor(ws, log_input=log_input)
+        return self.gather_nodes(maxes, node_ids, log=log).cpu().numpy()
+
+    def subtree_token_mask(self, nodes, device=None):
+        """Keep-bitmask of the tokens in the subtree of each node in ``nodes`` -- the tokens whose spelling extends
+        that node's prefix, i.e. column ``nodes[b]`` of the reachability matrix ``M`` (``parallel.py:33-64``) -- as
+        an ``int32[B, ceil(V/32)]`` device tensor in the bit-mask layout of ``smc.masked_logsumexp_sample``."""
+        return self._engine.subtree_token_mask(nodes, device=device)
+
     # ---- reference API: numpy results on the host --------------------------------------------------------------
     def _pipe_streams(self, index):
         if index not in self._streams:

@@ -16,6 +16,8 @@
  *                               genlm/backend/trie/parallel.py:120-145 (batch_weight_max: scatter_reduce amax)
  *   gt_lse_sample               README.md:82-91 / genlm/backend/llm/base.py:131-146
  *                               (masked logsumexp + multinomial of the SMC particle step)
+ *   gt_gather_nodes             genlm/backend/trie/parallel.py:103,145 (the .cpu().numpy() of the whole slab)
+ *   gt_subtree_token_mask       genlm/backend/trie/parallel.py:33-64 (a column of the reachability matrix)
  *
  * Conventions
  *   - every function returns 0 on success, non-zero on failure; gt_last_error() returns a
@@ -164,6 +166,26 @@ int gt_weight_reduce(const gt_trie* t, const void* ws, int in_type, int64_t n_ro
 int gt_lse_sample(const void* logp, int in_type, int64_t n_rows, int64_t n_vocab, int64_t ld_logp,
                   const void* mask, int mask_kind, int64_t mask_ld, float temperature,
                   uint64_t seed, uint64_t offset, float* logZ_out, int32_t* tok_out, gt_stream stream);
+
+/* ---- read-outs that keep the [B, N] slab on the GPU ------------------------------------------ */
+
+#define GT_GATHER_LOG 1u /* return log-masses */
+
+/* out[b, k] = mass[b, node_ids[b * ids_ld + k]]  (ids_ld = 0: one id list shared by all rows; id < 0 or >= n_nodes
+ * reads as mass 0).  With norm_node != NULL the value is divided by mass[b, norm_node[b]] (with GT_GATHER_LOG:
+ * log mass - log normaliser) -- the conditional next-symbol distribution a caller of weight_sum forms from
+ * mass[children(node)] / mass[node].  Replaces the D2H copy of the whole slab in parallel.py:103,145 when only a few
+ * nodes per row are read.  mass / out: device, type GT_F32 or GT_F64; node_ids / norm_node: device int32. */
+int gt_gather_nodes(const void* mass, int type, int64_t n_rows, int64_t n_nodes, int64_t ld_mass,
+                    const int32_t* node_ids, int64_t n_ids, int64_t ids_ld, const int32_t* norm_node,
+                    unsigned flags, void* out, int64_t ld_out, gt_stream stream);
+
+/* mask_bits[b, i/32] bit i%32 = 1 iff item i's leaf lies in the subtree of node nodes[b] -- column nodes[b] of the
+ * reference's reachability matrix M (parallel.py:33-64) as a keep-bitmask in gt_lse_sample's GT_MASK_BITS_U32 layout
+ * (tokens whose spelling extends the prefix of that node).  nodes[b] < 0 or >= N gives an all-zero row.
+ * nodes / mask_bits: device; mask_ld >= ceil(V/32) words per row, every word of the first ceil(V/32) is written. */
+int gt_subtree_token_mask(const gt_trie* t, const int32_t* nodes, int64_t n_rows, uint32_t* mask_bits,
+                          int64_t mask_ld, gt_stream stream);
 
 #ifdef __cplusplus
 }

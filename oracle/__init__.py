@@ -9,7 +9,9 @@ CPU restatement of the reference's algorithm for the trie-mass / SMC-sampling ho
   float64, single thread per row;
 * ``parallel_weight_sum`` / ``parallel_weight_max`` -- the torch formulas of ``parallel.py:92-145`` in numpy
   float32 (secondary check only: the reference's own fp32 SpMM differs from its fp64 path by up to 1e-4 rel);
-* ``masked_logsumexp`` / ``masked_probs`` -- float64 restatement of ``README.md:82-87``.
+* ``masked_logsumexp`` / ``masked_probs`` -- float64 restatement of ``README.md:82-87``;
+* ``OracleTrie.subtree_token_mask`` / ``gather_nodes`` -- the read-outs (a column of the reachability matrix,
+  ``parallel.py:33-64``; indexing the numpy result of ``parallel.py:103,145``).
 
 Parity pin: ``tests/test_oracle.py`` checks every function here against outputs of the reference itself
 (``tests/golden/*.npz``, produced by ``tests/golden/make_golden.py`` importing ``/root/reference`` in the dev
@@ -126,6 +128,15 @@ class OracleTrie:
                 cols.append(cur)
         return np.array(rows, dtype=np.int64), np.array(cols, dtype=np.int64)
 
+    def subtree_token_mask(self, nodes):
+        """Column ``nodes[b]`` of the reachability matrix ``M[V, N]`` (``parallel.py:33-64``: ``M[i, n] = 1`` when
+        node ``n`` is item ``i``'s leaf or one of its ancestors) as a bool array ``[B, V]``."""
+        rows, cols = self.reachability()
+        out = np.zeros((len(nodes), self.n_items), dtype=bool)
+        for b, n in enumerate(nodes):
+            out[b, rows[cols == int(n)]] = True
+        return out
+
     # ---- base.py:346-393 through the C restatement -----------------------------------------------------
     def _batch(self, ws, op, threads=1):
         ws = np.asarray(ws)
@@ -205,3 +216,28 @@ def masked_probs(logps, mask=None, temperature=1.0):
         x = x + np.asarray(mask, dtype=np.float64)
     lz = masked_logsumexp(logps, mask, temperature)
     return np.exp(x - lz[..., None])
+
+
+# ---- read-outs of a mass slab (what a caller of parallel.py:103,145 does on the host with the numpy result) ----------
+def gather_nodes(mass, node_ids, normalizer=None, log=False):
+    """``mass[b, node_ids[b, k]]`` in float64 (ids outside ``[0, N)`` read as 0), optionally divided by
+    ``mass[b, normalizer[b]]``, optionally as logs."""
+    mass = np.asarray(mass, dtype=np.float64)
+    B, N = mass.shape
+    ids = np.asarray(node_ids, dtype=np.int64)
+    if ids.ndim == 1:
+        ids = np.broadcast_to(ids, (B, len(ids)))
+    ok = (ids >= 0) & (ids < N)
+    out = np.where(ok, np.take_along_axis(mass, np.where(ok, ids, 0), axis=1), 0.0)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        if normalizer is not None:
+            z = mass[np.arange(B), np.broadcast_to(np.asarray(normalizer, dtype=np.int64), (B,))][:, None]
+            return np.log(out) - np.log(z) if log else out / z
+        return np.log(out) if log else out
+
+
+def unpack_bits(bits, n):
+    """int32 / uint32 keep-bitmask ``[..., ceil(n/32)]`` -> bool ``[..., n]`` (bit ``i % 32`` of word ``i // 32``)."""
+    w = np.asarray(bits).astype(np.uint32)
+    b = (w[..., :, None] >> np.arange(32, dtype=np.uint32)) & 1
+    return b.reshape(*w.shape[:-1], -1)[..., :n].astype(bool)
