@@ -44,6 +44,17 @@ inline int32_t swizzle_slot(int32_t s, int32_t slot_bytes) {
     return (c2 << cs) | (s & ((1 << cs) - 1));
 }
 
+// Aligned blocks of the per-tile pyramid stop at 2^kPyramidTop leaves: a warp builds levels 1..kPyramidTop of its
+// 2^kPyramidTop leaves (2^(kPyramidTop-5) per lane, then five shuffle levels), so the pyramid has no cross-warp step.
+// 8: 256 leaves per warp.  7 (128 leaves per warp, all eight compute warps of a 1024-leaf tile busy) was measured
+// slower on B200 (tile kernel 50.2 vs 48.6 us at 64 rows): the phase is bound by shared-memory bandwidth, not by the
+// number of warps that work, and the 256-leaf blocks come back as extra two-term ranges.
+#ifndef GT_PYR_TOP
+#define GT_PYR_TOP 8
+#endif
+constexpr int kPyramidTop = GT_PYR_TOP;
+static_assert(kPyramidTop == 7 || kPyramidTop == 8, "pyramid top level must be 7 or 8");
+
 struct Plan {
     int32_t T = 0, Q = 0, NT = 0, NS = 0;
     int32_t R = 0;           // rows per CTA of the fp32 pipeline (the fp64 pipeline uses R/2: same slot size)

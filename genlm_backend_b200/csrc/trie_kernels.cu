@@ -358,44 +358,83 @@ template <typename VT, int R> struct RowVec {
     }
 };
 
-// ---- phase 1, bulk-copy variant: persistent CTAs, rows fetched by the copy engine one item ahead -------------------
-// Used when every row segment is 16-byte aligned (row stride and row length multiples of 16 bytes).  An item is
-// (segment s, group of RP rows); items are numbered segment-major and every CTA takes one contiguous run, so the
-// segment's records stay in shared memory across consecutive items.  Rows land in shared memory in their input type
-// (two stages); conversion / exp happens in the gather.
-template <typename VT, typename IN_T, int RP, int NST>
+// Streaming stores of one slot's R row values to R row pointers at a compile-time byte offset, all under one
+// predicate: address = register + immediate, so a store is one instruction and no pointer is recomputed per store.
+template <int OFF, typename VT, int R> struct EmitStore {
+    __device__ __forceinline__ static void run(VT* const (&p)[R], const RowVec<VT, R>& x, bool ok) {
+        if (ok) {
+#pragma unroll
+            for (int r = 0; r < R; ++r) __stcs(reinterpret_cast<VT*>(reinterpret_cast<unsigned char*>(p[r]) + OFF), x.v[r]);
+        }
+    }
+};
+template <int OFF> struct EmitStore<OFF, float, 4> {
+    __device__ __forceinline__ static void run(float* const (&p)[4], const RowVec<float, 4>& x, bool ok) {
+        asm volatile(
+            "{\n.reg .pred q;\nsetp.ne.u32 q, %8, 0;\n"
+            "@q st.global.cs.f32 [%0+%9], %4;\n@q st.global.cs.f32 [%1+%9], %5;\n"
+            "@q st.global.cs.f32 [%2+%9], %6;\n@q st.global.cs.f32 [%3+%9], %7;\n}\n" ::"l"(p[0]), "l"(p[1]), "l"(p[2]), "l"(p[3]),
+            "f"(x.v[0]), "f"(x.v[1]), "f"(x.v[2]), "f"(x.v[3]), "r"((unsigned)ok), "n"(OFF)
+            : "memory");
+    }
+};
+template <int OFF> struct EmitStore<OFF, double, 2> {
+    __device__ __forceinline__ static void run(double* const (&p)[2], const RowVec<double, 2>& x, bool ok) {
+        asm volatile(
+            "{\n.reg .pred q;\nsetp.ne.u32 q, %4, 0;\n"
+            "@q st.global.cs.f64 [%0+%5], %2;\n@q st.global.cs.f64 [%1+%5], %3;\n}\n" ::"l"(p[0]), "l"(p[1]), "d"(x.v[0]), "d"(x.v[1]),
+            "r"((unsigned)ok), "n"(OFF)
+            : "memory");
+    }
+};
+
+// ---- phase 1, bulk-copy variant: persistent CTAs, rows fetched by the copy engine one group ahead -----------------
+// Used when every row segment is 16-byte aligned (row stride and row length multiples of 16 bytes).  The work is the
+// NS x n_rows (segment, row) pairs, numbered segment-major; every CTA takes one contiguous, equally long run of them
+// -- balance is to the row, not to the row group -- and walks it in groups of up to RP rows of one segment, so the
+// segment's records stay in shared memory across consecutive groups and each record read serves RP rows.  Rows land
+// in shared memory in their input type (NST stages); conversion / exp happens in the gather.
+constexpr int kPermPad = 16;  // bytes after every staged row; they hold zeros, which is what padding records read
+template <typename VT, typename IN_T, int RP, int NST, bool LOG>
 __global__ void __launch_bounds__(kThreads, 2) permute_bulk_kernel(PlanView P, const IN_T* __restrict__ ws, int64_t ld_ws,
-                                                                   VT* __restrict__ z, int n_rows, int log_input) {
+                                                                   VT* __restrict__ z, int n_rows) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int Q = P.Q;
-    IN_T* stage = reinterpret_cast<IN_T*>(smem_raw);                                         // [NST][RP][Q]
-    int4* s_rec = reinterpret_cast<int4*>(smem_raw + (size_t)NST * RP * Q * sizeof(IN_T));   // [max_seg_recs]
+    constexpr int kPadElems = kPermPad / (int)sizeof(IN_T);
+    const int pitch = Q + kPadElems;                                                             // elements per staged row
+    IN_T* stage = reinterpret_cast<IN_T*>(smem_raw);                                             // [NST][RP][pitch]
+    int4* s_rec = reinterpret_cast<int4*>(smem_raw + (size_t)NST * RP * pitch * sizeof(IN_T));   // [max_seg_recs]
     uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(s_rec) + (size_t)P.max_seg_recs * 16);
     uint64_t* full = bars;          // [NST] rows of a stage have landed
     uint64_t* rec_bar = bars + NST; // records of the current segment have landed
 
     const int tid = threadIdx.x;
-    const int RGp = (n_rows + RP - 1) / RP;
-    const int n_items = P.NS * RGp;
-    const int i0 = (int)((int64_t)blockIdx.x * n_items / gridDim.x);
-    const int i1 = (int)((int64_t)(blockIdx.x + 1) * n_items / gridDim.x);
-    if (i0 >= i1) return;
-    const bool lg = log_input != 0;
+    const int64_t n_units = (int64_t)P.NS * n_rows;
+    const int64_t u0 = (int64_t)blockIdx.x * n_units / gridDim.x, u1 = (int64_t)(blockIdx.x + 1) * n_units / gridDim.x;
+    if (u0 >= u1) return;
+    const int dbg = P.debug_stop;  // profiling aid: 21 = rows are fetched but not gathered / stored, 22 = gather / store only
 
-    auto seg_len = [&](int s) { return (int)min((int64_t)Q, P.V - (int64_t)s * Q); };
-    auto fetch_rows = [&](int s, int rg, int st) {  // thread 0
-        const int nrows = min(RP, n_rows - rg * RP);
-        const unsigned bytes = (unsigned)seg_len(s) * (unsigned)sizeof(IN_T);
-        mbar_expect_tx(full + st, (unsigned)nrows * bytes);
-        for (int r = 0; r < nrows; ++r)
-            bulk_g2s(stage + ((size_t)st * RP + r) * Q, ws + (size_t)(rg * RP + r) * ld_ws + (size_t)s * Q, bytes, full + st);
+    // the group that starts at unit u: rows [row, row + n) of segment s
+    auto group_at = [&](int64_t u, int& gs, int& grow, int& gn) {
+        gs = (int)(u / n_rows);
+        grow = (int)(u - (int64_t)gs * n_rows);
+        gn = (int)min((int64_t)min(RP, n_rows - grow), u1 - u);
+    };
+    auto seg_len = [&](int sg) { return (int)min((int64_t)Q, P.V - (int64_t)sg * Q); };
+    auto fetch_rows = [&](int sg, int row, int n, int st) {  // thread 0
+        const unsigned bytes = (unsigned)seg_len(sg) * (unsigned)sizeof(IN_T);
+        if (dbg == 22) { mbar_expect_tx(full + st, 0); return; }
+        mbar_expect_tx(full + st, (unsigned)n * bytes);
+        for (int r = 0; r < n; ++r)
+            bulk_g2s(stage + ((size_t)st * RP + r) * pitch, ws + (size_t)(row + r) * ld_ws + (size_t)sg * Q, bytes, full + st);
     };
     auto fetch_recs = [&](int c0, int c1) {  // thread 0
         mbar_expect_tx(rec_bar, (unsigned)(c1 - c0) * 16u);
         if (c1 > c0) bulk_g2s(s_rec, P.p1_rec + c0, (unsigned)(c1 - c0) * 16u, rec_bar);
     };
 
-    int s = i0 / RGp, rg = i0 - s * RGp;
+    int s, row, n;
+    group_at(u0, s, row, n);
     int c0 = __ldg(P.p1_chunk_ptr + s), c1 = __ldg(P.p1_chunk_ptr + s + 1), c2 = __ldg(P.p1_chunk_ptr + min(s + 2, P.NS));
     if (tid == 0) {
         for (int i = 0; i < NST; ++i) mbar_init(full + i, 1);
@@ -403,13 +442,21 @@ __global__ void __launch_bounds__(kThreads, 2) permute_bulk_kernel(PlanView P, c
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         fetch_recs(c0, c1);  // plan metadata: may run ahead of the previous kernel's completion
     }
+    // Padding records carry position 0xFFFF, clamped to Q below: element Q of every staged row is a zero that no
+    // row fetch overwrites (a short last segment leaves stale row data below Q, which no record refers to).
+    if (tid < NST * RP * kPadElems) stage[(size_t)(tid / kPadElems) * pitch + Q + tid % kPadElems] = IN_T(0);
     pdl_wait();  // the previous call's tile kernel may still be reading z; ws may come from a kernel of the caller
-    // item position -> (segment, row group), for the thread that issues the fetches NST-1 items ahead
-    int fs = s, frg = rg, fitem = i0;
+    // the thread that issues the fetches runs NST-1 groups ahead
+    int64_t fu = u0;
+    int fk = 0;
     auto fetch_advance = [&]() {
-        if (fitem < i1) fetch_rows(fs, frg, (fitem - i0) % NST);
-        ++fitem;
-        if (++frg == RGp) { frg = 0; ++fs; }
+        if (fu < u1) {
+            int fs, frow, fn;
+            group_at(fu, fs, frow, fn);
+            fetch_rows(fs, frow, fn, fk % NST);
+            fu += fn;
+        }
+        ++fk;
     };
     if (tid == 0)
         for (int i = 0; i < NST - 1; ++i) fetch_advance();
@@ -417,41 +464,62 @@ __global__ void __launch_bounds__(kThreads, 2) permute_bulk_kernel(PlanView P, c
 
     bool new_seg = true;
     unsigned par_rec = 0;
-    for (int item = i0; item < i1; ++item) {
-        const int k = item - i0, st = k % NST;
-        int sn = s, rgn = rg + 1;
-        if (rgn == RGp) { rgn = 0; ++sn; }
-        const bool has_next = item + 1 < i1;
-        if (tid == 0) fetch_advance();  // item k + NST - 1: its stage was released by the barrier at the end of item k - 1
+    int k = 0;
+    for (int64_t u = u0; u < u1; ++k) {
+        const int st = k % NST;
+        const int64_t un = u + n;
+        const bool has_next = un < u1;
+        int sn = s, rown = row, nn = n;
+        if (has_next) group_at(un, sn, rown, nn);
+        if (tid == 0) fetch_advance();  // group k + NST - 1: its stage was released by the barrier at the end of group k - 1
         if (new_seg) { mbar_wait(rec_bar, par_rec); par_rec ^= 1u; }
         mbar_wait(full + st, (unsigned)(k / NST) & 1u);
 
-        const int nrows = min(RP, n_rows - rg * RP);
-        const IN_T* sr0 = stage + (size_t)st * RP * Q;
-        const int nrec = c1 - c0;
+        const IN_T* sr0 = stage + (size_t)st * RP * pitch;
+        const int nrec = dbg == 21 ? 0 : c1 - c0;
+#ifndef GT_PB_FAT
+        VT* zr[RP];
+#pragma unroll
+        for (int r = 0; r < RP; ++r) zr[r] = z + (size_t)(row + r) * P.Zrow;
+        const unsigned uq = (unsigned)Q;
+        for (int i = tid; i < nrec; i += kThreads) {
+            const int4 rec = s_rec[i];
+            const unsigned p0 = min((unsigned)rec.y & 0xFFFFu, uq), p1 = min((unsigned)rec.y >> 16, uq);
+            const unsigned p2 = min((unsigned)rec.z & 0xFFFFu, uq), p3 = min((unsigned)rec.z >> 16, uq);
+#pragma unroll
+            for (int r = 0; r < RP; ++r) {
+                if (r < n) {
+                    const IN_T* sr = sr0 + (size_t)r * pitch;
+                    store4<VT>(zr[r] + rec.x, convert_in<VT, IN_T>(sr[p0], LOG), convert_in<VT, IN_T>(sr[p1], LOG),
+                               convert_in<VT, IN_T>(sr[p2], LOG), convert_in<VT, IN_T>(sr[p3], LOG));
+                }
+            }
+        }
+#else
         for (int i = tid; i < nrec; i += kThreads) {
             const int4 rec = s_rec[i];
             const unsigned s0 = (unsigned)rec.y & 0xFFFFu, s1 = (unsigned)rec.y >> 16;
             const unsigned s2 = (unsigned)rec.z & 0xFFFFu, s3 = (unsigned)rec.z >> 16;
 #pragma unroll
             for (int r = 0; r < RP; ++r) {
-                if (r < nrows) {
-                    const IN_T* sr = sr0 + (size_t)r * Q;
-                    const VT a = s0 != 0xFFFFu ? convert_in<VT, IN_T>(sr[s0], lg) : VT(0);
-                    const VT b = s1 != 0xFFFFu ? convert_in<VT, IN_T>(sr[s1], lg) : VT(0);
-                    const VT c = s2 != 0xFFFFu ? convert_in<VT, IN_T>(sr[s2], lg) : VT(0);
-                    const VT d = s3 != 0xFFFFu ? convert_in<VT, IN_T>(sr[s3], lg) : VT(0);
-                    store4<VT>(z + (size_t)(rg * RP + r) * P.Zrow + rec.x, a, b, c, d);
+                if (r < n) {
+                    const IN_T* sr = sr0 + (size_t)r * pitch;
+                    const VT a = s0 != 0xFFFFu ? convert_in<VT, IN_T>(sr[s0], LOG) : VT(0);
+                    const VT b = s1 != 0xFFFFu ? convert_in<VT, IN_T>(sr[s1], LOG) : VT(0);
+                    const VT c = s2 != 0xFFFFu ? convert_in<VT, IN_T>(sr[s2], LOG) : VT(0);
+                    const VT d = s3 != 0xFFFFu ? convert_in<VT, IN_T>(sr[s3], LOG) : VT(0);
+                    store4<VT>(z + (size_t)(row + r) * P.Zrow + rec.x, a, b, c, d);
                 }
             }
         }
+#endif
         __syncthreads();  // this stage (and, on a segment change, the record buffer) may be overwritten
         new_seg = has_next && sn != s;
         if (new_seg) {
             c0 = c1; c1 = c2; c2 = __ldg(P.p1_chunk_ptr + min(sn + 2, P.NS));
             if (tid == 0) fetch_recs(c0, c1);
         }
-        s = sn; rg = rgn;
+        s = sn; row = rown; n = nn; u = un;
     }
 }
 
@@ -465,6 +533,10 @@ constexpr int kTraceCtas = 512, kTraceItems = 32, kTraceEvents = 12;
     } while (0)
 #ifndef GT_COMPUTE_WARPS
 #define GT_COMPUTE_WARPS 8
+#endif
+#ifndef GT_ELL_BATCH
+#define GT_ELL_BATCH 4  // terms of a multi-term range loaded per step (4, or 8: measured slower, the phase is bound by
+                        // shared-memory bandwidth, not by the latency of a batch)
 #endif
 constexpr int kComputeThreads = 32 * GT_COMPUTE_WARPS;        // warps 0 .. GT_COMPUTE_WARPS-1
 constexpr int kEmitThreads = kTileThreads - kComputeThreads;  // the remaining warps
@@ -540,16 +612,21 @@ __device__ __forceinline__ void phase_scatter(VT* vals, const VT* stage, const u
     if (tid == 0) RV::template ident<OP>().store(vals + swz<B>(2 * T - 1) * R);  // identity slot (ELL padding, spanning nodes)
 }
 
-// 2. pyramid of aligned blocks: level k block i at (swizzled) slot 2T - (T >> (k-1)) + i.
-//    Lane u owns leaves 8u .. 8u+7: levels 1..3 in registers, 4..8 by warp shuffles (256 leaves per warp).
+// 2. pyramid of aligned blocks: level k block i at (swizzled) slot 2T - (T >> (k-1)) + i, levels 1 .. kPyramidTop.
+//    Lane u owns LPL = 2^(kPyramidTop-5) consecutive leaves: the first log2(LPL) levels in registers, five more by warp
+//    shuffles, so a warp covers 32*LPL leaves and no level needs a cross-warp step (longer aligned blocks are
+//    multi-term ranges of the ELL phase).  kPyramidTop = 8: 8 leaves per lane, 256 leaves per warp.
 //    The swizzle makes the 16-byte chunk loads and the strided level stores bank-conflict free.
 template <typename VT, int R, int OP, int NWARPS>
 __device__ __forceinline__ void phase_pyramid(VT* vals, int T, int warp, int lane) {
     using RV = RowVec<VT, R>;
     constexpr int B = (int)sizeof(VT) * R;
     constexpr int SPC = 16 / B;  // slots per 16-byte chunk
+    constexpr int LL = kPyramidTop - 5, LPL = 1 << LL;  // in-lane levels, leaves per lane
+    static_assert(LL >= 1 && LPL >= SPC, "a lane owns at least one 16-byte chunk of leaves");
     auto level_slot = [&](int k, int i) { return 2 * T - (T >> (k - 1)) + i; };  // level k >= 1, block i
-    for (int ub = warp * 32; ub < (T >> 3); ub += NWARPS * 32) {
+#if GT_PYR_TOP == 8 && !defined(GT_PYR_GENERIC)
+    for (int ub = warp * 32; ub < (T >> 3); ub += NWARPS * 32) {  // hand-scheduled form of the loop below for 8 leaves per lane
         const int u = ub + lane;
         RV x[8];
 #pragma unroll
@@ -576,6 +653,56 @@ __device__ __forceinline__ void phase_pyramid(VT* vals, int T, int warp, int lan
             if ((lane & ((1 << j) - 1)) == 0) y.store(vals + swz<B>(level_slot(3 + j, u >> j)) * R);
         }
     }
+    return;
+#elif GT_PYR_TOP == 7 && !defined(GT_PYR_GENERIC)
+    for (int ub = warp * 32; ub < (T >> 2); ub += NWARPS * 32) {  // hand-scheduled form of the loop below for 4 leaves per lane
+        const int u = ub + lane;
+        RV x[4];
+#pragma unroll
+        for (int ch = 0; ch < 4 / SPC; ++ch) {
+            const int c = (4 * u) / SPC + ch;
+            const int cc = c ^ ((c >> 3) & (B / 2 - 1));
+            const float4 raw = *reinterpret_cast<const float4*>(reinterpret_cast<const unsigned char*>(vals) + (size_t)cc * 16);
+            memcpy(&x[ch * SPC], &raw, 16);
+        }
+        const RV a0 = RV::template combine<OP>(x[0], x[1]), a1 = RV::template combine<OP>(x[2], x[3]);
+        a0.store(vals + swz<B>(level_slot(1, 2 * u)) * R);
+        a1.store(vals + swz<B>(level_slot(1, 2 * u + 1)) * R);
+        RV y = RV::template combine<OP>(a0, a1);
+        y.store(vals + swz<B>(level_slot(2, u)) * R);
+#pragma unroll
+        for (int j = 1; j <= 5; ++j) {
+            y = RV::template combine<OP>(y, y.shfl_down(1 << (j - 1)));
+            if ((lane & ((1 << j) - 1)) == 0) y.store(vals + swz<B>(level_slot(2 + j, u >> j)) * R);
+        }
+    }
+    return;
+#endif
+    for (int ub = warp * 32; ub < T / LPL; ub += NWARPS * 32) {
+        const int u = ub + lane;
+        RV x[LPL];
+#pragma unroll
+        for (int ch = 0; ch < LPL / SPC; ++ch) {
+            const int c = (LPL * u) / SPC + ch;
+            const int cc = c ^ ((c >> 3) & (B / 2 - 1));
+            const float4 raw = *reinterpret_cast<const float4*>(reinterpret_cast<const unsigned char*>(vals) + (size_t)cc * 16);
+            memcpy(&x[ch * SPC], &raw, 16);
+        }
+#pragma unroll
+        for (int k = 1; k <= LL; ++k) {  // level k: LPL >> k blocks of this lane, written in place over x[0 ..)
+#pragma unroll
+            for (int e = 0; e < (LPL >> k); ++e) {
+                x[e] = RV::template combine<OP>(x[2 * e], x[2 * e + 1]);
+                x[e].store(vals + swz<B>(level_slot(k, (LPL >> k) * u + e)) * R);
+            }
+        }
+        RV y = x[0];
+#pragma unroll
+        for (int j = 1; j <= 5; ++j) {
+            y = RV::template combine<OP>(y, y.shfl_down(1 << (j - 1)));
+            if ((lane & ((1 << j) - 1)) == 0) y.store(vals + swz<B>(level_slot(LL + j, u >> j)) * R);
+        }
+    }
 }
 
 // 3. ranges that need more than one block: ELL chunks of 32 ranges, one warp per chunk, term rows read from shared
@@ -592,7 +719,25 @@ __device__ __forceinline__ void phase_ell(VT* vals, const uint16_t* s_terms, con
         const int2 d = dsc[c];
         const uint16_t* tp = s_terms + (d.x - er0) * 32 + lane;
         RV acc = RV::template ident<OP>();
-        for (int kb = 0; kb < d.y; kb += 4) {
+        // eight terms at a time while they last (all sixteen shared-memory loads of a batch are independent: the
+        // longest ranges of a tile set the length of this phase), then at most one batch of four
+        int kb = 0;
+#if GT_ELL_BATCH >= 8
+        for (; kb + 8 <= d.y; kb += 8) {
+            int sl[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) sl[e] = tp[(kb + e) * 32];
+            RV v[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] = RV::load(vals + sl[e] * R);
+#pragma unroll
+            for (int w = 1; w < 8; w <<= 1)
+#pragma unroll
+                for (int e = 0; e + w < 8; e += 2 * w) v[e] = RV::template combine<OP>(v[e], v[e + w]);
+            acc = RV::template combine<OP>(acc, v[0]);
+        }
+#endif
+        for (; kb < d.y; kb += 4) {
             int sl[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) sl[e] = tp[(kb + e) * 32];
@@ -799,11 +944,37 @@ __global__ void __launch_bounds__(kTileThreads, 2) tile_kernel(PlanView P, TileA
             //    overwritten by span_kernel.
             if (dbg != 3) {
                 constexpr int U = 4;
+                static_assert(U == 4, "the emit loop spells out its four store groups");
                 const int na = n0 & ~7;
                 const int lead = (int)(((reinterpret_cast<uintptr_t>(orow[0]) / sizeof(VT)) + (unsigned)n0) & 31u);
                 const unsigned count = (unsigned)(n1 - n0);
                 const uint16_t* sl_base = s_slots - na;
                 const unsigned char* vbytes = reinterpret_cast<const unsigned char*>(vals);
+#ifdef GT_EMIT_V2
+                // Branch-free variant, 69 instead of 196 instructions per trip -- and measured SLOWER on B200 (tile
+                // kernel 53.7 vs 48.4 us): the stores then leave in bursts, fill the load/store queue that the compute
+                // group's shared-memory instructions share, and each compute phase stretches.  Kept for reference.
+                for (int nb = n0 - lead + tid; nb < n1; nb += U * kEmitThreads) {
+                    // slot reads are unconditional (node ids outside the interval are clamped into it), stores are
+                    // predicated: no branch in the loop body
+                    RV x[U];
+                    bool ok[U];
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        const int n = nb + u * kEmitThreads;
+                        ok[u] = (unsigned)(n - n0) < count;
+                        const int nc = min(max(n, n0), n1 - 1);
+                        x[u] = RV::load(reinterpret_cast<const VT*>(vbytes + (unsigned)sl_base[nc] * (unsigned)B));
+                    }
+                    VT* p[R];
+#pragma unroll
+                    for (int r = 0; r < R; ++r) p[r] = orow[r] + nb;
+                    EmitStore<0 * kEmitThreads * (int)sizeof(VT), VT, R>::run(p, x[0], ok[0]);
+                    EmitStore<1 * kEmitThreads * (int)sizeof(VT), VT, R>::run(p, x[1], ok[1]);
+                    EmitStore<2 * kEmitThreads * (int)sizeof(VT), VT, R>::run(p, x[2], ok[2]);
+                    EmitStore<3 * kEmitThreads * (int)sizeof(VT), VT, R>::run(p, x[3], ok[3]);
+                }
+#else
                 for (int nb = n0 - lead + tid; nb < n1; nb += U * kEmitThreads) {
                     VT* p[R];
 #pragma unroll
@@ -823,6 +994,7 @@ __global__ void __launch_bounds__(kTileThreads, 2) tile_kernel(PlanView P, TileA
                             for (int r = 0; r < R; ++r) __stcs(p[r] + u * kEmitThreads, x[u].v[r]);
                         }
                 }
+#endif
                 // 5. pieces of spanning nodes that overlap this tile (reduced by span_kernel, which runs next on the stream)
                 for (int i = pc0 + tid; i < pc1; i += kEmitThreads) {
                     const bool mine = i == pc0 + tid;
@@ -1064,24 +1236,30 @@ static int sm_count() {
 }
 
 template <typename IN_T, int RP, int NST> static size_t permute_bulk_smem(const PlanView& v) {
-    return (size_t)NST * RP * v.Q * sizeof(IN_T) + (size_t)v.max_seg_recs * 16 + 8 * (NST + 1);
+    return (size_t)NST * RP * (v.Q * sizeof(IN_T) + kPermPad) + (size_t)v.max_seg_recs * 16 + 8 * (NST + 1);
 }
 // rows must be 16-byte aligned segment by segment for the copy engine
 template <typename IN_T> static bool permute_bulk_ok(const PlanView& v, const void* ws, int64_t ld_ws) {
     return (reinterpret_cast<uintptr_t>(ws) & 15) == 0 && ((ld_ws * (int64_t)sizeof(IN_T)) & 15) == 0 &&
            ((v.V * (int64_t)sizeof(IN_T)) & 15) == 0 && (((int64_t)v.Q * (int64_t)sizeof(IN_T)) & 15) == 0;
 }
+template <typename VT, typename IN_T, int RP, int NST, bool LOG>
+static int launch_permute_bulk_lg(const PlanView& v, const void* ws, int64_t ld_ws, const Scratch<VT>& sc, int rows, cudaStream_t st) {
+    const size_t smem = permute_bulk_smem<IN_T, RP, NST>(v);
+    GT_CUDA(allow_smem(permute_bulk_kernel<VT, IN_T, RP, NST, LOG>, smem));
+    // one CTA per resident slot; each takes an equal share of the (segment, row) pairs, at least RP of them
+    const int64_t groups = ((int64_t)v.NS * rows + RP - 1) / RP;
+    const int slots = sm_count() * resident_ctas(reinterpret_cast<const void*>(permute_bulk_kernel<VT, IN_T, RP, NST, LOG>), kThreads, smem);
+    const unsigned grid = (unsigned)std::min<int64_t>(groups, slots);
+    GT_CUDA(launch_pdl(permute_bulk_kernel<VT, IN_T, RP, NST, LOG>, dim3(grid), dim3(kThreads), smem, st, v, static_cast<const IN_T*>(ws),
+                       ld_ws, sc.z, rows));
+    return GT_OK;
+}
 template <typename VT, typename IN_T, int RP, int NST>
 static int launch_permute_bulk(const PlanView& v, const void* ws, int64_t ld_ws, const Scratch<VT>& sc, int rows,
                                bool log_input, cudaStream_t st) {
-    const size_t smem = permute_bulk_smem<IN_T, RP, NST>(v);
-    GT_CUDA(allow_smem(permute_bulk_kernel<VT, IN_T, RP, NST>, smem));
-    const int64_t items = (int64_t)v.NS * ((rows + RP - 1) / RP);
-    const int slots = sm_count() * resident_ctas(reinterpret_cast<const void*>(permute_bulk_kernel<VT, IN_T, RP, NST>), kThreads, smem);
-    const unsigned grid = (unsigned)std::min<int64_t>(items, slots);
-    GT_CUDA(launch_pdl(permute_bulk_kernel<VT, IN_T, RP, NST>, dim3(grid), dim3(kThreads), smem, st, v, static_cast<const IN_T*>(ws),
-                       ld_ws, sc.z, rows, log_input ? 1 : 0));
-    return GT_OK;
+    return log_input ? launch_permute_bulk_lg<VT, IN_T, RP, NST, true>(v, ws, ld_ws, sc, rows, st)
+                     : launch_permute_bulk_lg<VT, IN_T, RP, NST, false>(v, ws, ld_ws, sc, rows, st);
 }
 
 template <typename VT, typename IN_T, int R>

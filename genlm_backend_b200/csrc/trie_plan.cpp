@@ -30,9 +30,9 @@ int build_plan(const Layout& L, int32_t T, int32_t Q, int32_t R, Plan& P) {
     if (Q < 4 || Q > 16384 || (Q & 3)) { set_error("segment size must be a multiple of 4 in [4, 16384]"); return GT_ERR_ARG; }
     if (R != 2 && R != 4) { set_error("rows per CTA must be 2 or 4"); return GT_ERR_ARG; }
     const int logT = ilog2(T);
-    // Aligned blocks stop at 256 leaves (level 8): one warp builds levels 1..8 of its 256 leaves with shuffles, so
-    // the pyramid needs no cross-warp step; the few ranges longer than that just carry more terms.
-    const int kTop = std::min(logT, 8);
+    // Aligned blocks stop at 2^kPyramidTop leaves: one warp builds all levels of its block with shuffles, so the
+    // pyramid needs no cross-warp step; the few ranges longer than that just carry more terms.
+    const int kTop = std::min(logT, kPyramidTop);
     P.T = T; P.Q = Q; P.R = R; P.slot_bytes = 4 * R;
     const int32_t SB = P.slot_bytes;
     auto swz = [&](int32_t s) -> uint16_t { return (uint16_t)(s < 2 * T ? swizzle_slot(s, SB) : s); };

@@ -19,7 +19,20 @@ from ..sharding import row_blocks
 
 # rows per pipelined slice of the host->device->host path
 _PIPE_ROWS = 32
+_PIPE_FIRST = 8
 _PIPE_SLOTS = 3
+
+
+def _pipe_slices(lo, hi):
+    """Row slices of the host->device->host pipeline.  The first slice is short: nothing overlaps its H2D copy, and
+    the D2H stream -- the PCIe-bound part, 2.7 MB per row and reduction at 128k tokens -- starts as soon as it is
+    reduced; the following slices are ``_PIPE_ROWS`` rows."""
+    out, r0 = [], lo
+    while r0 < hi:
+        r1 = min(hi, r0 + (_PIPE_FIRST if r0 == lo else _PIPE_ROWS))
+        out.append((r0, r1))
+        r0 = r1
+    return out
 
 
 class ParallelTokenCharacterTrie(TokenCharacterTrie):
@@ -165,8 +178,7 @@ class ParallelTokenCharacterTrie(TokenCharacterTrie):
             streams = self._pipe_streams(index)
             start = torch.cuda.Event()
             start.record(torch.cuda.current_stream(ws.device.index if ws.is_cuda else index))
-            for k, r0 in enumerate(range(lo, hi, _PIPE_ROWS)):
-                r1 = min(hi, r0 + _PIPE_ROWS)
+            for k, (r0, r1) in enumerate(_pipe_slices(lo, hi)):
                 st = streams[k % _PIPE_SLOTS]
                 st.wait_event(start)  # inputs produced on the caller's stream are ready
                 with torch.cuda.device(index), torch.cuda.stream(st):

@@ -63,7 +63,7 @@ def emulate(engine, ws, op="sum"):
         assert not np.isnan(vals[:, phys[:nleaf]]).any() or np.isnan(ws).any()
         # phase 2.2: pyramid, level k block i at logical slot 2T - (T >> (k-1)) + i (physical: swizzled)
         prev = vals[:, phys[:T]]
-        for k in range(1, min(logT, 8) + 1):  # aligned blocks stop at 256 leaves (level 8)
+        for k in range(1, info["max_levels"] + 1):  # aligned blocks stop at 2^max_levels leaves (a warp's share)
             cur = red(prev[:, 0::2], prev[:, 1::2]).astype(np.float32)
             off = 2 * T - (T >> (k - 1))
             vals[:, phys[off:off + cur.shape[1]]] = cur

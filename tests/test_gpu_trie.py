@@ -237,3 +237,42 @@ def test_multi_device_row_sharding_matches_single():
     many = ParallelTokenCharacterTrie(dec, devices=list(range(n)))
     assert np.array_equal(one.batch_weight_sum(ws), many.batch_weight_sum(ws))
     assert np.array_equal(one.batch_weight_max(ws), many.batch_weight_max(ws))
+
+
+def test_async_autobatch_1024_requests_full_size():
+    """BASELINE config 3: AsyncTokenCharacterTrie autobatching 1,024 concurrent weight_sum requests at 128,256 tokens
+    (reference: async_impl.py:46-137, tests/test_trie.py:157-207).  Every future gets its own row's result: a sample of
+    rows against the oracle, all rows through the root / leaf properties."""
+    import asyncio
+
+    from genlm_backend_b200 import AsyncTokenCharacterTrie
+
+    V, R = 128256, 1024
+    at = AsyncTokenCharacterTrie.from_vocab(synth_vocab(V), backend="parallel")
+    trie = at.trie
+    ws = dirichlet_rows(R, V, alpha=0.1, seed=31)
+    rows = [torch.tensor(w) for w in ws]
+
+    async def main():
+        sums = await asyncio.gather(*[at.weight_sum(r) for r in rows])
+        maxes = await asyncio.gather(*[at.weight_max(r) for r in rows[:64]])
+        await at.cleanup()
+        return sums, maxes
+
+    sums, maxes = asyncio.run(main())
+    assert len(sums) == R and all(s.shape == (len(trie),) and s.dtype == np.float32 for s in sums)
+    leaf = trie._layout["leaf_node"]
+    o = oracle_for(trie)
+    pick = [0, 1, 511, 1023]
+    want = o.weight_sum(ws[pick].astype(np.float64))
+    for j, i in enumerate(pick):
+        r, z = rel_err(sums[i], want[j])
+        assert r <= SUM_RTOL and z == 0.0
+    for i in range(R):  # each request got its own row back
+        assert np.array_equal(sums[i][leaf], ws[i])
+        assert abs(float(sums[i][trie.root]) - float(ws[i].astype(np.float64).sum())) <= 1e-6
+    wm = o.weight_max(ws[:4].astype(np.float64)).astype(np.float32)
+    for i in range(4):
+        assert np.array_equal(maxes[i], wm[i])
+    for i in range(64):
+        assert float(maxes[i][trie.root]) == float(ws[i].max())
