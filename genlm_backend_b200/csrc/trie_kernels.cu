@@ -546,7 +546,7 @@ struct TileSmem {
     size_t vals, vals_bytes, stage, p2, slots, terms, desc, bars, total;
     __host__ __device__ TileSmem(const PlanView& P, int slot_bytes, int elem_bytes, int R) {
         size_t o = 0;
-        vals_bytes = (size_t)(P.SV + 4) * slot_bytes;                       // value slots + trash slot
+        vals_bytes = (size_t)(P.SV + 16) * slot_bytes;                      // value slots + one trash slot per bank group
         vals = o;  o += 2 * vals_bytes;                                     // double-buffered between the groups
         stage = o; o += (size_t)R * P.max_tile_z * elem_bytes;              // staged rows of the next item
         p2 = o;    o += (size_t)P.max_tile_z * 2;                           // staged element -> value slot

@@ -53,11 +53,11 @@ def emulate(engine, ws, op="sum"):
     SV = info["max_tile_values"]
     for t in range(NT):
         # phase 2.1: leaves
-        vals = np.full((B, SV + 1), np.nan, dtype=np.float32)  # slot SV = trash slot for staged padding
+        vals = np.full((B, SV + 16), np.nan, dtype=np.float32)  # slots SV .. SV+15: trash slots for staged padding
         zlo, zhi = A["z_tile_off"][t], A["z_tile_off"][t + 1]
         slot = A["p2_slot"][zlo:zhi]
         nleaf = min(T, V - t * T)
-        assert slot.max() <= SV and np.array_equal(np.sort(slot[slot < SV]), np.sort(phys[:nleaf]))
+        assert slot.max() < SV + 16 and np.array_equal(np.sort(slot[slot < SV]), np.sort(phys[:nleaf]))
         vals[:, slot] = z[:, zlo:zhi]
         vals[:, phys[nleaf:T]] = ident
         assert not np.isnan(vals[:, phys[:nleaf]]).any() or np.isnan(ws).any()
