@@ -49,6 +49,9 @@ def parse_args():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-sampler", action="store_true", help="skip the secondary sampler-kernel measurement")
+    ap.add_argument("--allgather", action="store_true",
+                    help="N > 1 only: also time the optional NCCL all-gather of the node masses (BASELINE config 5's exchange); "
+                         "reported separately, never part of the timed step")
     return ap.parse_args()
 
 
@@ -231,9 +234,19 @@ def run_ours(args):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # NCCL writes its banner ("NCCL version ...") to stdout by default; stdout carries exactly one JSON line
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL prints its banner ("NCCL version ...") to stdout when the first communicator is created; stdout carries
+        # exactly one JSON line, so file descriptor 1 points at stderr until that has happened
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
 
     def barrier():
         if world > 1:
@@ -369,6 +382,30 @@ def run_ours(args):
     barrier()
     clocks.stop()
 
+    # optional exchange of BASELINE config 5: all-gather of the [B, N] node masses over NVLink (not on the hot path) -------
+    allgather = None
+    if world > 1 and args.allgather:
+        from genlm_backend_b200.sharding import all_gather_rows
+
+        local = sum_sets[0].contiguous()  # this rank's [B, N] block (the slab's row padding is not sent)
+        for _ in range(3):
+            full = all_gather_rows(local, world * B)
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 10
+        a.record()
+        for _ in range(reps):
+            full = all_gather_rows(local, world * B)
+        b.record()
+        torch.cuda.synchronize()
+        ms = max_over_ranks(a.elapsed_time(b) / reps)
+        ok = bool(torch.equal(full[rank * B:(rank + 1) * B], local))
+        allgather = {"ms": ms, "rows_per_rank": B, "bytes_received_per_gpu": (world - 1) * B * N * 4,
+                     "GBps_per_gpu_in": (world - 1) * B * N * 4 / (ms * 1e-3) / 1e9, "own_block_intact": ok,
+                     "api": "genlm_backend_b200.sharding.all_gather_rows -> torch.distributed.all_gather_into_tensor (NCCL)",
+                     "note": "one reduction's [B, N] fp32 node masses per rank; reported separately, not part of a step"}
+        del full
+
     if world > 1:
         dist.destroy_process_group()
     if rank != 0:
@@ -419,6 +456,8 @@ def run_ours(args):
                       "span_both": ms_span_both, "sum_op_all_phases": ms_sum_op},
         "clocks": clocks.summary(),
     }
+    if allgather is not None:
+        line["allgather"] = allgather
     if world == 1 and not args.no_sampler:
         line["sampler"] = sampler_metrics(dev, V, peak)
     if world == 1 and not args.no_cpu_baseline:
