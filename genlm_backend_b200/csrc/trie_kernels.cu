@@ -943,8 +943,11 @@ __global__ void __launch_bounds__(kTileThreads, 2) tile_kernel(PlanView P, TileA
             //    Spanning nodes inside the interval carry the identity slot: what is written for them here is
             //    overwritten by span_kernel.
             if (dbg != 3) {
+#if defined(GT_EMIT_V2) && defined(GT_EMIT_U)
+                constexpr int U = GT_EMIT_U;  // nodes per thread and trip of the branch-free variant: 1, 2 or 4
+#else
                 constexpr int U = 4;
-                static_assert(U == 4, "the emit loop spells out its four store groups");
+#endif
                 const int na = n0 & ~7;
                 const int lead = (int)(((reinterpret_cast<uintptr_t>(orow[0]) / sizeof(VT)) + (unsigned)n0) & 31u);
                 const unsigned count = (unsigned)(n1 - n0);
@@ -970,9 +973,9 @@ __global__ void __launch_bounds__(kTileThreads, 2) tile_kernel(PlanView P, TileA
 #pragma unroll
                     for (int r = 0; r < R; ++r) p[r] = orow[r] + nb;
                     EmitStore<0 * kEmitThreads * (int)sizeof(VT), VT, R>::run(p, x[0], ok[0]);
-                    EmitStore<1 * kEmitThreads * (int)sizeof(VT), VT, R>::run(p, x[1], ok[1]);
-                    EmitStore<2 * kEmitThreads * (int)sizeof(VT), VT, R>::run(p, x[2], ok[2]);
-                    EmitStore<3 * kEmitThreads * (int)sizeof(VT), VT, R>::run(p, x[3], ok[3]);
+                    if constexpr (U > 1) EmitStore<1 * kEmitThreads * (int)sizeof(VT), VT, R>::run(p, x[1 % U], ok[1 % U]);
+                    if constexpr (U > 2) EmitStore<2 * kEmitThreads * (int)sizeof(VT), VT, R>::run(p, x[2 % U], ok[2 % U]);
+                    if constexpr (U > 2) EmitStore<3 * kEmitThreads * (int)sizeof(VT), VT, R>::run(p, x[3 % U], ok[3 % U]);
                 }
 #else
                 for (int nb = n0 - lead + tid; nb < n1; nb += U * kEmitThreads) {
