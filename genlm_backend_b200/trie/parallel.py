@@ -53,6 +53,7 @@ class ParallelTokenCharacterTrie(TokenCharacterTrie):
         self._devices = None if devices is None else [int(d) for d in devices]
         self._reach = None
         self._streams = {}
+        self._stage = {}  # (device, pipeline slot) -> (pinned [rows, V] staging buffer, event of its last H2D copy)
         # position of each leaf's weight in the input rows (the identity: idx_to_leaf[:, 0])
         self.positions = torch.tensor(self.idx_to_leaf[:, 0], dtype=torch.long, device=self.device)
 
@@ -155,13 +156,39 @@ class ParallelTokenCharacterTrie(TokenCharacterTrie):
                 self._streams[index] = [torch.cuda.Stream(device=index) for _ in range(_PIPE_SLOTS)]
         return self._streams[index]
 
+    def _host_rows(self, ws):
+        """A list / tuple of 1-D CPU float32 rows of the right length (what the async wrapper hands over for requests
+        that arrive as host tensors), or ``None``.  Such a batch is staged slice by slice through pinned buffers
+        instead of being stacked first: the host copy of a slice overlaps the device work of the slices before it."""
+        if not isinstance(ws, (list, tuple)) or len(ws) < 2:
+            return None
+        V = len(self.decode)
+        for r in ws:
+            if not (isinstance(r, torch.Tensor) and r.device.type == "cpu" and r.dtype == torch.float32 and r.dim() == 1):
+                return None
+            assert r.shape[0] == V, [r.shape[0], V]
+        return ws
+
+    def _stage_buffer(self, index, slot, rows):
+        key = (index, slot)
+        buf, ev = self._stage.get(key, (None, None))
+        if buf is None or buf.shape[0] < rows:
+            buf = torch.empty((rows, len(self.decode)), dtype=torch.float32, pin_memory=True)
+            ev = torch.cuda.Event()
+            self._stage[key] = (buf, ev)
+        else:
+            ev.synchronize()  # the H2D copy that last read this buffer has finished
+        return buf, ev
+
     def _batch_to_host(self, ws, ops, log_input=False):
         """Run ``ops`` over the batch and return host arrays.  Rows are split contiguously over the configured
         GPUs; on each GPU slices of ``_PIPE_ROWS`` rows flow H2D -> kernels -> D2H on rotating streams so the
         copies overlap the kernels and each other.  Results land in pinned host memory that the returned
         numpy arrays own."""
-        ws = self._as_batch(ws)
-        B, N = ws.shape[0], len(self)
+        host_rows = self._host_rows(ws)
+        if host_rows is None:
+            ws = self._as_batch(ws)
+        B, N = (len(host_rows) if host_rows is not None else ws.shape[0]), len(self)
         devices = self._device_list()
         # pinned host slabs with the device slabs' padded row stride, so every D2H copy is one flat contiguous
         # transfer; callers get the [B, N] view (each row is a contiguous float32 array)
@@ -177,14 +204,20 @@ class ParallelTokenCharacterTrie(TokenCharacterTrie):
             dev = torch.device("cuda", index)
             streams = self._pipe_streams(index)
             start = torch.cuda.Event()
-            start.record(torch.cuda.current_stream(ws.device.index if ws.is_cuda else index))
+            start.record(torch.cuda.current_stream(ws.device.index if host_rows is None and ws.is_cuda else index))
             for k, (r0, r1) in enumerate(_pipe_slices(lo, hi)):
                 st = streams[k % _PIPE_SLOTS]
                 st.wait_event(start)  # inputs produced on the caller's stream are ready
                 with torch.cuda.device(index), torch.cuda.stream(st):
-                    chunk = ws[r0:r1]
-                    if chunk.device != dev:
-                        chunk = chunk.to(dev, non_blocking=True)
+                    if host_rows is not None:
+                        stage, staged = self._stage_buffer(index, k % _PIPE_SLOTS, _PIPE_ROWS)
+                        torch.stack(host_rows[r0:r1], out=stage[: r1 - r0])
+                        chunk = stage[: r1 - r0].to(dev, non_blocking=True)
+                        staged.record(st)
+                    else:
+                        chunk = ws[r0:r1]
+                        if chunk.device != dev:
+                            chunk = chunk.to(dev, non_blocking=True)
                     o_sum, o_max = self._engine.reduce(chunk, ops, log_input=log_input, slot=k % _PIPE_SLOTS)
                     if o_sum is not None:
                         outs["sum"][r0:r1].copy_(o_sum._base[: r1 - r0], non_blocking=True)
