@@ -4,9 +4,10 @@
 // temperature variant genlm/backend/llm/base.py:131-146):
 //     masked = logp + mask;  logZ = masked.logsumexp(-1);  tok = multinomial((masked - logZ).exp(), 1)
 //
-// One CTA per row.  Thread t owns the 16-byte groups g = t, t+512, ... of the row and keeps an online
-// (max, sum-exp) pair for them; after a block reduction (fp64) a Philox uniform picks first the owning
-// thread, then the element among that thread's ~V/512 elements, which are re-read from L2 (a few KB).
+// One CTA of kSThreads = 256 threads per row, four rows in flight per SM.  Thread t owns the 16-byte groups
+// g = t, t + kSThreads, ... of the row and keeps an online (max, sum-exp) pair for them; after a block reduction
+// (fp64) a Philox uniform picks first the owning thread, then the element among that thread's ~V/kSThreads
+// elements, which are re-read from L2 (a few KB).
 // The draw is an exact inverse CDF over a fixed permutation of the vocabulary, so it is distributed as
 // the reference's multinomial but is not stream-identical to torch's generator.
 #include <cuda_runtime.h>
@@ -20,7 +21,13 @@
 
 namespace gt {
 
-constexpr int kSThreads = 512;
+#ifndef GT_SAMPLER_THREADS
+#define GT_SAMPLER_THREADS 256
+#endif
+// Threads per row; 1024 / kSThreads rows are in flight per SM.  256 (4 rows per SM) measured 12 % faster than 512 on
+// B200 at 512 rows x 128k: all rows of a launch start in one wave and the block-wide tail of a row (reduction, draw,
+// second pass) overlaps three other rows' streaming instead of one.
+constexpr int kSThreads = GT_SAMPLER_THREADS;
 constexpr float kLog2e = 1.4426950408889634f;
 
 // 2^x for x <= 0 (flush-to-zero below 2^-126: such terms vanish against the row maximum anyway): one MUFU, without
@@ -250,11 +257,62 @@ __device__ __forceinline__ void warp_find(const double* arr, int n, double targe
     }
 }
 
-template <typename IN_T, int MK>
-__global__ void __launch_bounds__(kSThreads, 2) lse_sample_kernel(SampleArgs A) {
+// Second pass of a row, executed by the whole CTA once per row: the picked thread owned groups pick, pick + NT, ...;
+// candidate c of them goes to thread c % NT (one candidate per thread unless the row has more than NT^2 groups),
+// a second inverse-CDF step picks the thread and it walks its candidates' elements.  (Measured both ways: inlined is
+// 1-5 % faster for fp32 rows than a __noinline__ call, which spills the row view to the stack.)
+template <typename IN_T, int MK, int NT>
+__device__ __forceinline__ void locate_token(const RowView<IN_T, MK>& rv, int pick, double resid, float M, float SC, int ng,
+                                          double* s_mass, int* s_pick, double* s_resid, int32_t* tok_out) {
     constexpr int EPV = RowView<IN_T, MK>::EPV;
-    __shared__ double s_mass[kSThreads];
-    __shared__ float s_wmax[kSThreads / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n_cand = (ng - pick + NT - 1) / NT;
+    const float ms2 = -M * SC;
+    double local = 0.0;
+    for (int c = tid; c < n_cand; c += NT) {
+        float x[EPV];
+        rv.fetch(pick + c * NT, x);
+#pragma unroll
+        for (int k = 0; k < EPV; ++k) local += (double)fast_exp2(fmaf(x[k], SC, ms2));
+    }
+    s_mass[tid] = local;
+    __syncthreads();
+    if (warp == 0) {
+        int k2; double before2;
+        warp_find(s_mass, min(n_cand, NT), resid, k2, before2);
+        if (lane == 0) { *s_pick = k2; *s_resid = (before2 < 0.0) ? -1.0 : resid - before2; }
+    }
+    __syncthreads();
+    const int k2 = *s_pick;
+    if (k2 < 0) {  // exp underflow relative to the global max wiped the picked thread's mass
+        if (tid == 0) *tok_out = -1;
+    } else if (tid == k2) {
+        const double rr = *s_resid;
+        int chosen = -1; double run = 0.0;
+        for (int c = k2; c < n_cand; c += NT) {
+            const int g = pick + c * NT;
+            float x[EPV];
+            rv.fetch(g, x);
+#pragma unroll
+            for (int k = 0; k < EPV; ++k) {
+                const float w = fast_exp2(fmaf(x[k], SC, ms2));
+                if (w > 0.f) {
+                    // the first positive element always qualifies; later ones while the running sum has not
+                    // passed the residual (rr < 0: keep going to the last positive element)
+                    if (chosen < 0 || rr < 0.0 || run <= rr) chosen = g * EPV - rv.phase + k;
+                    run += (double)w;
+                }
+            }
+        }
+        *tok_out = chosen;
+    }
+}
+
+template <typename IN_T, int MK, int NT>
+__global__ void __launch_bounds__(NT, 1024 / NT) lse_sample_kernel(SampleArgs A) {
+    constexpr int EPV = RowView<IN_T, MK>::EPV;
+    __shared__ double s_mass[NT];
+    __shared__ float s_wmax[NT / 32];
     __shared__ float s_M;
     __shared__ int s_pick;
     __shared__ double s_resid;
@@ -284,16 +342,18 @@ __global__ void __launch_bounds__(kSThreads, 2) lse_sample_kernel(SampleArgs A) 
         const int ng = rv.n_groups();
 
         // ---- pass 1: online (max, sum exp) per thread ------------------------------------------------
-        // Thread t owns groups t, t + 512, ...  Its interior groups are streamed in rounds of U with no per-group
+        // Thread t owns groups t, t + NT, ...  Its interior groups are streamed in rounds of U with no per-group
         // checks: the 16-byte loads (+ mask words) of the next round are requested while the current round is reduced,
         // so every thread keeps 64 bytes of the row in flight.  What is left (fewer than U interior groups, and the
         // one or two edge groups of an unaligned row) is handled group by group afterwards.
         const float SC = rv.scale();
         float m = -INFINITY, s = 0.f;
-        constexpr int U = (EPV >= 8 || MK == GT_MASK_ADD_F32) ? 2 : 4;
+        // groups in flight per thread: 64 bytes of row (+ mask words); one group for 2-byte rows under an additive mask,
+        // whose 32 mask bytes per group would otherwise push the loop into spills
+        constexpr int U = (EPV >= 8 && MK == GT_MASK_ADD_F32) ? 1 : (EPV >= 8 || MK == GT_MASK_ADD_F32) ? 2 : 4;
         const int g_lo = rv.phase ? 1 : 0, g_hi = (rv.phase + rv.V) / EPV;  // interior groups: [g_lo, g_hi)
-        const int g0 = tid < g_lo ? tid + kSThreads : tid;
-        const int cnt = g0 < g_hi ? (g_hi - 1 - g0) / kSThreads + 1 : 0;
+        const int g0 = tid < g_lo ? tid + NT : tid;
+        const int cnt = g0 < g_hi ? (g_hi - 1 - g0) / NT + 1 : 0;
         const int rounds = cnt / U;
         auto stream = [&](auto vec_tag) {  // vec_tag: the mask lines up with the row's groups (vector mask loads)
             constexpr bool VEC = decltype(vec_tag)::value;
@@ -301,7 +361,7 @@ __global__ void __launch_bounds__(kSThreads, 2) lse_sample_kernel(SampleArgs A) 
             typename RowView<IN_T, MK>::Cursor c = rv.cursor(g0);
             if (rounds > 0) {
 #pragma unroll
-                for (int u = 0; u < U; ++u) raw[u] = rv.template issue<VEC>(c, u * kSThreads);
+                for (int u = 0; u < U; ++u) raw[u] = rv.template issue<VEC>(c, u * NT);
             }
             for (int r = 0; r < rounds; ++r) {
                 const bool more = r + 1 < rounds;
@@ -315,20 +375,20 @@ __global__ void __launch_bounds__(kSThreads, 2) lse_sample_kernel(SampleArgs A) 
                     for (int uu = 0; uu < UH; ++uu) {
                         const int u = h + uu;
                         float yu[EPV];
-                        rv.template finish<VEC>(c, u * kSThreads, raw[u], yu);
+                        rv.template finish<VEC>(c, u * NT, raw[u], yu);
 #pragma unroll
                         for (int k = 0; k < EPV; ++k) y[uu * EPV + k] = yu[k];
                         // the register set is free again: request this thread's group of the next round right away
-                        if (more) raw[u] = rv.template issue<VEC>(c, (U + u) * kSThreads);
+                        if (more) raw[u] = rv.template issue<VEC>(c, (U + u) * NT);
                     }
                     online_update<UH * EPV>(y, SC, m, s);
                 }
-                rv.advance(c, U * kSThreads);
+                rv.advance(c, U * NT);
             }
             for (int i = rounds * U; i < cnt; ++i) {
                 float y[EPV];
                 rv.template finish<VEC>(c, 0, rv.template issue<VEC>(c, 0), y);
-                rv.advance(c, kSThreads);
+                rv.advance(c, NT);
                 online_update<EPV>(y, SC, m, s);
             }
         };
@@ -340,7 +400,7 @@ __global__ void __launch_bounds__(kSThreads, 2) lse_sample_kernel(SampleArgs A) 
                 rv.fetch_edge(0, y);
                 online_update<EPV>(y, SC, m, s);
             }
-            if (g_hi < ng && g_hi >= g_lo && tid == g_hi % kSThreads) {
+            if (g_hi < ng && g_hi >= g_lo && tid == g_hi % NT) {
                 float y[EPV];
                 rv.fetch_edge(g_hi, y);
                 online_update<EPV>(y, SC, m, s);
@@ -356,7 +416,7 @@ __global__ void __launch_bounds__(kSThreads, 2) lse_sample_kernel(SampleArgs A) 
         __syncthreads();
         if (tid == 0) {
             float M0 = s_wmax[0];
-            for (int w = 1; w < kSThreads / 32; ++w) M0 = fmaxf(M0, s_wmax[w]);
+            for (int w = 1; w < NT / 32; ++w) M0 = fmaxf(M0, s_wmax[w]);
             s_M = M0;
         }
         __syncthreads();
@@ -366,7 +426,7 @@ __global__ void __launch_bounds__(kSThreads, 2) lse_sample_kernel(SampleArgs A) 
 
         if (warp == 0) {
             double tot = 0.0;
-            for (int i = lane; i < kSThreads; i += 32) tot += s_mass[i];
+            for (int i = lane; i < NT; i += 32) tot += s_mass[i];
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
             // 53-bit uniform in [0,1): Philox4x32-10, counter = offset + row, key = seed
@@ -376,7 +436,7 @@ __global__ void __launch_bounds__(kSThreads, 2) lse_sample_kernel(SampleArgs A) 
             const double u = (double)(((uint64_t)(r[0] >> 5) << 26) | (uint64_t)(r[1] >> 6)) * (1.0 / 9007199254740992.0);
             const bool ok = (M > -INFINITY) && (tot > 0.0) && (tot < (double)INFINITY);  // false for NaN
             int pick = -1; double before = 0.0;
-            if (ok) warp_find(s_mass, kSThreads, u * tot, pick, before);
+            if (ok) warp_find(s_mass, NT, u * tot, pick, before);
             if (lane == 0) {
                 s_pick = pick;
                 s_resid = before < 0.0 ? -1.0 : u * tot - before;
@@ -393,46 +453,7 @@ __global__ void __launch_bounds__(kSThreads, 2) lse_sample_kernel(SampleArgs A) 
         }
 
         // ---- pass 2: re-read the picked thread's groups (L2-hot, a few KB) and locate the element ------
-        float x[EPV];
-        const int g = pick + tid * kSThreads;
-        double local = 0.0;
-        if (g < ng) {
-            rv.fetch(g, x);
-            const float ms = -M * SC;
-#pragma unroll
-            for (int k = 0; k < EPV; ++k) { x[k] = fast_exp2(fmaf(x[k], SC, ms)); local += (double)x[k]; }
-        } else {
-#pragma unroll
-            for (int k = 0; k < EPV; ++k) x[k] = 0.f;
-        }
-        s_mass[tid] = local;
-        __syncthreads();
-        if (warp == 0) {
-            const int n_cand = (ng - pick + kSThreads - 1) / kSThreads;  // threads holding a group
-            int k2; double before2;
-            warp_find(s_mass, n_cand, resid, k2, before2);
-            if (lane == 0) { s_pick = k2; s_resid = (before2 < 0.0) ? -1.0 : resid - before2; }
-        }
-        __syncthreads();
-        const int k2 = s_pick;
-        if (k2 < 0) {  // exp underflow relative to the global max wiped the picked thread's mass
-            if (tid == 0) A.tok[b] = -1;
-        } else if (tid == k2) {
-            const double rr = s_resid;
-            int chosen = -1; double run = 0.0;
-#pragma unroll
-            for (int k = 0; k < EPV; ++k) {
-                if (x[k] > 0.f && (chosen < 0 || rr < 0.0 || run <= rr)) {
-                    // first positive element always qualifies; later ones while the running sum has not
-                    // passed the residual (rr < 0: keep going to the last positive element)
-                    chosen = k;
-                    run += (double)x[k];
-                } else if (x[k] > 0.f) {
-                    run += (double)x[k];
-                }
-            }
-            A.tok[b] = g * EPV - rv.phase + chosen;
-        }
+        locate_token<IN_T, MK, NT>(rv, pick, resid, M, SC, ng, s_mass, &s_pick, &s_resid, A.tok + b);
         __syncthreads();
     }
 }
@@ -442,7 +463,10 @@ template <typename IN_T, int MK> static int launch_sampler_mk(const SampleArgs& 
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int grid = A.n_rows < sms * 8 ? A.n_rows : sms * 8;
-    lse_sample_kernel<IN_T, MK><<<grid, kSThreads, 0, st>>>(A);
+    // 2-byte rows under an additive fp32 mask move twice as many mask bytes as row bytes per group and measured faster
+    // with two wide CTAs per SM (40 vs 51 us); every other combination prefers four CTAs of kSThreads
+    constexpr int NT = (sizeof(IN_T) == 2 && MK == GT_MASK_ADD_F32) ? 2 * kSThreads : kSThreads;
+    lse_sample_kernel<IN_T, MK, NT><<<grid, NT, 0, st>>>(A);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { set_error("lse_sample launch failed: %s", cudaGetErrorString(e)); return GT_ERR_CUDA; }
     return GT_OK;

@@ -145,3 +145,30 @@ def test_full_size_rows_are_sampled_in_proportion():
     exp = np.add.reduceat(p, edges[:-1]) * n
     chi, pval = stats.chisquare(obs, exp * (obs.sum() / exp.sum()))
     assert pval > 1e-4, (chi, pval)
+
+
+@pytest.mark.parametrize("V,dtype", [(300_001, torch.float32), (140_003, torch.float64), (600_011, torch.bfloat16)])
+def test_rows_longer_than_one_candidate_per_thread(V, dtype):
+    """Rows with more 16-byte groups than threads^2: the second pass gives a thread several candidate groups.
+    Point masses must be drawn exactly wherever they sit, and a two-point row splits in proportion."""
+    rng = np.random.default_rng(V)
+    spots = [0, 1, V // 2, V - 5, V - 1] + rng.integers(0, V, 11).tolist()
+    logp = torch.full((len(spots) + 1, V), float("-inf"), dtype=dtype)
+    for b, i in enumerate(spots):
+        logp[b, i] = -0.25
+    a, c = V // 3, V - 2  # 1/4 : 3/4
+    logp[-1, a], logp[-1, c] = np.log(0.25), np.log(0.75)
+    dev = logp.cuda()
+    logZ, tok = smc.masked_logsumexp_sample(dev, None, seed=11)
+    assert tok.cpu().numpy()[:-1].tolist() == spots
+    np.testing.assert_allclose(logZ.cpu().numpy()[:-1], -0.25, atol=2e-3 if dtype == torch.bfloat16 else 1e-6)
+    two = dev[-1:].repeat(512, 1)
+    draws = np.concatenate([smc.masked_logsumexp_sample(two, None, seed=5, offset=512 * i)[1].cpu().numpy() for i in range(32)])
+    assert set(np.unique(draws)) == {a, c}
+    frac = (draws == c).mean()
+    assert abs(frac - 0.75) < 5 * np.sqrt(0.75 * 0.25 / len(draws))  # 5 sigma
+    # a dense row of this length: logZ against the float64 oracle
+    dense = torch.tensor(logsoftmax_rows(2, V, seed=3)).to(dtype)
+    lz, tk = smc.masked_logsumexp_sample(dense.cuda(), None, seed=1)
+    np.testing.assert_allclose(lz.cpu().numpy(), oracle.masked_logsumexp(dense.to(torch.float64).numpy()), rtol=1e-5, atol=2e-5)
+    assert ((tk.cpu().numpy() >= 0) & (tk.cpu().numpy() < V)).all()
