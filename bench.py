@@ -378,6 +378,19 @@ def run_ours(args):
         _ = float(sums[0, N - 1]) + float(maxes[B - 1, N - 1])  # results are on the host
     torch.cuda.synchronize()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
+    # the same step when the caller reads K nodes per row instead of the whole slab (gt_gather_nodes): the [B, N] results
+    # stay on the GPU, H2D of the rows and D2H of 2 x [B, K] values are inside the timed region
+    Ks = 257  # e.g. the 256 byte children + end-of-token child of the node a particle stands on
+    ids = torch.tensor(np.random.default_rng(5).integers(0, N, size=(B, Ks)), dtype=torch.int32, device=dev)
+    for i in range(3):
+        trie.batch_weight_sum_max_at(host_sets[i % 2], ids)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(E):
+        s_at, m_at = trie.batch_weight_sum_max_at(host_sets[i % 2], ids)
+        _ = float(s_at[0, 0]) + float(m_at[B - 1, Ks - 1])
+    torch.cuda.synchronize()
+    sparse_s = max_over_ranks(time.perf_counter() - t0)
     clocks.loaded = False
     barrier()
     clocks.stop()
@@ -437,6 +450,12 @@ def run_ours(args):
             "value": world * B * E / e2e_s, "unit": UNIT, "h2d_bytes_per_step": B * V * 4,
             "d2h_bytes_per_step": 2 * B * N * 4, "steps": E,
             "api": "ParallelTokenCharacterTrie.batch_weight_sum_max(pinned host tensor) -> numpy",
+        },
+        "e2e_sparse_readout": {
+            "value": world * B * E / sparse_s, "unit": UNIT, "nodes_read_per_row": Ks, "h2d_bytes_per_step": B * V * 4,
+            "d2h_bytes_per_step": 2 * B * Ks * 4, "steps": E,
+            "api": "ParallelTokenCharacterTrie.batch_weight_sum_max_at(pinned host tensor, node_ids) -> numpy [B, K] x 2",
+            "note": "not the headline: same kernels, results read through gt_gather_nodes instead of copying the [B, N] slabs",
         },
         "gpu_launches": launches_per_step * K,
         "roofline": {

@@ -138,6 +138,17 @@ class ParallelTokenCharacterTrie(TokenCharacterTrie):
         sums = self.batch_weight_sum_tensor(ws, log_input=log_input)
         return self.gather_nodes(sums, node_ids, normalizer=normalizer, log=log).cpu().numpy()
 
+    def batch_weight_sum_max_at(self, ws, node_ids, normalizer=None, log=False, log_input=False):
+        """Both reductions from one staging pass, read out at ``node_ids``: ``(sums, maxes)`` as ``[B, K]`` float32
+        numpy arrays (``normalizer`` applies to the sums only)."""
+        ws = self._as_batch(ws)
+        if not ws.is_cuda:
+            ws = ws.to(torch.device("cuda", self._device_list()[0]), non_blocking=True)
+        sums, maxes = self._engine.reduce(ws, ("sum", "max"), log_input=log_input)
+        out_s = self.gather_nodes(sums, node_ids, normalizer=normalizer, log=log)
+        out_m = self.gather_nodes(maxes, node_ids, log=log)
+        return out_s.cpu().numpy(), out_m.cpu().numpy()
+
     def batch_weight_max_at(self, ws, node_ids, log=False, log_input=False):
         """``batch_weight_max(ws)[b, node_ids[b, k]]`` as a ``[B, K]`` float32 numpy array."""
         maxes = self.batch_weight_max_tensor(ws, log_input=log_input)

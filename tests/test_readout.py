@@ -154,3 +154,15 @@ def test_batch_weight_at_equals_full_slab():
     kids = torch.tensor(trie.jump[trie.root])
     cond = trie.batch_weight_sum_at(ws, kids, normalizer=trie.root)
     np.testing.assert_allclose(cond.sum(axis=1), 1.0, rtol=1e-5)
+
+
+@pytest.mark.gpu
+def test_batch_weight_sum_max_at_one_pass():
+    g = load_golden("synth3000")
+    dec = tokens(unflat(g["blob"], g["lens"]))
+    trie = ParallelTokenCharacterTrie(dec)
+    ws = torch.tensor(dirichlet_rows(9, len(dec), alpha=0.3, seed=8))
+    ids = torch.tensor(np.random.default_rng(2).integers(0, len(trie), size=(9, 33)))
+    s_at, m_at = trie.batch_weight_sum_max_at(ws, ids)
+    assert np.array_equal(s_at, np.take_along_axis(trie.batch_weight_sum(ws), ids.numpy(), axis=1))
+    assert np.array_equal(m_at, np.take_along_axis(trie.batch_weight_max(ws), ids.numpy(), axis=1))
