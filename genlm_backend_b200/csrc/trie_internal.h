@@ -66,7 +66,7 @@ struct Plan {
     // phase 1 (permute): per segment s, records of 4 staged elements.
     //   p1_chunk_ptr[s] .. p1_chunk_ptr[s+1] : record index range of segment s
     //   p1_rec[c] = {zoff, src01, src23, 0}: zoff = offset (floats, multiple of 4) inside a staged row,
-    //   src* = two uint16 positions inside the segment each (0xFFFF = padding)
+    //   src* = two uint16 positions inside the segment each (padding elements: position 0)
     std::vector<int32_t> p1_chunk_ptr;  // [NS+1]
     std::vector<int32_t> p1_rec;        // [4 * n_records]
 

@@ -394,8 +394,9 @@ template <int OFF> struct EmitStore<OFF, double, 2> {
 // -- balance is to the row, not to the row group -- and walks it in groups of up to RP rows of one segment, so the
 // segment's records stay in shared memory across consecutive groups and each record read serves RP rows.  Rows land
 // in shared memory in their input type (NST stages); conversion / exp happens in the gather.
-constexpr int kPermPad = 16;  // bytes after every staged row; they hold zeros, which is what padding records read
-template <typename VT, typename IN_T, int RP, int NST, bool LOG>
+constexpr int kPermPad = 16;  // slack after every staged row: a row segment lands at its 16-byte phase in global memory
+// ALIGNED: every row segment starts and ends on a 16-byte boundary (the common case; no phase, no tail).
+template <typename VT, typename IN_T, int RP, int NST, bool LOG, bool ALIGNED>
 __global__ void __launch_bounds__(kThreads, 2) permute_bulk_kernel(PlanView P, const IN_T* __restrict__ ws, int64_t ld_ws,
                                                                    VT* __restrict__ z, int n_rows) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -421,12 +422,33 @@ __global__ void __launch_bounds__(kThreads, 2) permute_bulk_kernel(PlanView P, c
         gn = (int)min((int64_t)min(RP, n_rows - grow), u1 - u);
     };
     auto seg_len = [&](int sg) { return (int)min((int64_t)Q, P.V - (int64_t)sg * Q); };
+    // A bulk copy wants 16-byte aligned addresses and sizes on both sides, rows need not have them (an odd vocabulary
+    // size shifts every row): the copy covers the aligned span around the segment, and the segment's first element
+    // lands `phase` bytes into the staged row.  The span ends at most 15 bytes past the segment, inside the same row or
+    // the next one -- except for the very last segment of the batch, whose bulk copy stops at the last whole 16 bytes
+    // and whose tail elements are loaded one by one (tail fix-up below).
+    auto row_ptr = [&](int sg, int r) { return ws + (size_t)r * ld_ws + (size_t)sg * Q; };
+    auto phase_bytes = [&](int sg, int r) { return ALIGNED ? 0u : (unsigned)(reinterpret_cast<uintptr_t>(row_ptr(sg, r)) & 15u); };
+    auto is_batch_end = [&](int sg, int r) { return !ALIGNED && r == n_rows - 1 && sg == P.NS - 1; };
     auto fetch_rows = [&](int sg, int row, int n, int st) {  // thread 0
-        const unsigned bytes = (unsigned)seg_len(sg) * (unsigned)sizeof(IN_T);
         if (dbg == 22) { mbar_expect_tx(full + st, 0); return; }
-        mbar_expect_tx(full + st, (unsigned)n * bytes);
+        if constexpr (ALIGNED) {
+            const unsigned bytes = (unsigned)seg_len(sg) * (unsigned)sizeof(IN_T);
+            mbar_expect_tx(full + st, (unsigned)n * bytes);
+            for (int r = 0; r < n; ++r) bulk_g2s(stage + ((size_t)st * RP + r) * pitch, row_ptr(sg, row + r), bytes, full + st);
+            return;
+        }
+        unsigned span[RP], total = 0;
+        for (int r = 0; r < n; ++r) {
+            const unsigned need = phase_bytes(sg, row + r) + (unsigned)seg_len(sg) * (unsigned)sizeof(IN_T);
+            span[r] = is_batch_end(sg, row + r) ? (need & ~15u) : ((need + 15u) & ~15u);
+            total += span[r];
+        }
+        mbar_expect_tx(full + st, total);
         for (int r = 0; r < n; ++r)
-            bulk_g2s(stage + ((size_t)st * RP + r) * pitch, ws + (size_t)(row + r) * ld_ws + (size_t)sg * Q, bytes, full + st);
+            if (span[r])
+                bulk_g2s(stage + ((size_t)st * RP + r) * pitch,
+                         reinterpret_cast<const unsigned char*>(row_ptr(sg, row + r)) - phase_bytes(sg, row + r), span[r], full + st);
     };
     auto fetch_recs = [&](int c0, int c1) {  // thread 0
         mbar_expect_tx(rec_bar, (unsigned)(c1 - c0) * 16u);
@@ -442,9 +464,6 @@ __global__ void __launch_bounds__(kThreads, 2) permute_bulk_kernel(PlanView P, c
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         fetch_recs(c0, c1);  // plan metadata: may run ahead of the previous kernel's completion
     }
-    // Padding records carry position 0xFFFF, clamped to Q below: element Q of every staged row is a zero that no
-    // row fetch overwrites (a short last segment leaves stale row data below Q, which no record refers to).
-    if (tid < NST * RP * kPadElems) stage[(size_t)(tid / kPadElems) * pitch + Q + tid % kPadElems] = IN_T(0);
     pdl_wait();  // the previous call's tile kernel may still be reading z; ws may come from a kernel of the caller
     // the thread that issues the fetches runs NST-1 groups ahead
     int64_t fu = u0;
@@ -475,44 +494,36 @@ __global__ void __launch_bounds__(kThreads, 2) permute_bulk_kernel(PlanView P, c
         if (new_seg) { mbar_wait(rec_bar, par_rec); par_rec ^= 1u; }
         mbar_wait(full + st, (unsigned)(k / NST) & 1u);
 
-        const IN_T* sr0 = stage + (size_t)st * RP * pitch;
+        IN_T* sr0 = stage + (size_t)st * RP * pitch;
+        if (is_batch_end(s, row + n - 1) && dbg != 22) {  // tail fix-up: once per launch, in one CTA
+            const unsigned ph = phase_bytes(s, row + n - 1), need = ph + (unsigned)seg_len(s) * (unsigned)sizeof(IN_T);
+            const int count = (int)((need & 15u) / sizeof(IN_T));           // elements past the last whole 16 bytes
+            const int first = seg_len(s) - count;                           // ... and where they start in the segment
+            if (tid < count) sr0[(size_t)(n - 1) * pitch + ph / sizeof(IN_T) + first + tid] = row_ptr(s, row + n - 1)[first + tid];
+            __syncthreads();
+        }
         const int nrec = dbg == 21 ? 0 : c1 - c0;
-#ifndef GT_PB_FAT
         VT* zr[RP];
+        const IN_T* sr[RP];
 #pragma unroll
-        for (int r = 0; r < RP; ++r) zr[r] = z + (size_t)(row + r) * P.Zrow;
-        const unsigned uq = (unsigned)Q;
+        for (int r = 0; r < RP; ++r) {
+            const int rr = row + min(r, n - 1);
+            zr[r] = z + (size_t)rr * P.Zrow;
+            sr[r] = sr0 + (size_t)min(r, n - 1) * pitch + phase_bytes(s, rr) / sizeof(IN_T);
+        }
+        // Padding positions of a record carry source position 0: what lands in z there goes to a trash slot of the
+        // tile kernel and is never read, so no position needs a check.
         for (int i = tid; i < nrec; i += kThreads) {
             const int4 rec = s_rec[i];
-            const unsigned p0 = min((unsigned)rec.y & 0xFFFFu, uq), p1 = min((unsigned)rec.y >> 16, uq);
-            const unsigned p2 = min((unsigned)rec.z & 0xFFFFu, uq), p3 = min((unsigned)rec.z >> 16, uq);
+            const unsigned p0 = (unsigned)rec.y & 0xFFFFu, p1 = (unsigned)rec.y >> 16;
+            const unsigned p2 = (unsigned)rec.z & 0xFFFFu, p3 = (unsigned)rec.z >> 16;
 #pragma unroll
             for (int r = 0; r < RP; ++r) {
-                if (r < n) {
-                    const IN_T* sr = sr0 + (size_t)r * pitch;
-                    store4<VT>(zr[r] + rec.x, convert_in<VT, IN_T>(sr[p0], LOG), convert_in<VT, IN_T>(sr[p1], LOG),
-                               convert_in<VT, IN_T>(sr[p2], LOG), convert_in<VT, IN_T>(sr[p3], LOG));
-                }
+                if (r < n)
+                    store4<VT>(zr[r] + rec.x, convert_in<VT, IN_T>(sr[r][p0], LOG), convert_in<VT, IN_T>(sr[r][p1], LOG),
+                               convert_in<VT, IN_T>(sr[r][p2], LOG), convert_in<VT, IN_T>(sr[r][p3], LOG));
             }
         }
-#else
-        for (int i = tid; i < nrec; i += kThreads) {
-            const int4 rec = s_rec[i];
-            const unsigned s0 = (unsigned)rec.y & 0xFFFFu, s1 = (unsigned)rec.y >> 16;
-            const unsigned s2 = (unsigned)rec.z & 0xFFFFu, s3 = (unsigned)rec.z >> 16;
-#pragma unroll
-            for (int r = 0; r < RP; ++r) {
-                if (r < n) {
-                    const IN_T* sr = sr0 + (size_t)r * pitch;
-                    const VT a = s0 != 0xFFFFu ? convert_in<VT, IN_T>(sr[s0], LOG) : VT(0);
-                    const VT b = s1 != 0xFFFFu ? convert_in<VT, IN_T>(sr[s1], LOG) : VT(0);
-                    const VT c = s2 != 0xFFFFu ? convert_in<VT, IN_T>(sr[s2], LOG) : VT(0);
-                    const VT d = s3 != 0xFFFFu ? convert_in<VT, IN_T>(sr[s3], LOG) : VT(0);
-                    store4<VT>(z + (size_t)(row + r) * P.Zrow + rec.x, a, b, c, d);
-                }
-            }
-        }
-#endif
         __syncthreads();  // this stage (and, on a segment change, the record buffer) may be overwritten
         new_seg = has_next && sn != s;
         if (new_seg) {
@@ -1241,28 +1252,33 @@ static int sm_count() {
 template <typename IN_T, int RP, int NST> static size_t permute_bulk_smem(const PlanView& v) {
     return (size_t)NST * RP * (v.Q * sizeof(IN_T) + kPermPad) + (size_t)v.max_seg_recs * 16 + 8 * (NST + 1);
 }
-// rows must be 16-byte aligned segment by segment for the copy engine
+// the copy engine moves whole 16-byte units: elements must be naturally aligned and a segment a whole number of units
 template <typename IN_T> static bool permute_bulk_ok(const PlanView& v, const void* ws, int64_t ld_ws) {
-    return (reinterpret_cast<uintptr_t>(ws) & 15) == 0 && ((ld_ws * (int64_t)sizeof(IN_T)) & 15) == 0 &&
-           ((v.V * (int64_t)sizeof(IN_T)) & 15) == 0 && (((int64_t)v.Q * (int64_t)sizeof(IN_T)) & 15) == 0;
+    (void)ld_ws;
+    return (reinterpret_cast<uintptr_t>(ws) % sizeof(IN_T)) == 0 && (((int64_t)v.Q * (int64_t)sizeof(IN_T)) & 15) == 0;
 }
-template <typename VT, typename IN_T, int RP, int NST, bool LOG>
-static int launch_permute_bulk_lg(const PlanView& v, const void* ws, int64_t ld_ws, const Scratch<VT>& sc, int rows, cudaStream_t st) {
+template <typename VT, typename IN_T, int RP, int NST, bool LOG, bool ALIGNED>
+static int launch_permute_bulk_la(const PlanView& v, const void* ws, int64_t ld_ws, const Scratch<VT>& sc, int rows, cudaStream_t st) {
     const size_t smem = permute_bulk_smem<IN_T, RP, NST>(v);
-    GT_CUDA(allow_smem(permute_bulk_kernel<VT, IN_T, RP, NST, LOG>, smem));
+    GT_CUDA(allow_smem(permute_bulk_kernel<VT, IN_T, RP, NST, LOG, ALIGNED>, smem));
     // one CTA per resident slot; each takes an equal share of the (segment, row) pairs, at least RP of them
     const int64_t groups = ((int64_t)v.NS * rows + RP - 1) / RP;
-    const int slots = sm_count() * resident_ctas(reinterpret_cast<const void*>(permute_bulk_kernel<VT, IN_T, RP, NST, LOG>), kThreads, smem);
+    const int slots = sm_count() * resident_ctas(reinterpret_cast<const void*>(permute_bulk_kernel<VT, IN_T, RP, NST, LOG, ALIGNED>), kThreads, smem);
     const unsigned grid = (unsigned)std::min<int64_t>(groups, slots);
-    GT_CUDA(launch_pdl(permute_bulk_kernel<VT, IN_T, RP, NST, LOG>, dim3(grid), dim3(kThreads), smem, st, v, static_cast<const IN_T*>(ws),
-                       ld_ws, sc.z, rows));
+    GT_CUDA(launch_pdl(permute_bulk_kernel<VT, IN_T, RP, NST, LOG, ALIGNED>, dim3(grid), dim3(kThreads), smem, st, v,
+                       static_cast<const IN_T*>(ws), ld_ws, sc.z, rows));
     return GT_OK;
 }
 template <typename VT, typename IN_T, int RP, int NST>
 static int launch_permute_bulk(const PlanView& v, const void* ws, int64_t ld_ws, const Scratch<VT>& sc, int rows,
                                bool log_input, cudaStream_t st) {
-    return log_input ? launch_permute_bulk_lg<VT, IN_T, RP, NST, true>(v, ws, ld_ws, sc, rows, st)
-                     : launch_permute_bulk_lg<VT, IN_T, RP, NST, false>(v, ws, ld_ws, sc, rows, st);
+    const bool aligned = (reinterpret_cast<uintptr_t>(ws) & 15) == 0 && ((ld_ws * (int64_t)sizeof(IN_T)) & 15) == 0 &&
+                         ((v.V * (int64_t)sizeof(IN_T)) & 15) == 0;
+    if (aligned)
+        return log_input ? launch_permute_bulk_la<VT, IN_T, RP, NST, true, true>(v, ws, ld_ws, sc, rows, st)
+                         : launch_permute_bulk_la<VT, IN_T, RP, NST, false, true>(v, ws, ld_ws, sc, rows, st);
+    return log_input ? launch_permute_bulk_la<VT, IN_T, RP, NST, true, false>(v, ws, ld_ws, sc, rows, st)
+                     : launch_permute_bulk_la<VT, IN_T, RP, NST, false, false>(v, ws, ld_ws, sc, rows, st);
 }
 
 template <typename VT, typename IN_T, int R>

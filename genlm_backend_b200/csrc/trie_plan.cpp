@@ -69,7 +69,9 @@ int build_plan(const Layout& L, int32_t T, int32_t Q, int32_t R, Plan& P) {
 
     constexpr uint16_t kPadSlot = 0xFFC0;  // kPadSlot + c: padding element bound for trash slot c (resolved below)
     P.p2_slot.assign((size_t)z, kPadSlot);
-    std::vector<uint16_t> z_src((size_t)z, 0xFFFF);  // position inside the source segment
+    // position inside the source segment; padding elements name position 0 (any valid one would do: what the permute
+    // kernel writes for them lands in a trash slot of the tile kernel)
+    std::vector<uint16_t> z_src((size_t)z, 0);
     {
         // Order inside a run is free (both kernels follow these tables), and so is the place of a run's padding.
         // The tile kernel scatters staged quad q with lane q: for e = 0..3 the lanes of one shared-memory wavefront

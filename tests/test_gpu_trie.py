@@ -276,3 +276,28 @@ def test_async_autobatch_1024_requests_full_size():
         assert np.array_equal(maxes[i], wm[i])
     for i in range(64):
         assert float(maxes[i][trie.root]) == float(ws[i].max())
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16, torch.bfloat16, torch.float64])
+@pytest.mark.parametrize("V", [5003, 4097, 12289])
+def test_rows_of_any_alignment(V, dtype):
+    """Row starts that are not 16-byte aligned (odd vocabulary sizes, column-offset views, 2- / 4- / 8-byte elements):
+    the bulk-copy permute fetches the aligned span around each segment and fixes up the batch's last elements."""
+    trie = ParallelTokenCharacterTrie(synth_vocab(V, seed=V % 13))
+    o = oracle_for(trie)
+    B = 7
+    base = dirichlet_rows(B, V + 9, alpha=0.3, seed=V % 7)
+    for off in (0, 1, 3, 6):  # first element of row 0 at byte offset off * itemsize of a 512-byte aligned buffer
+        wide = torch.tensor(base).to(dtype).cuda()
+        view = wide[:, off:off + V]
+        assert view.stride(0) == V + 9
+        back = view.to(torch.float64).cpu().numpy()
+        hs, hm = trie.batch_weight_tensor(view, ops=("sum", "max"))
+        r, z = rel_err(hs.cpu().numpy(), o.weight_sum(back))
+        assert r <= SUM_RTOL and z == 0.0, (off, r, z)
+        assert np.array_equal(hm.cpu().numpy(), o.weight_max(back).astype(np.float32)), off
+        # a batch that ends exactly at the end of its allocation: the last segment's tail is loaded element by element
+        tight = view.contiguous()[1:].clone()
+        hs2 = trie.batch_weight_sum_tensor(tight)
+        r, z = rel_err(hs2.cpu().numpy(), o.weight_sum(back[1:]))
+        assert r <= SUM_RTOL and z == 0.0, (off, "tight", r, z)

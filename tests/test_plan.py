@@ -39,15 +39,20 @@ def test_plan_invariants():
     lay = trie._layout
     assert info["n_tiles"] == -(-V // T) and info["n_segs"] == -(-V // Q)
     assert info["staged_row_elems"] % 4 == 0 and info["staged_row_elems"] >= V
-    # staging is a permutation of the row (plus padding)
+    # staging is a permutation of the row plus padding; a padding element is one the tile kernel sends to a trash slot
+    # (past the value array), whatever source position its record names
     rec, cptr = eng.plan_array("p1_rec").reshape(-1, 4), eng.plan_array("p1_chunk_ptr")
     zoff = rec[:, 0]
+    p2 = eng.plan_array("p2_slot").astype(np.int64)
     seen = np.zeros(V, dtype=np.int64)
     for s in range(info["n_segs"]):
-        lohi = rec[cptr[s]:cptr[s + 1], 1:3].astype(np.int64) & 0xFFFFFFFF
+        r = rec[cptr[s]:cptr[s + 1]]
+        lohi = r[:, 1:3].astype(np.int64) & 0xFFFFFFFF
         e = np.stack([lohi[:, 0] & 0xFFFF, lohi[:, 0] >> 16, lohi[:, 1] & 0xFFFF, lohi[:, 1] >> 16], axis=1).reshape(-1)
-        e = e[e != 0xFFFF] + s * Q
-        np.add.at(seen, e, 1)
+        dst = (r[:, 0].astype(np.int64)[:, None] + np.arange(4)[None, :]).reshape(-1)
+        real = p2[dst] < info["max_tile_values"]
+        assert (e < min(Q, V - s * Q)).all()  # every named position, padding included, lies inside the segment
+        np.add.at(seen, e[real] + s * Q, 1)
     assert (seen == 1).all()
     assert len(np.unique(zoff)) == len(zoff) and (zoff % 4 == 0).all()
     # node intervals partition the id space; spanning nodes are exactly those without a slot

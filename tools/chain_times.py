@@ -14,7 +14,7 @@ import torch
 from genlm_backend_b200 import ParallelTokenCharacterTrie, _lib
 from genlm_backend_b200.synthetic import synth_vocab, dirichlet_rows
 
-V = 128256
+V = int(os.environ.get("GT_VOCAB", "128256"))
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 trie = ParallelTokenCharacterTrie(synth_vocab(V))
 eng = trie._engine
