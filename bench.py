@@ -334,25 +334,26 @@ def run_ours(args):
 
     # per-kernel timing for the roofline (one op, one phase at a time), same buffers ----------------------------------
     def time_phase(phases, ops, iters):
-        """Average device time of one launch group, replayed from a CUDA graph that holds one launch per buffer set
-        (so host launch overhead never limits the rate of short kernels)."""
+        """Average device time of one launch group, replayed from a CUDA graph that holds 16 launches rotating over the
+        buffer sets (so host launch overhead never limits the rate of short kernels)."""
         for i in range(3):
             step(i % nsets, phases, ops)
         torch.cuda.synchronize()
+        per_graph = 4 * nsets  # launches per graph: the per-replay launch bubble (~1 us) is spread over 16 launches
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
-            for k in range(nsets):
-                step(k, phases, ops)
+            for k in range(per_graph):
+                step(k % nsets, phases, ops)
         g.replay()
         torch.cuda.synchronize()
-        reps = max(1, iters // nsets)
+        reps = max(2, iters // per_graph)
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
         for _ in range(reps):
             g.replay()
         b.record()
         torch.cuda.synchronize()
-        return a.elapsed_time(b) / (reps * nsets)
+        return a.elapsed_time(b) / (reps * per_graph)
 
     clocks.loaded = True
     iters = max(50, min(K, 400))
