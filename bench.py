@@ -286,8 +286,8 @@ def run_ours(args):
         step(i % nsets)
     torch.cuda.synchronize()
 
-    # The timed loop replays CUDA graphs: one graph holds one step per buffer set (back-to-back steps of a stream, as a
-    # serving loop issues them), single-step graphs cover the remainder so that exactly K steps run.
+    # The timed loop replays CUDA graphs: one graph holds 16 steps rotating over the buffer sets (back-to-back steps of a
+    # stream, as a serving loop issues them), single-step graphs cover the remainder so that exactly K steps run.
     graphs = None
     if not args.no_graph:
         graphs = []
@@ -296,10 +296,11 @@ def run_ours(args):
             with torch.cuda.graph(g):
                 step(k)
             graphs.append(g)
+        per_multi = 4 * nsets
         multi = torch.cuda.CUDAGraph()
         with torch.cuda.graph(multi):
-            for k in range(nsets):
-                step(k)
+            for k in range(per_multi):
+                step(k % nsets)
         for k in range(nsets):
             graphs[k].replay()
         multi.replay()
@@ -311,10 +312,10 @@ def run_ours(args):
             for i in range(n):
                 step(i % nsets)
             return
-        for _ in range(n // nsets):
+        for _ in range(n // per_multi):
             multi.replay()
-        for i in range(n % nsets):
-            graphs[i].replay()
+        for i in range(n % per_multi):
+            graphs[i % nsets].replay()
 
     clocks = ClockSampler(local_rank)
     clocks.start()
@@ -444,7 +445,7 @@ def run_ours(args):
             "parallelism": f"rows sharded, {world} independent GPU(s), no collective",
             "l2_policy": f"rotating {nsets} buffer sets of {set_bytes / 1e6:.0f} MB ({nsets * set_bytes / 1e6:.0f} MB total) "
                          f"vs L2 {l2_bytes / 1e6:.0f} MB",
-            "launch": f"CUDA graphs of {nsets} consecutive steps (one per buffer set), single-step graphs for the remainder" if graphs is not None else "direct launches",
+            "launch": f"CUDA graphs of {4 * nsets} consecutive steps rotating over the {nsets} buffer sets, single-step graphs for the remainder" if graphs is not None else "direct launches",
             "tile_leaves": info["tile_leaves"], "seg_positions": info["seg_positions"], "n_span": info["n_span"],
         },
         "e2e": {
