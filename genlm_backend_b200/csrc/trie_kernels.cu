@@ -1351,7 +1351,7 @@ static int reduce_typed(const PlanView& v, const void* ws, int in_type, int64_t 
             // rows per CTA in the permute phase: R unless the segment buffer would not fit in shared memory
             constexpr int RP = sizeof(VT) == 4 ? 2 : 1;  // rows per CTA of the permute kernel
             const bool wide = permute_smem<VT, RP>(v) <= kMaxSmem;
-            const bool use_bulk = getenv("GT_NO_BULK_PERMUTE") == nullptr;
+            static const bool use_bulk = getenv("GT_NO_BULK_PERMUTE") == nullptr;  // read once: not on the launch path
 #ifndef GT_PB_RP
 #define GT_PB_RP 2
 #endif

@@ -5,6 +5,7 @@ PyTorch is used for device memory, streams and host<->device copies only; every 
 hand-written kernels behind the C ABI (``csrc/trie_kernels.cu``).  There is no CPU path.
 """
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -22,8 +23,6 @@ _OUT_TYPES = {torch.float32: _lib.GT_F32, torch.float64: _lib.GT_F64}
 OPS = {"sum": _lib.GT_OP_SUM, "max": _lib.GT_OP_MAX}
 
 # rows whose staging scratch we keep per stream slot (the C side chunks larger batches itself)
-import os
-
 _WORKSPACE_ROWS = int(os.environ.get("GT_WORKSPACE_ROWS", "64"))  # 64 rows of staging (35 MB) stay L2-resident between the kernels
 
 
