@@ -55,6 +55,14 @@ inline int32_t swizzle_slot(int32_t s, int32_t slot_bytes) {
 constexpr int kPyramidTop = GT_PYR_TOP;
 static_assert(kPyramidTop == 7 || kPyramidTop == 8, "pyramid top level must be 7 or 8");
 
+// Term rows of an ELL chunk are padded (with the identity slot) to a multiple of this.  2: the kernel adds terms four
+// at a time and finishes with one pair; 4 wasted a third of all term rows, since most chunks hold two-term ranges.
+#ifndef GT_ELL_ROW_PAD
+#define GT_ELL_ROW_PAD 2
+#endif
+constexpr int kEllRowPad = GT_ELL_ROW_PAD;
+static_assert(kEllRowPad == 2 || kEllRowPad == 4, "ELL term rows are padded to pairs or quads");
+
 struct Plan {
     int32_t T = 0, Q = 0, NT = 0, NS = 0;
     int32_t R = 0;           // rows per CTA of the fp32 pipeline (the fp64 pipeline uses R/2: same slot size)

@@ -717,7 +717,7 @@ __device__ __forceinline__ void phase_pyramid(VT* vals, int T, int warp, int lan
 }
 
 // 3. ranges that need more than one block: ELL chunks of 32 ranges, one warp per chunk, term rows read from shared
-//    memory (k is a multiple of 4: the planner pads rows with the identity slot).  Chunks are sorted by descending
+//    memory (k is a multiple of kEllRowPad: the planner pads rows with the identity slot).  Chunks are sorted by descending
 //    term count: rounds alternate direction so that the warps that drew the longest chunks of one round draw the
 //    shortest of the next.
 template <typename VT, int R, int OP, int NWARPS>
@@ -748,12 +748,16 @@ __device__ __forceinline__ void phase_ell(VT* vals, const uint16_t* s_terms, con
             acc = RV::template combine<OP>(acc, v[0]);
         }
 #endif
-        for (; kb < d.y; kb += 4) {
+        for (; kb + 4 <= d.y; kb += 4) {
             int sl[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) sl[e] = tp[(kb + e) * 32];
 #pragma unroll
             for (int e = 0; e < 4; ++e) acc = RV::template combine<OP>(acc, RV::load(vals + sl[e] * R));
+        }
+        if (kb < d.y) {  // term rows come in pairs (kEllRowPad = 2): most chunks of a tile hold two-term ranges only
+            const int s0 = tp[kb * 32], s1 = tp[(kb + 1) * 32];
+            acc = RV::template combine<OP>(acc, RV::template combine<OP>(RV::load(vals + s0 * R), RV::load(vals + s1 * R)));
         }
         acc.store(vals + (2 * T + c * 32 + lane) * R);
     }

@@ -296,7 +296,7 @@ int build_plan(const Layout& L, int32_t T, int32_t Q, int32_t R, Plan& P) {
             int32_t k_real = 0;
             for (size_t lane = 0; lane < 32; ++lane)
                 if (placed[j0 + lane] >= 0) k_real = std::max<int32_t>(k_real, (int32_t)m[(size_t)placed[j0 + lane]].terms.size());
-            const int32_t k = (k_real + 3) & ~3;  // whole batches of 4 term rows; the padding reads the identity slot
+            const int32_t k = (k_real + kEllRowPad - 1) & ~(kEllRowPad - 1);  // the padding reads the identity slot
             P.ell_desc.push_back((int32_t)(P.ell_terms.size() / 32));
             P.ell_desc.push_back(k);
             // The order in which a range adds its terms is free, and a range with fewer terms than the chunk has rows
