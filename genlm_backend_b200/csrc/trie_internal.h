@@ -55,13 +55,14 @@ inline int32_t swizzle_slot(int32_t s, int32_t slot_bytes) {
 constexpr int kPyramidTop = GT_PYR_TOP;
 static_assert(kPyramidTop == 7 || kPyramidTop == 8, "pyramid top level must be 7 or 8");
 
-// Term rows of an ELL chunk are padded (with the identity slot) to a multiple of this.  2: the kernel adds terms four
-// at a time and finishes with one pair; 4 wasted a third of all term rows, since most chunks hold two-term ranges.
+// Term rows of an ELL chunk are padded (with the identity slot) to a multiple of this.  The kernel adds terms four at a
+// time and finishes with a pair and / or a single term.  Measured on B200 (tile kernel, 64 rows, both reductions):
+// 4 -> 46.75 us (a third of all term rows were padding: most chunks hold two- and three-term ranges), 2 -> 46.1, 1 -> 45.9.
 #ifndef GT_ELL_ROW_PAD
-#define GT_ELL_ROW_PAD 2
+#define GT_ELL_ROW_PAD 1
 #endif
 constexpr int kEllRowPad = GT_ELL_ROW_PAD;
-static_assert(kEllRowPad == 2 || kEllRowPad == 4, "ELL term rows are padded to pairs or quads");
+static_assert(kEllRowPad == 1 || kEllRowPad == 2 || kEllRowPad == 4, "ELL term rows: unpadded, or padded to pairs or quads");
 
 struct Plan {
     int32_t T = 0, Q = 0, NT = 0, NS = 0;

@@ -755,10 +755,19 @@ __device__ __forceinline__ void phase_ell(VT* vals, const uint16_t* s_terms, con
 #pragma unroll
             for (int e = 0; e < 4; ++e) acc = RV::template combine<OP>(acc, RV::load(vals + sl[e] * R));
         }
+#if GT_ELL_ROW_PAD == 1
+        if (kb + 2 <= d.y) {  // no padding rows at all: a pair, then a single term
+            const int s0 = tp[kb * 32], s1 = tp[(kb + 1) * 32];
+            acc = RV::template combine<OP>(acc, RV::template combine<OP>(RV::load(vals + s0 * R), RV::load(vals + s1 * R)));
+            kb += 2;
+        }
+        if (kb < d.y) acc = RV::template combine<OP>(acc, RV::load(vals + (int)tp[kb * 32] * R));
+#else
         if (kb < d.y) {  // term rows come in pairs (kEllRowPad = 2): most chunks of a tile hold two-term ranges only
             const int s0 = tp[kb * 32], s1 = tp[(kb + 1) * 32];
             acc = RV::template combine<OP>(acc, RV::template combine<OP>(RV::load(vals + s0 * R), RV::load(vals + s1 * R)));
         }
+#endif
         acc.store(vals + (2 * T + c * 32 + lane) * R);
     }
 }

@@ -74,7 +74,7 @@ def test_plan_invariants():
     terms = eng.plan_array("ell_terms")
     assert terms.max() <= 2 * T - 1 and (terms != ident).sum() > 0
     rows = eng.plan_array("ell_row_ptr")
-    assert rows[0] == 0 and rows[-1] * 32 == len(terms) and (eng.plan_array("ell_desc").reshape(-1, 2)[:, 1] % 2 == 0).all()
+    assert rows[0] == 0 and rows[-1] * 32 == len(terms) and (eng.plan_array("ell_desc").reshape(-1, 2)[:, 1] > 0).all()
 
 
 def test_plan_parameter_validation():
