@@ -182,8 +182,9 @@ class ClockSampler(threading.Thread):
 
 # ---- secondary measurement: the SMC row op (BASELINE.json configs[3], per-GPU share) ---------------------------------
 def sampler_metrics(dev, vocab, peak, rows=512, iters=20):
-    """Fused masked logsumexp + categorical draw over `rows` x `vocab` fp32 log-probabilities with a per-row bool mask
-    (one particle per row).  Device time from a CUDA graph rotating over two logit buffers larger than L2."""
+    """Fused masked logsumexp + categorical draw over `rows` x `vocab` fp32 log-probabilities (one particle per row) for
+    the mask kinds an SMC step uses.  Device time from a CUDA graph of 8 launches rotating over two logit buffers that
+    are larger than L2 together."""
     import torch
 
     from genlm_backend_b200 import smc
@@ -192,15 +193,25 @@ def sampler_metrics(dev, vocab, peak, rows=512, iters=20):
     sets = [torch.log_softmax(torch.randn(rows, vocab, device=dev, generator=gen), dim=-1) for _ in range(2)]
     masks = [torch.rand(rows, vocab, device=dev, generator=gen) < 0.5 for _ in range(2)]
     out = {}
-    for name, mk in (("shared_f32_mask", lambda k: masks[0][0].float().log()), ("per_row_bool_mask", lambda k: masks[k])):
+
+    def pack_bits(keep):  # bool [B, V] -> int32 [B, ceil(V/32)] keep-bitmask (bit i of word w = element 32 w + i)
+        pad = (-keep.shape[-1]) % 32
+        k = torch.nn.functional.pad(keep, (0, pad)).view(keep.shape[0], -1, 32).to(torch.int64)
+        w = (k << torch.arange(32, device=keep.device, dtype=torch.int64)).sum(-1)
+        return torch.where(w >= 2**31, w - 2**32, w).to(torch.int32)
+
+    per_graph = 8
+    cases = (("no_mask", lambda k: None, 0), ("shared_f32_mask", lambda k: masks[0][0].float().log(), 0),
+             ("per_row_bit_mask", lambda k: pack_bits(masks[k]), 4 * ((vocab + 31) // 32)), ("per_row_bool_mask", lambda k: masks[k], vocab))
+    for name, mk, mask_bytes in cases:
         ms_ = [mk(0), mk(1)]
         for i in range(3):
             smc.masked_logsumexp_sample(sets[i % 2], ms_[i % 2], seed=i)
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
-            for k in range(2):
-                smc.masked_logsumexp_sample(sets[k], ms_[k], seed=k)
+            for k in range(per_graph):
+                smc.masked_logsumexp_sample(sets[k % 2], ms_[k % 2], seed=k)
         g.replay()
         torch.cuda.synchronize()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -209,12 +220,12 @@ def sampler_metrics(dev, vocab, peak, rows=512, iters=20):
             g.replay()
         b.record()
         torch.cuda.synchronize()
-        sec = a.elapsed_time(b) / (2 * iters) / 1e3
-        bytes_per_row = 4 * vocab + (vocab if name == "per_row_bool_mask" else 0) + 8
+        sec = a.elapsed_time(b) / (per_graph * iters) / 1e3
+        bytes_per_row = 4 * vocab + mask_bytes + 8
         out[name] = {"rows_per_s": rows / sec, "us_per_launch": sec * 1e6, "achieved_GBps": rows * bytes_per_row / sec / 1e9,
                      "frac_of_hbm_peak": rows * bytes_per_row / sec / 1e9 / peak}
     return {"kernel": "lse_sample_kernel<float>", "rows": rows, "vocab": vocab, "bound": "hbm",
-            "bytes_per_row": "4V (+V for a per-row bool mask) + 8", **out}
+            "bytes_per_row": "4V (+ the bytes of a per-row mask: V/8 for bits, V for bools) + 8", **out}
 
 
 # ---- our arm -------------------------------------------------------------------------------------------------------
