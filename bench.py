@@ -290,7 +290,7 @@ def run_ours(args):
     def step(k, phases=0, ops=("sum", "max")):
         eng.reduce(ws_sets[k], ops, out_sum=sum_sets[k], out_max=max_sets[k], phases=phases)
 
-    launches_per_step = 2 + (1 if info["n_span"] > 0 else 0)  # permute + tile (both reductions) + span
+    launches_per_step = 1 + (1 if info["n_span"] > 0 else 0)  # fused mass kernel (both reductions) + span
 
     # warm-up (also sets kernel attributes, allocates the scratch) ------------------------------------------------
     for i in range(W):
@@ -457,7 +457,7 @@ def run_ours(args):
             "l2_policy": f"rotating {nsets} buffer sets of {set_bytes / 1e6:.0f} MB ({nsets * set_bytes / 1e6:.0f} MB total) "
                          f"vs L2 {l2_bytes / 1e6:.0f} MB",
             "launch": f"CUDA graphs of {4 * nsets} consecutive steps rotating over the {nsets} buffer sets, single-step graphs for the remainder" if graphs is not None else "direct launches",
-            "tile_leaves": info["tile_leaves"], "seg_positions": info["seg_positions"], "n_span": info["n_span"],
+            "tile_leaves": info["tile_leaves"], "n_span": info["n_span"],
         },
         "e2e": {
             "value": world * B * E / e2e_s, "unit": UNIT, "h2d_bytes_per_step": B * V * 4,

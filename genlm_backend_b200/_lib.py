@@ -22,10 +22,10 @@ GT_MASK_NONE, GT_MASK_ADD_F32, GT_MASK_BOOL_U8, GT_MASK_BITS_U32 = 0, 1, 2, 3
 class PlanInfo(ctypes.Structure):
     _fields_ = [
         ("n_tokens", c_int64), ("n_nodes", c_int64),
-        ("tile_leaves", c_int32), ("seg_positions", c_int32), ("n_tiles", c_int32), ("n_segs", c_int32),
-        ("rows_per_item", c_int32), ("n_span", c_int32), ("span_terms", c_int64),
-        ("max_levels", c_int32), ("max_tile_values", c_int32),
-        ("staged_row_elems", c_int64), ("meta_bytes", c_int64),
+        ("tile_leaves", c_int32), ("n_tiles", c_int32), ("rows_per_item", c_int32), ("permute_unit", c_int32),
+        ("n_span", c_int32), ("max_levels", c_int32), ("span_terms", c_int64),
+        ("max_tile_values", c_int32), ("reserved", c_int32),
+        ("staged_slots", c_int64), ("meta_bytes", c_int64),
     ]
 
 
@@ -44,7 +44,7 @@ SIGNATURES = {
     "gt_export_reachability": (c_int, [c_void_p, c_void_p, c_void_p]),
     "gt_upload": (c_int, [c_void_p, c_int]),
     "gt_get_plan_info": (c_int, [c_void_p, ctypes.POINTER(PlanInfo)]),
-    "gt_plan": (c_int, [c_void_p, c_int32, c_int32, c_int32]),
+    "gt_plan": (c_int, [c_void_p, c_int32]),
     "gt_export_plan_array": (c_int64, [c_void_p, c_char_p, c_void_p, c_int64, ctypes.POINTER(c_int32)]),
     "gt_debug_read_trace": (c_int64, [c_void_p, c_int, c_void_p, c_int64, c_void_p]),
     "gt_workspace_bytes": (c_size_t, [c_void_p, c_int64]),

@@ -29,9 +29,10 @@ struct Layout {
 
 // ---- tile plan (host copy; see trie_plan.cpp for how it is derived) -------------------------
 //
-// Source segments: vocabulary positions [s*Q, (s+1)*Q).   Tiles: DFS leaf ranks [t*T, (t+1)*T).
-// Staging buffer z (one row = Zrow floats, tile-major): tile t occupies [z_tile_off[t], z_tile_off[t+1]),
-// inside it one run per source segment (padded to 4 elements).
+// Tiles: DFS leaf ranks [t*T, (t+1)*T).  Staging buffer z (device scratch): one block per row group of R rows,
+// [NT][T] value slots of R elements each -- tile t's block is the leaf region of the tile's shared-memory value
+// array, byte for byte, so the tile kernel fetches it with one bulk copy.  leaf_dest[i] is the slot (in that
+// [NT*T] numbering, swizzled) that item i's weight goes to.
 // Shared-memory slot swizzle.  Slots below 2T (leaves + pyramid) are stored at swizzle_slot(s): the 16-byte
 // chunk index c is XORed with (c >> 3) & (slot_bytes/2 - 1), a bijection inside every aligned group of 8 chunks.
 // It makes "lane u touches slots 8u .. 8u+7" (the in-lane pyramid levels) and its strided level stores
@@ -65,24 +66,15 @@ constexpr int kEllRowPad = GT_ELL_ROW_PAD;
 static_assert(kEllRowPad == 1 || kEllRowPad == 2 || kEllRowPad == 4, "ELL term rows: unpadded, or padded to pairs or quads");
 
 struct Plan {
-    int32_t T = 0, Q = 0, NT = 0, NS = 0;
-    int32_t R = 0;           // rows per CTA of the fp32 pipeline (the fp64 pipeline uses R/2: same slot size)
+    int32_t T = 0, NT = 0;
+    int32_t R = 0;           // rows per work item of the fp32 pipeline (the fp64 pipeline uses R/2: same slot size)
     int32_t slot_bytes = 0;  // 4 * R
     int32_t max_tile_nodes = 0, max_tile_ell_rows = 0;  // sizes of the shared-memory metadata stages
-    int32_t max_tile_chunks = 0, max_tile_z = 0;        // ELL chunks / staged elements of the largest tile
-    int64_t Zrow = 0;  // floats per staged row (multiple of 4)
+    int32_t max_tile_chunks = 0;                        // ELL chunks of the largest tile
 
-    // phase 1 (permute): per segment s, records of 4 staged elements.
-    //   p1_chunk_ptr[s] .. p1_chunk_ptr[s+1] : record index range of segment s
-    //   p1_rec[c] = {zoff, src01, src23, 0}: zoff = offset (floats, multiple of 4) inside a staged row,
-    //   src* = two uint16 positions inside the segment each (padding elements: position 0)
-    std::vector<int32_t> p1_chunk_ptr;  // [NS+1]
-    std::vector<int32_t> p1_rec;        // [4 * n_records]
-
-    // phase 2 (tile): staged element i of tile t goes to value slot p2_slot[z_tile_off[t] + i]
-    // (uint16; 0xFFFF = padding).
-    std::vector<int32_t> z_tile_off;    // [NT+1]
-    std::vector<uint16_t> p2_slot;      // [Zrow]
+    // permute: item i's weight is stored at value slot leaf_dest[i] of its row group's staging block
+    // (= t * T + swizzled leaf slot inside tile t, t = DFS rank / T)
+    std::vector<int32_t> leaf_dest;     // [V]
 
     // per-tile value array: slots [0,T) leaves in DFS order, [T,2T-1) pyramid of aligned blocks (levels 1..8),
     // 2T-1 the identity element, [2T, ..) multi-term ranges.
@@ -127,5 +119,5 @@ struct gt_trie {
 
 namespace gt {
 // trie_plan.cpp
-int build_plan(const Layout& L, int32_t T, int32_t Q, int32_t R, Plan& P);
+int build_plan(const Layout& L, int32_t T, int32_t R, Plan& P);
 }

@@ -23,144 +23,29 @@ namespace gt {
 
 static inline int ilog2(int32_t x) { int k = 0; while ((1 << (k + 1)) <= x) ++k; return k; }
 
-int build_plan(const Layout& L, int32_t T, int32_t Q, int32_t R, Plan& P) {
+int build_plan(const Layout& L, int32_t T, int32_t R, Plan& P) {
     const int64_t V = L.V, N = L.N;
     if ((T != 1024 && T != 2048)) { set_error("tile size must be 1024 or 2048 leaves (two value arrays of a tile must fit in shared memory)"); return GT_ERR_ARG; }
-    // Q*8 bytes (one fp64 row segment) must fit in shared memory
-    if (Q < 4 || Q > 16384 || (Q & 3)) { set_error("segment size must be a multiple of 4 in [4, 16384]"); return GT_ERR_ARG; }
-    if (R != 2 && R != 4) { set_error("rows per CTA must be 2 or 4"); return GT_ERR_ARG; }
+    if (R != 4) { set_error("rows per work item must be 4 (16-byte value slots: 4 fp32 rows, 2 fp64 rows)"); return GT_ERR_ARG; }
     const int logT = ilog2(T);
     // Aligned blocks stop at 2^kPyramidTop leaves: one warp builds all levels of its block with shuffles, so the
     // pyramid needs no cross-warp step; the few ranges longer than that just carry more terms.
     const int kTop = std::min(logT, kPyramidTop);
-    P.T = T; P.Q = Q; P.R = R; P.slot_bytes = 4 * R;
+    P.T = T; P.R = R; P.slot_bytes = 4 * R;
     const int32_t SB = P.slot_bytes;
     auto swz = [&](int32_t s) -> uint16_t { return (uint16_t)(s < 2 * T ? swizzle_slot(s, SB) : s); };
     const int bank_mod = 128 / SB;  // slots per 128-byte shared-memory wavefront
     P.NT = (int32_t)((V + T - 1) / T);
-    P.NS = (int32_t)((V + Q - 1) / Q);
-    const int32_t NT = P.NT, NS = P.NS;
+    const int32_t NT = P.NT;
+    if ((int64_t)NT * T >= (int64_t)1 << 31) { set_error("vocabulary too large"); return GT_ERR_LIMIT; }
 
-    // ---- staging layout: tile-major, inside a tile one run per source segment, padded to 4 -------
-    // count[t][s]
-    std::vector<int32_t> cnt((size_t)NT * NS, 0);
-    for (int64_t r = 0; r < V; ++r) cnt[(size_t)(r / T) * NS + L.perm[(size_t)r] / Q]++;
-    std::vector<int64_t> run_off((size_t)NT * NS + 1, 0);  // start of run (t,s) in a staged row
-    P.z_tile_off.assign((size_t)NT + 1, 0);
-    int64_t z = 0;
-    // run_len[t][s]: staged length of run (t,s): the count padded to 4; the last run of a tile absorbs what is
-    // needed to make the tile's staged range a multiple of 8 elements (16-byte aligned uint16 slot tables, and
-    // 16-byte cp.async granules for every row type)
-    std::vector<int32_t> run_len((size_t)NT * NS, 0);
-    for (int32_t t = 0; t < NT; ++t) {
-        P.z_tile_off[t] = (int32_t)z;
-        for (int32_t s = 0; s < NS; ++s) {
-            run_off[(size_t)t * NS + s] = z;
-            int32_t len = (cnt[(size_t)t * NS + s] + 3) & ~3;
-            if (s == NS - 1 && ((z + len) & 7)) len += 4;
-            run_len[(size_t)t * NS + s] = len;
-            z += len;
-        }
-        P.max_tile_z = std::max<int32_t>(P.max_tile_z, (int32_t)(z - P.z_tile_off[t]));
+    // ---- permute table: the item at DFS rank r goes to leaf slot r % T of tile r / T.  The swizzle permutes slots
+    // inside aligned groups of 8 chunks only, so applying it to the rank is applying it to the tile-local slot.
+    P.leaf_dest.assign((size_t)V, 0);
+    for (int64_t r = 0; r < V; ++r) {
+        const int32_t t = (int32_t)(r / T);
+        P.leaf_dest[(size_t)L.perm[(size_t)r]] = t * T + (int32_t)swz((int32_t)(r - (int64_t)t * T));
     }
-    P.z_tile_off[NT] = (int32_t)z;
-    P.Zrow = z;
-    if (z >= (int64_t)1 << 31) { set_error("staged row too long"); return GT_ERR_LIMIT; }
-
-    constexpr uint16_t kPadSlot = 0xFFC0;  // kPadSlot + c: padding element bound for trash slot c (resolved below)
-    P.p2_slot.assign((size_t)z, kPadSlot);
-    // position inside the source segment; padding elements name position 0 (any valid one would do: what the permute
-    // kernel writes for them lands in a trash slot of the tile kernel)
-    std::vector<uint16_t> z_src((size_t)z, 0);
-    {
-        // Order inside a run is free (both kernels follow these tables), and so is the place of a run's padding.
-        // The tile kernel scatters staged quad q with lane q: for e = 0..3 the lanes of one shared-memory wavefront
-        // (bank_mod consecutive quads of the tile) store element e of their quads, and the stores of a wavefront
-        // collide when two of their slots fall in the same bank group (slot mod bank_mod).  So the tile's staged
-        // positions form windows of bank_mod quads x 4 columns, and every (window, column) wants bank_mod different
-        // bank groups.  Greedy, run by run in staged order: a position takes an element of the run whose bank group
-        // is still free in its (window, column) -- the group with the most elements left first -- else a padding
-        // element, else it accepts the conflict.  (A run is a random 1/NS sample of the tile's leaves, so its bank
-        // groups are unevenly filled and some conflicts are unavoidable: measured 1.5 wavefronts per store at
-        // T = 1024, Q = 4096 against 2.1 for a fixed "quad g takes group g" rule.)
-        std::vector<std::vector<std::pair<uint16_t, uint16_t>>> runs((size_t)NT * NS);  // (slot, src)
-        for (int64_t r = 0; r < V; ++r) {
-            const int32_t t = (int32_t)(r / T), pos = L.perm[(size_t)r], s = pos / Q;
-            runs[(size_t)t * NS + s].push_back({swz((int32_t)(r - (int64_t)t * T)), (uint16_t)(pos - s * Q)});
-        }
-        std::vector<uint32_t> used;  // [(window, column)] bank groups taken, per tile
-        // Second criterion, among the elements of the chosen bank group: the permute kernel gathers element e of 32
-        // consecutive records of a segment with one 4-byte shared-memory load per lane, so inside a segment's record
-        // list every (32 records, column) wants 32 different source banks (position mod 32).
-        std::vector<int64_t> seg_pos((size_t)NS, 0);          // staged elements of segment s placed so far
-        std::vector<uint32_t> src_used((size_t)NS * 4, 0u);   // [(segment, column)] source banks taken in the current 32 records
-        for (int32_t t = 0; t < NT; ++t) {
-            const int64_t tile_at = P.z_tile_off[t];
-            used.assign((size_t)((P.z_tile_off[t + 1] - tile_at) / (4 * bank_mod) + 1) * 4, 0u);
-            for (int32_t sg = 0; sg < NS; ++sg) {
-                const size_t ri = (size_t)t * NS + sg;
-                auto& run = runs[ri];
-                const int64_t at = run_off[ri];
-                const int32_t len = run_len[ri];
-                std::vector<std::vector<std::pair<uint16_t, uint16_t>>> cls((size_t)bank_mod);
-                for (auto& e : run) cls[e.first % bank_mod].push_back(e);
-                size_t remaining = run.size();
-                for (int32_t pos = 0; pos < len; ++pos) {
-                    const int64_t rel = at + pos - tile_at;
-                    uint32_t& m = used[(size_t)(rel / (4 * bank_mod)) * 4 + (size_t)(rel & 3)];
-                    const int64_t sp = seg_pos[(size_t)sg]++;  // runs are whole records: column = sp & 3 = rel & 3
-                    if ((sp & 127) < 4) src_used[(size_t)sg * 4 + (size_t)(sp & 3)] = 0u;  // a new group of 32 records
-                    uint32_t& sm = src_used[(size_t)sg * 4 + (size_t)(sp & 3)];
-                    int best = -1;
-                    for (int c = 0; c < bank_mod; ++c)
-                        if (!cls[c].empty() && !((m >> c) & 1u) && (best < 0 || cls[c].size() > cls[best].size())) best = c;
-                    if (best < 0 && (int64_t)remaining < (int64_t)(len - pos)) {
-                        // a padding element goes here: it lands in one of bank_mod trash slots past the value array,
-                        // the one whose bank group is still free in this (window, column) if there is one
-                        int c = 0;
-                        while (c < bank_mod - 1 && ((m >> c) & 1u)) ++c;
-                        m |= 1u << c;
-                        P.p2_slot[(size_t)(at + pos)] = (uint16_t)(kPadSlot + c);
-                        continue;
-                    }
-                    if (best < 0)
-                        for (int c = 0; c < bank_mod; ++c)
-                            if (!cls[c].empty() && (best < 0 || cls[c].size() > cls[best].size())) best = c;
-                    auto& pool = cls[best];
-                    size_t pick = pool.size() - 1;
-                    for (size_t q = pool.size(); q-- > 0;)
-                        if (!((sm >> (pool[q].second & 31)) & 1u)) { pick = q; break; }
-                    const auto e = pool[pick];
-                    pool.erase(pool.begin() + (long)pick);
-                    --remaining;
-                    m |= 1u << best;
-                    sm |= 1u << (e.second & 31);
-                    P.p2_slot[(size_t)(at + pos)] = e.first;
-                    z_src[(size_t)(at + pos)] = e.second;
-                }
-            }
-        }
-    }
-    // phase-1 records: segment-major
-    P.p1_chunk_ptr.assign((size_t)NS + 1, 0);
-    P.p1_rec.clear();
-    P.p1_rec.reserve((size_t)z);
-    for (int32_t s = 0; s < NS; ++s) {
-        P.p1_chunk_ptr[s] = (int32_t)(P.p1_rec.size() / 4);
-        for (int32_t t = 0; t < NT; ++t) {
-            const int64_t a = run_off[(size_t)t * NS + s];
-            const int64_t n = run_len[(size_t)t * NS + s];
-            for (int64_t k = 0; k < n; k += 4) {
-                const uint32_t s0 = z_src[(size_t)(a + k)], s1 = z_src[(size_t)(a + k + 1)];
-                const uint32_t s2 = z_src[(size_t)(a + k + 2)], s3 = z_src[(size_t)(a + k + 3)];
-                P.p1_rec.push_back((int32_t)(a + k));
-                P.p1_rec.push_back((int32_t)(s0 | (s1 << 16)));
-                P.p1_rec.push_back((int32_t)(s2 | (s3 << 16)));
-                P.p1_rec.push_back(0);
-            }
-        }
-    }
-    P.p1_chunk_ptr[NS] = (int32_t)(P.p1_rec.size() / 4);
 
     // ---- node intervals per tile -------------------------------------------------------------------
     P.tile_node_lo.assign((size_t)NT + 1, (int32_t)N);
@@ -394,9 +279,7 @@ int build_plan(const Layout& L, int32_t T, int32_t Q, int32_t R, Plan& P) {
         P.ell_row_ptr[(size_t)t + 1] = P.ell_row_ptr[(size_t)t] + rows;
     }
     if ((int64_t)P.ell_row_ptr[(size_t)NT] * 32 != (int64_t)P.ell_terms.size()) { set_error("internal: ELL row count"); return GT_ERR_STATE; }
-    // staged padding elements land in the trash slots past the value array (same for every tile): one per bank group
     P.max_tile_values = (P.max_tile_values + 3) & ~3;
-    for (auto& sl : P.p2_slot) if (sl >= kPadSlot) sl = (uint16_t)(P.max_tile_values + (sl - kPadSlot));
     return GT_OK;
 }
 
@@ -404,22 +287,18 @@ int build_plan(const Layout& L, int32_t T, int32_t Q, int32_t R, Plan& P) {
 
 extern "C" {
 
-int gt_plan(gt_trie* t, int32_t tile_leaves, int32_t seg_positions, int32_t rows_per_cta) {
+int gt_plan(gt_trie* t, int32_t tile_leaves) {
     if (!t) { gt::set_error("gt_plan: null trie"); return GT_ERR_ARG; }
     auto env_int = [](const char* name, int dflt) { const char* s = getenv(name); return s && *s ? atoi(s) : dflt; };
     if (t->plan && tile_leaves <= 0) tile_leaves = t->plan->T;
-    if (t->plan && seg_positions <= 0) seg_positions = t->plan->Q;
-    if (t->plan && rows_per_cta <= 0) rows_per_cta = t->plan->R;
     if (tile_leaves <= 0) tile_leaves = env_int("GT_TILE_LEAVES", 1024);
-    if (seg_positions <= 0) seg_positions = env_int("GT_SEG_POSITIONS", 4096);
-    if (rows_per_cta <= 0) rows_per_cta = env_int("GT_ROWS_PER_CTA", 4);
     if (t->plan) {
-        if (t->plan->T == tile_leaves && t->plan->Q == seg_positions && t->plan->R == rows_per_cta) return GT_OK;
-        gt::set_error("gt_plan: a plan with T=%d Q=%d R=%d already exists", t->plan->T, t->plan->Q, t->plan->R);
+        if (t->plan->T == tile_leaves) return GT_OK;
+        gt::set_error("gt_plan: a plan with T=%d already exists", t->plan->T);
         return GT_ERR_STATE;
     }
     std::unique_ptr<gt::Plan> p(new gt::Plan());
-    const int rc = gt::build_plan(t->layout, tile_leaves, seg_positions, rows_per_cta, *p);
+    const int rc = gt::build_plan(t->layout, tile_leaves, 4, *p);
     if (rc != GT_OK) return rc;
     t->plan = std::move(p);
     return GT_OK;
@@ -430,7 +309,7 @@ int64_t gt_export_plan_array(const gt_trie* t, const char* name, void* dst, int6
     const gt::Plan& P = *t->plan;
     const void* src = nullptr; int64_t n = -1; int32_t es = 4;
 #define GT_ARR(field) if (!strcmp(name, #field)) { src = P.field.data(); n = (int64_t)P.field.size(); es = (int32_t)sizeof(P.field[0]); }
-    GT_ARR(p1_chunk_ptr) GT_ARR(p1_rec) GT_ARR(z_tile_off) GT_ARR(p2_slot) GT_ARR(ell_chunk_ptr) GT_ARR(ell_desc)
+    GT_ARR(leaf_dest) GT_ARR(ell_chunk_ptr) GT_ARR(ell_desc)
     GT_ARR(ell_terms) GT_ARR(ell_row_ptr) GT_ARR(tile_node_lo) GT_ARR(node_slot) GT_ARR(piece_ptr) GT_ARR(piece_slot) GT_ARR(piece_idx)
     GT_ARR(span_node) GT_ARR(span_pp)
 #undef GT_ARR

@@ -22,8 +22,10 @@ _IN_TYPES = {
 _OUT_TYPES = {torch.float32: _lib.GT_F32, torch.float64: _lib.GT_F64}
 OPS = {"sum": _lib.GT_OP_SUM, "max": _lib.GT_OP_MAX}
 
-# rows whose staging scratch we keep per stream slot (the C side chunks larger batches itself)
-_WORKSPACE_ROWS = int(os.environ.get("GT_WORKSPACE_ROWS", "64"))  # 64 rows of staging (35 MB) stay L2-resident between the kernels
+# rows whose staging scratch we keep per stream (the C side processes larger batches in chunks of this many rows):
+# 64 rows of staging are 34 MB at 128k tokens and stay in L2 between the permute warps and the copy engine
+_WORKSPACE_ROWS = int(os.environ.get("GT_WORKSPACE_ROWS", "64"))
+_MAX_WORKSPACES = 16  # per engine: (device, stream) pairs we keep scratch for
 
 
 def require_cuda():
@@ -75,8 +77,8 @@ class TrieEngine:
         check(lib.gt_export_reachability(self._handle, rows.ctypes.data, cols.ctypes.data), "gt_export_reachability")
         return rows, cols
 
-    def plan(self, tile_leaves=0, seg_positions=0, rows_per_cta=0):
-        check(lib.gt_plan(self._handle, tile_leaves, seg_positions, rows_per_cta), "gt_plan")
+    def plan(self, tile_leaves=0):
+        check(lib.gt_plan(self._handle, tile_leaves), "gt_plan")
 
     def plan_info(self):
         self.plan()
@@ -100,12 +102,18 @@ class TrieEngine:
             check(lib.gt_upload(self._handle, int(index)), "gt_upload")
             self._uploaded.add(index)
 
-    def _workspace(self, index, slot, rows):
+    def _workspace(self, index, stream, rows):
+        """Scratch for launches on ``stream`` (a raw ``cudaStream_t``) of device ``index``.  One buffer per
+        (device, stream): calls on one stream are ordered, so they may share it; calls on different streams (or
+        threads using different streams) never do."""
         need = int(lib.gt_workspace_bytes(self._handle, min(max(rows, 1), _WORKSPACE_ROWS)))
-        key = (index, slot)
+        key = (index, int(stream or 0))
         buf = self._workspaces.get(key)
         if buf is None or buf.numel() < need:
-            buf = torch.empty(max(need, 256), dtype=torch.uint8, device=torch.device("cuda", index))
+            if buf is None and len(self._workspaces) >= _MAX_WORKSPACES:
+                self._workspaces.pop(next(iter(self._workspaces)))  # the caching allocator keeps the block stream-ordered
+            # allocated on `stream` (the caller made it current), so a later reuse of the block is ordered after our kernels
+            buf = torch.empty(max(need, 4096), dtype=torch.uint8, device=torch.device("cuda", index))
             self._workspaces[key] = buf
         return buf
 
@@ -121,7 +129,7 @@ class TrieEngine:
         ld = self.row_stride(dtype)
         return torch.empty((max(B, 1), ld), dtype=dtype, device=device)[:B, : self.N]
 
-    def reduce(self, ws, ops, out_dtype=torch.float32, log_input=False, out_sum=None, out_max=None, slot=0, phases=0):
+    def reduce(self, ws, ops, out_dtype=torch.float32, log_input=False, out_sum=None, out_max=None, phases=0):
         """Launch the mass kernels for a ``[B, V]`` CUDA tensor on its device's current stream.
 
         Returns ``(out_sum, out_max)`` device tensors of shape ``[B, N]`` (``None`` for an op not asked for).
@@ -160,9 +168,9 @@ class TrieEngine:
         if out_sum is not None and out_max is not None and B > 1 and out_sum.stride(0) != out_max.stride(0):
             raise ValueError("out_sum and out_max must share a row stride")
         ld_ws = ws.stride(0) if B > 1 else max(self.V, 1)
-        work = self._workspace(index, slot, B)
         with torch.cuda.device(index):
             stream = torch.cuda.current_stream(index).cuda_stream
+            work = self._workspace(index, stream, B)
             check(
                 lib.gt_weight_reduce(
                     self._handle, ws.data_ptr(), _IN_TYPES[ws.dtype], B, ld_ws,

@@ -229,7 +229,7 @@ class ParallelTokenCharacterTrie(TokenCharacterTrie):
                         chunk = ws[r0:r1]
                         if chunk.device != dev:
                             chunk = chunk.to(dev, non_blocking=True)
-                    o_sum, o_max = self._engine.reduce(chunk, ops, log_input=log_input, slot=k % _PIPE_SLOTS)
+                    o_sum, o_max = self._engine.reduce(chunk, ops, log_input=log_input)
                     if o_sum is not None:
                         outs["sum"][r0:r1].copy_(o_sum._base[: r1 - r0], non_blocking=True)
                     if o_max is not None:

@@ -10,10 +10,11 @@
  *                                                                    _order, _order_full)
  *   gt_export_reachability      genlm/backend/trie/parallel.py:21-64 (_build_parent_map,
  *                                                                    _build_reachability_matrix)
- *   gt_weight_sum_*             genlm/backend/trie/base.py:346-368   (_update_trie_numba_sum)
- *                               genlm/backend/trie/parallel.py:92-103 (batch_weight_sum: sparse.mm)
- *   gt_weight_max_*             genlm/backend/trie/base.py:371-393   (_update_trie_numba_max)
- *                               genlm/backend/trie/parallel.py:120-145 (batch_weight_max: scatter_reduce amax)
+ *   gt_weight_reduce            ops & GT_OP_SUM:  genlm/backend/trie/base.py:346-368   (_update_trie_numba_sum)
+ *                                                 genlm/backend/trie/parallel.py:92-103 (batch_weight_sum: sparse.mm)
+ *                               ops & GT_OP_MAX:  genlm/backend/trie/base.py:371-393   (_update_trie_numba_max)
+ *                                                 genlm/backend/trie/parallel.py:120-145 (batch_weight_max:
+ *                                                 scatter_reduce amax)
  *   gt_lse_sample               README.md:82-91 / genlm/backend/llm/base.py:131-146
  *                               (masked logsumexp + multinomial of the SMC particle step)
  *   gt_gather_nodes             genlm/backend/trie/parallel.py:103,145 (the .cpu().numpy() of the whole slab)
@@ -24,7 +25,8 @@
  *     thread-local message for the last failure on the calling thread;
  *   - plain pointers and sizes only, no torch / numpy types;
  *   - all device pointers are caller-owned; nothing is allocated per call; every launch goes to the
- *     caller-supplied stream (a cudaStream_t passed as void*); no hidden synchronisation;
+ *     caller-supplied stream (a cudaStream_t passed as void*); no hidden synchronisation (gt_upload, which
+ *     runs once per trie and device, is the exception: it returns when the metadata is resident);
  *   - node ids, leaf ids and row layout are exactly the reference's (post-order ids, root = N-1).
  */
 #ifndef GENLM_TRIE_B200_H
@@ -90,26 +92,26 @@ int gt_upload(gt_trie* t, int device);
 typedef struct gt_plan_info {
     int64_t n_tokens, n_nodes;
     int32_t tile_leaves;     /* T: DFS-ordered leaves per tile                       */
-    int32_t seg_positions;   /* Q: vocabulary positions per source segment           */
-    int32_t n_tiles, n_segs;
-    int32_t rows_per_item;   /* R: rows a CTA processes per metadata load            */
+    int32_t n_tiles;
+    int32_t rows_per_item;   /* R: fp32 rows that share a work item (16-byte value slots; fp64: R/2) */
+    int32_t permute_unit;    /* vocabulary positions per permute work unit           */
     int32_t n_span;          /* nodes whose leaf range crosses a tile boundary       */
+    int32_t max_levels;      /* levels of the per-tile aligned-block pyramid         */
     int64_t span_terms;      /* per-tile pieces the spanning nodes are reduced from  */
-    int32_t max_levels;      /* deepest in-tile dependency chain of branching nodes  */
-    int32_t max_tile_values; /* largest per-tile value array (leaf + branching slots)*/
-    int64_t staged_row_elems;/* elements per row of the tile-major staging buffer    */
+    int32_t max_tile_values; /* largest per-tile value array (leaf + pyramid + range slots) */
+    int32_t reserved;
+    int64_t staged_slots;    /* value slots per row group of the staging buffer (n_tiles * tile_leaves) */
     int64_t meta_bytes;      /* device-resident metadata                              */
 } gt_plan_info;
 int gt_get_plan_info(const gt_trie* t, gt_plan_info* info);
 
-/* Host-only: build the tile plan without touching a device (gt_upload calls this with its defaults when
- * no plan exists yet).  tile_leaves: 1024 or 2048; seg_positions: multiple of 4, <= 16384;
- * rows_per_cta: 2 or 4 (rows of a batch that share one CTA of the fp32 pipeline; the fp64 pipeline uses half);
- * pass 0 for the defaults.  Fails if a plan already exists with different parameters. */
-int gt_plan(gt_trie* t, int32_t tile_leaves, int32_t seg_positions, int32_t rows_per_cta);
+/* Host-only: build the tile plan without touching a device (gt_upload calls this with its default when
+ * no plan exists yet).  tile_leaves: 1024 or 2048, 0 for the default.  Fails if a plan already exists with a
+ * different tile size. */
+int gt_plan(gt_trie* t, int32_t tile_leaves);
 
 /* Host-only introspection of the plan arrays, used by the CPU tests that emulate the kernels' data flow.
- * `name` is one of: p1_chunk_ptr p1_rec z_tile_off p2_slot ell_chunk_ptr ell_desc ell_terms ell_row_ptr tile_node_lo
+ * `name` is one of: leaf_dest ell_chunk_ptr ell_desc ell_terms ell_row_ptr tile_node_lo
  * node_slot piece_ptr piece_slot piece_idx span_node span_pp.  Returns the element count (or -1), and copies
  * min(count, capacity) elements into dst when dst != NULL.  elem_size receives 2 or 4. */
 int64_t gt_export_plan_array(const gt_trie* t, const char* name, void* dst, int64_t capacity, int32_t* elem_size);
@@ -119,7 +121,9 @@ int64_t gt_export_plan_array(const gt_trie* t, const char* name, void* dst, int6
  * Returns the element count, or -1 when no trace buffer exists.  tools/trace_tile.py prints the phase durations. */
 int64_t gt_debug_read_trace(const gt_trie* t, int device, long long* dst, int64_t capacity, int32_t dims[3]);
 
-/* Caller-owned scratch needed for a batch of up to max_rows rows on the current device. */
+/* Caller-owned scratch needed to process up to max_rows rows per launch (larger batches are processed in
+ * chunks of what the scratch holds).  One call at a time may use a workspace: calls that share one must be
+ * ordered (same stream).  The pointer must be 256-byte aligned. */
 size_t gt_workspace_bytes(const gt_trie* t, int64_t max_rows);
 
 /* ---- trie mass kernels -------------------------------------------------------------------- */
@@ -127,9 +131,9 @@ size_t gt_workspace_bytes(const gt_trie* t, int64_t max_rows);
 #define GT_FLAG_LOG_INPUT 1u /* rows hold log-weights: exp() is fused into the load (-inf -> 0) */
 /* Profiling aids: restrict a call to some phases (default: all).  Used by bench.py to time one kernel in
  * isolation with CUDA events; results are only complete when all phases have run in order. */
-#define GT_FLAG_PHASE_PERMUTE 0x100u
-#define GT_FLAG_PHASE_TILE 0x200u /* tile kernel */
-#define GT_FLAG_PHASE_SPAN 0x400u /* the small spanning-node kernel that follows it */
+#define GT_FLAG_PHASE_PERMUTE 0x100u /* permute kernel */
+#define GT_FLAG_PHASE_TILE 0x200u    /* tile kernel (the staging buffer of an earlier call is reused) */
+#define GT_FLAG_PHASE_SPAN 0x400u    /* the small spanning-node kernel that follows it */
 #define GT_FLAG_PHASE_MASK 0x700u
 
 /* Input / output element types. */
@@ -146,8 +150,11 @@ size_t gt_workspace_bytes(const gt_trie* t, int64_t max_rows);
  *   out_sum / out_max   device pointers (one may be NULL when the op is not requested), row stride
  *            ld_out elements, type out_type (GT_F32 or GT_F64)
  *   ops      GT_OP_SUM | GT_OP_MAX
- *   workspace  device scratch of at least gt_workspace_bytes(t, n_rows) bytes
- * Sums are accumulated in fp64 and rounded once; max is exact. */
+ *   workspace  device scratch, see gt_workspace_bytes / gt_workspace_init
+ * Numerics: every node is a sum of non-negative terms (aligned leaf blocks; no prefix differences).  With
+ * out_type GT_F32 the terms inside a tile of 1024 leaves are added pairwise in fp32 and the per-tile pieces of a
+ * node that spans tiles in fp64, rounded once (measured <= 2e-7 relative to the fp64 reference); with GT_F64
+ * everything is fp64.  max is exact. */
 int gt_weight_reduce(const gt_trie* t, const void* ws, int in_type, int64_t n_rows, int64_t ld_ws,
                      void* out_sum, void* out_max, int out_type, int64_t ld_out, unsigned ops,
                      unsigned flags, void* workspace, size_t workspace_bytes, gt_stream stream);

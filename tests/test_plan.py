@@ -15,46 +15,36 @@ def oracle_for(trie):
     return oracle.OracleLayout(trie.idx_to_leaf, lay["child_ptr"], lay["child_idx"])
 
 
-@pytest.mark.parametrize("V,T,Q,R", [(1, 1024, 4, 2), (5, 1024, 4, 4), (700, 1024, 128, 2), (3000, 1024, 512, 4),
-                                     (3000, 2048, 8192, 2), (20011, 2048, 8192, 2), (20011, 1024, 1000, 4),
-                                     (20011, 1024, 16384, 2), (20011, 2048, 4096, 4), (50257, 1024, 4096, 4)])
-def test_emulated_kernels_match_oracle(V, T, Q, R):
+@pytest.mark.parametrize("V,T", [(1, 1024), (5, 1024), (700, 1024), (3000, 1024), (3000, 2048), (20011, 2048),
+                                 (20011, 1024), (50257, 1024)])
+def test_emulated_kernels_match_oracle(V, T):
     trie = TokenCharacterTrie(synth_vocab(max(V, 256), seed=2)[-V:])
-    trie._engine.plan(T, Q, R)
+    trie._engine.plan(T)
     ws = dirichlet_rows(3, V, alpha=0.1, seed=1)
     o = oracle_for(trie)
     have = emulate(trie._engine, ws, "sum")
-    assert not np.isnan(have).any()  # every node written exactly through one of the three phases
+    assert not np.isnan(have).any()  # every node written, and none of them from a leaf slot past the vocabulary
     r, z = rel_err(have, o.weight_sum(ws))
     assert r <= 2e-6 and z == 0.0
     assert np.array_equal(emulate(trie._engine, ws, "max"), o.weight_max(ws).astype(np.float32))
 
 
 def test_plan_invariants():
-    V, T, Q = 20011, 1024, 1000
+    V, T = 20011, 1024
     trie = TokenCharacterTrie(synth_vocab(V, seed=4))
     eng = trie._engine
-    eng.plan(T, Q)
+    eng.plan(T)
     info = eng.plan_info()
     lay = trie._layout
-    assert info["n_tiles"] == -(-V // T) and info["n_segs"] == -(-V // Q)
-    assert info["staged_row_elems"] % 4 == 0 and info["staged_row_elems"] >= V
-    # staging is a permutation of the row plus padding; a padding element is one the tile kernel sends to a trash slot
-    # (past the value array), whatever source position its record names
-    rec, cptr = eng.plan_array("p1_rec").reshape(-1, 4), eng.plan_array("p1_chunk_ptr")
-    zoff = rec[:, 0]
-    p2 = eng.plan_array("p2_slot").astype(np.int64)
-    seen = np.zeros(V, dtype=np.int64)
-    for s in range(info["n_segs"]):
-        r = rec[cptr[s]:cptr[s + 1]]
-        lohi = r[:, 1:3].astype(np.int64) & 0xFFFFFFFF
-        e = np.stack([lohi[:, 0] & 0xFFFF, lohi[:, 0] >> 16, lohi[:, 1] & 0xFFFF, lohi[:, 1] >> 16], axis=1).reshape(-1)
-        dst = (r[:, 0].astype(np.int64)[:, None] + np.arange(4)[None, :]).reshape(-1)
-        real = p2[dst] < info["max_tile_values"]
-        assert (e < min(Q, V - s * Q)).all()  # every named position, padding included, lies inside the segment
-        np.add.at(seen, e[real] + s * Q, 1)
-    assert (seen == 1).all()
-    assert len(np.unique(zoff)) == len(zoff) and (zoff % 4 == 0).all()
+    assert info["n_tiles"] == -(-V // T) and info["staged_slots"] == info["n_tiles"] * T
+    assert info["rows_per_item"] == 4 and info["permute_unit"] % 32 == 0
+    # the permute table sends the item at DFS rank r to leaf slot swizzle(r % T) of tile r // T: a bijection onto the
+    # first V leaf slots in DFS order
+    dest = eng.plan_array("leaf_dest").astype(np.int64)
+    rank = np.empty(V, dtype=np.int64)
+    rank[lay["perm"]] = np.arange(V)
+    assert np.array_equal(dest, (rank // T) * T + swizzle_slot(rank % T, 16))
+    assert len(np.unique(dest)) == V
     # node intervals partition the id space; spanning nodes are exactly those without a slot
     lo = eng.plan_array("tile_node_lo")
     assert lo[0] == 0 and lo[-1] == len(trie) and (np.diff(lo) > 0).all()
@@ -81,10 +71,10 @@ def test_plan_parameter_validation():
     trie = TokenCharacterTrie([Token(0, b"a")])
     from genlm_backend_b200._lib import GtError
 
-    for T, Q, R in [(1000, 8192, 2), (512, 8192, 2), (4096, 8192, 2), (2048, 6, 2), (2048, 32768, 2), (2048, 4096, 3)]:
+    for T in (1000, 512, 4096):
         with pytest.raises(GtError):
-            trie._engine.plan(T, Q, R)
-    trie._engine.plan(2048, 4096, 2)
-    trie._engine.plan()  # defaults resolve to the existing plan
+            trie._engine.plan(T)
+    trie._engine.plan(2048)
+    trie._engine.plan()  # the default resolves to the existing plan
     with pytest.raises(GtError):
-        trie._engine.plan(1024, 4096)
+        trie._engine.plan(1024)
