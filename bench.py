@@ -47,6 +47,10 @@ def parse_args():
     ap.add_argument("--sets", type=int, default=4, help="rotating buffer sets (each 33 MB in + 176 MB out)")
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 10)")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-pipeline", action="store_true",
+                    help="every step stages its own rows with the permute kernel (default: each step's tile kernel stages the "
+                         "next step's rows, gt_weight_reduce_next)")
+    ap.add_argument("--min-ms", type=float, default=50.0, help="the K timed steps are repeated until this much device time has passed")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-sampler", action="store_true", help="skip the secondary sampler-kernel measurement")
     ap.add_argument("--allgather", action="store_true",
@@ -287,62 +291,80 @@ def run_ours(args):
     set_bytes = B * V * 4 + 2 * B * N * 4
     l2_bytes = torch.cuda.get_device_properties(dev).L2_cache_size
 
-    def step(k, phases=0, ops=("sum", "max")):
-        eng.reduce(ws_sets[k], ops, out_sum=sum_sets[k], out_max=max_sets[k], phases=phases)
+    pipelined = not args.no_pipeline
 
-    launches_per_step = 1 + (1 if info["n_span"] > 0 else 0)  # fused mass kernel (both reductions) + span
+    def step(k, phases=0, ops=("sum", "max"), nxt=None):
+        eng.reduce(ws_sets[k], ops, out_sum=sum_sets[k], out_max=max_sets[k], phases=phases, next_ws=nxt)
+
+    # kernels per step: tile kernel (both reductions; its producer warps stage the next step's rows) + span kernel;
+    # unpipelined steps start with the permute kernel
+    launches_per_step = (1 if pipelined else 2) + (1 if info["n_span"] > 0 else 0)
 
     # warm-up (also sets kernel attributes, allocates the scratch) ------------------------------------------------
     for i in range(W):
-        step(i % nsets)
+        step(i % nsets, nxt=ws_sets[(i + 1) % nsets] if pipelined else None)
     torch.cuda.synchronize()
 
-    # The timed loop replays CUDA graphs: one graph holds 16 steps rotating over the buffer sets (back-to-back steps of a
-    # stream, as a serving loop issues them), single-step graphs cover the remainder so that exactly K steps run.
-    graphs = None
-    if not args.no_graph:
-        graphs = []
-        for k in range(nsets):
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                step(k)
-            graphs.append(g)
-        per_multi = 4 * nsets
-        multi = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(multi):
-            for k in range(per_multi):
-                step(k % nsets)
-        for k in range(nsets):
-            graphs[k].replay()
-        multi.replay()
-        torch.cuda.synchronize()
-
-    def run_steps(n):
-        """Enqueue exactly n steps, rotating over the buffer sets."""
-        if graphs is None:
+    # The timed loop replays ONE CUDA graph that holds exactly K consecutive steps of a stream of batches rotating over
+    # the buffer sets, as a serving loop issues them.  Pipelined (default): step i names batch i + 1, whose rows its tile
+    # kernel stages (the last step names the first batch of the next replay).
+    def capture(n):
+        chain = pipelined and n % 2 == 0  # the staging buffers alternate: an even step count returns to the entry state
+        eng._staged.clear()
+        if chain:  # entry state of every replay: batch 0 staged by the step before
+            step(nsets - 1, nxt=ws_sets[0])
+            torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
             for i in range(n):
-                step(i % nsets)
-            return
-        for _ in range(n // per_multi):
-            multi.replay()
-        for i in range(n % per_multi):
-            graphs[i % nsets].replay()
+                last = i == n - 1
+                nxt = None
+                if pipelined and (not last or chain):
+                    nxt = ws_sets[0] if last else ws_sets[(i + 1) % nsets]
+                step(i % nsets, nxt=nxt)
+        if not chain:
+            eng._staged.clear()
+        return g
+
+    graph = None if args.no_graph else capture(K)
+
+    def run_steps():
+        """Enqueue exactly K steps, rotating over the buffer sets."""
+        if graph is None:
+            for i in range(K):
+                step(i % nsets, nxt=ws_sets[(i + 1) % nsets] if pipelined and i + 1 < K else None)
+        else:
+            graph.replay()
+
+    run_steps()
+    torch.cuda.synchronize()
 
     clocks = ClockSampler(local_rank)
     clocks.start()
 
-    # timed region: exactly K steps ---------------------------------------------------------------------------------
+    # timed region: the K steps, repeated until at least --min-ms of device time has passed ---------------------------
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    run_steps()
+    ev1.record()
+    torch.cuda.synchronize()
+    reps = max(1, int(np.ceil(args.min_ms / max(ev0.elapsed_time(ev1), 1e-3))))
+    if world > 1:
+        t = torch.tensor([reps], dtype=torch.int64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        reps = int(t.item())
     barrier()
     clocks.loaded = True
     ev0.record()
-    run_steps(K)
+    for _ in range(reps):
+        run_steps()
     ev1.record()
     torch.cuda.synchronize()
     clocks.loaded = False
     barrier()
-    ms_total = max_over_ranks(ev0.elapsed_time(ev1))
+    ms_total = max_over_ranks(ev0.elapsed_time(ev1)) / reps
     value = world * B * K / (ms_total / 1e3)
+    eng._staged.clear()
 
     # per-kernel timing for the roofline (one op, one phase at a time), same buffers ----------------------------------
     def time_phase(phases, ops, iters):
@@ -456,7 +478,9 @@ def run_ours(args):
             "parallelism": f"rows sharded, {world} independent GPU(s), no collective",
             "l2_policy": f"rotating {nsets} buffer sets of {set_bytes / 1e6:.0f} MB ({nsets * set_bytes / 1e6:.0f} MB total) "
                          f"vs L2 {l2_bytes / 1e6:.0f} MB",
-            "launch": f"CUDA graphs of {4 * nsets} consecutive steps rotating over the {nsets} buffer sets, single-step graphs for the remainder" if graphs is not None else "direct launches",
+            "launch": (f"one CUDA graph of the {K} steps, replayed {reps}x ({ms_total * reps:.1f} ms timed)" if graph is not None else f"direct launches, {reps} repetitions")
+                      + ("; pipelined: each step's tile kernel stages the next step's rows (gt_weight_reduce_next), no permute kernel in steady state" if pipelined else "; unpipelined: permute kernel per step"),
+            "timed_repeats": reps,
             "tile_leaves": info["tile_leaves"], "n_span": info["n_span"],
         },
         "e2e": {
@@ -470,7 +494,7 @@ def run_ours(args):
             "api": "ParallelTokenCharacterTrie.batch_weight_sum_max_at(pinned host tensor, node_ids) -> numpy [B, K] x 2",
             "note": "not the headline: same kernels, results read through gt_gather_nodes instead of copying the [B, N] slabs",
         },
-        "gpu_launches": launches_per_step * K,
+        "gpu_launches": launches_per_step * K * reps,
         "roofline": {
             "bound": "hbm", "kernel": "tile_kernel<float,4> (both reductions of the step in one launch)", "achieved": achieved,
             "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,

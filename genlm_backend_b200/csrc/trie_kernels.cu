@@ -189,12 +189,24 @@ __device__ __forceinline__ void mbar_wait(uint64_t* b, unsigned parity) {
         __nanosleep(40);
     }
 }
+// one non-blocking look at the barrier's phase
+__device__ __forceinline__ bool mbar_test(uint64_t* b, unsigned parity) {
+    unsigned done;
+    asm volatile("{\n.reg .pred p;\nmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                 : "=r"(done) : "r"((unsigned)__cvta_generic_to_shared(b)), "r"(parity) : "memory");
+    return done != 0;
+}
 // bytes: multiple of 16; both addresses 16-byte aligned
 __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, unsigned bytes, uint64_t* b) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                      (unsigned)__cvta_generic_to_shared(smem_dst)),
                  "l"(gsrc), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(b))
                  : "memory");
+}
+
+// fire-and-forget request to bring [gsrc, gsrc + bytes) into L2 (bytes: multiple of 16; gsrc 16-byte aligned)
+__device__ __forceinline__ void bulk_prefetch_l2(const void* gsrc, unsigned bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gsrc), "r"(bytes) : "memory");
 }
 
 // Device twin of gt::swizzle_slot (trie_internal.h) for slots below 2T; B = bytes per slot.
@@ -323,9 +335,14 @@ constexpr int kTraceCtas = 512, kTraceItems = 32, kTraceEvents = 12;
 
 // Shared-memory carve-up of mass_kernel (all sections 128-byte aligned: the bank group of a slot is slot % 8 in
 // the leaf blocks and in the rest buffers alike).
+constexpr int kRideStages = 3;            // staged units of the rider (see below) per CTA
+constexpr int kRideAhead = 10;            // units requested into L2 ahead of their stage fill
+constexpr int kRideRowBytes = 4096;       // row data of one staged unit: R rows x unit positions x element size
+constexpr int kRideMaxUnit = 256;         // positions per unit at most (their leaf_dest entries: 1 KB)
+constexpr int kRideStageBytes = kRideRowBytes + kRideMaxUnit * 4;
 struct MassSmem {
-    size_t leaf, leaf_bytes, rest, rest_bytes, meta, meta_bytes, terms, desc, slots, hdr, bars, total;
-    __host__ __device__ MassSmem(const PlanView& P, int slot_bytes) {
+    size_t leaf, leaf_bytes, rest, rest_bytes, meta, meta_bytes, terms, desc, slots, hdr, bars, ride, total;
+    __host__ __device__ MassSmem(const PlanView& P, int slot_bytes, bool with_ride) {
         auto up = [](size_t x) { return (x + 127) & ~size_t(127); };
         size_t o = 0;
         leaf_bytes = up((size_t)P.T * slot_bytes);
@@ -341,6 +358,7 @@ struct MassSmem {
         meta_bytes = m;
         meta = o; o += 2 * meta_bytes;
         bars = o; o += 128;
+        ride = o; o += with_ride ? (size_t)kRideStages * kRideStageBytes : 0;
         total = o;
     }
 };
@@ -361,6 +379,9 @@ template <typename VT> struct MassArgs {
     int64_t ld_out;
     int n_rows;
     unsigned ops;
+    // rider: while this launch reduces its rows, its producer warps stage `ride_rows` rows starting at `ride_ws`
+    // (same type, stride and log flag as ws) into the other staging buffer `ride_z` for the next launch (0: none)
+    const void* ride_ws; int ride_rows; VT* ride_z;
 };
 
 // ---- permute ---------------------------------------------------------------------------------------------------
@@ -402,13 +423,53 @@ __device__ __forceinline__ void permute_unit(const PlanView& P, const MassArgs<V
 }
 
 // Input-type dispatch (one switch per warp; the loops inside are type-specific).
-#define GT_IN_TYPE_SWITCH(in_type, CALL)                          \
-    switch (in_type) {                                            \
-        case GT_F32: { using IN_T = float; CALL; } break;         \
-        case GT_F64: { using IN_T = double; CALL; } break;        \
-        case GT_F16: { using IN_T = __half; CALL; } break;        \
-        default: { using IN_T = __nv_bfloat16; CALL; } break;     \
+#define GT_IN_TYPE_SWITCH(in_type, ...)                                  \
+    switch (in_type) {                                                   \
+        case GT_F32: { using IN_T = float; __VA_ARGS__; } break;         \
+        case GT_F64: { using IN_T = double; __VA_ARGS__; } break;        \
+        case GT_F16: { using IN_T = __half; __VA_ARGS__; } break;        \
+        default: { using IN_T = __nv_bfloat16; __VA_ARGS__; } break;     \
     }
+
+// ---- rider: the permute of the *next* launch's rows, done by the tile kernel's producer warp --------------------------
+// The tile kernel is bound by how fast its output stores drain to HBM; its producer warp issues a few bulk copies per
+// pair and is otherwise idle.  When the caller knows the rows of the next launch (the next chunk of a large batch, or
+// the next batch of a stream: gt_weight_reduce_next), that warp stages them into the other staging buffer meanwhile:
+// HBM reads and L2-resident scattered stores riding under an HBM-write-bound kernel.  The kernel boundary publishes
+// the staged rows, so no fence or flag is needed.  Unit = (row group, kRideUnit positions): the R row segments and
+// their leaf_dest entries arrive in shared memory by bulk copies (two stages, one unit ahead); the warp then moves 32
+// positions per step: R conflict-free shared-memory loads, one 16-byte scattered store.  Needs 16-byte aligned rows.
+__host__ __device__ inline int ride_unit_positions(int in_size, int R) {
+    const int u = kRideRowBytes / (R * in_size);
+    return u < kRideMaxUnit ? u : kRideMaxUnit;
+}
+// positions [p0, min(p0 + 128, ntok)) of a staged unit: lane l takes p0 + l + 32 j, j < 4, all loads before the stores
+template <typename VT, typename IN_T, int R>
+__device__ __forceinline__ void ride_move(const unsigned char* stage, int unit_pos, const IN_T* const (&grow)[R], int n_bulk, int p0, int ntok,
+                                          VT* zg, bool log_input, int lane) {
+    using RV = RowVec<VT, R>;
+    const IN_T* srow = reinterpret_cast<const IN_T*>(stage);
+    const int* sdest = reinterpret_cast<const int*>(stage + kRideRowBytes);
+    int d[4];
+    IN_T x[4][R];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int p = min(p0 + lane + 32 * j, ntok - 1);
+        d[j] = sdest[p];
+#pragma unroll
+        for (int r = 0; r < R; ++r)  // the last few positions of a row whose length is not a multiple of 16 bytes are not covered by the bulk copy
+            x[j][r] = p < n_bulk ? srow[r * unit_pos + p] : grow[r][p];
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        if (p0 + lane + 32 * j < ntok) {
+            RV y;
+#pragma unroll
+            for (int r = 0; r < R; ++r) y.v[r] = convert_in<VT, IN_T>(x[j][r], log_input);
+            y.store(zg + (size_t)d[j] * R);
+        }
+    }
+}
 
 constexpr int kPermThreads = 256;
 template <typename VT, int R>
@@ -507,7 +568,7 @@ __global__ void __launch_bounds__(kThreads, 2) mass_kernel(PlanView P, MassArgs<
     constexpr int B = (int)sizeof(VT) * R;  // bytes per slot
     static_assert(B == 16, "value slots are 16 bytes");
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const MassSmem L(P, B);
+    const MassSmem L(P, B, A.ride_rows > 0);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + L.bars);
     uint64_t* pairFull = bars;       // [2]
     uint64_t* pairEmpty = bars + 2;  // [2]
@@ -530,6 +591,7 @@ __global__ void __launch_bounds__(kThreads, 2) mass_kernel(PlanView P, MassArgs<
         mbar_init(pairEmpty, kEmitThreads); mbar_init(pairEmpty + 1, kEmitThreads);
         mbar_init(full, kComputeThreads); mbar_init(full + 1, kComputeThreads);
         mbar_init(empty, kEmitThreads); mbar_init(empty + 1, kEmitThreads);
+        for (int i = 0; i < kRideStages; ++i) mbar_init(bars + 8 + i, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -539,34 +601,118 @@ __global__ void __launch_bounds__(kThreads, 2) mass_kernel(PlanView P, MassArgs<
         // =========================== producer: one thread fetches pair after pair ====================================
         // Plan metadata may be fetched while the permute kernel is still running (programmatic dependent launch); the
         // leaf blocks may not: griddepcontrol.wait precedes the first one.
-        if (lane == 0) {
-            for (int q = 0; q < my_pairs; ++q) {
-                const int p = (int)blockIdx.x + q * G;
-                const int g = p / P.NT, t = p - g * P.NT;
-                const int buf = q & 1;
-                unsigned char* meta = smem_raw + L.meta + (size_t)buf * L.meta_bytes;
-                // tile boundaries (independent loads, one round trip, requested before the wait for the buffers)
-                const int n0 = __ldg(P.tile_node_lo + t), n1 = __ldg(P.tile_node_lo + t + 1);
-                const int er0 = __ldg(P.ell_row_ptr + t), er1 = __ldg(P.ell_row_ptr + t + 1);
-                const int ec0 = __ldg(P.ell_chunk_ptr + t), ec1 = __ldg(P.ell_chunk_ptr + t + 1);
-                const int pc0 = __ldg(P.piece_ptr + t), pc1 = __ldg(P.piece_ptr + t + 1);
-                mbar_wait(pairEmpty + buf, ((unsigned)(q >> 1) & 1u) ^ 1u);  // the pair two back has been drained
-                PairHdr* h = reinterpret_cast<PairHdr*>(meta + L.hdr);
-                h->t = t; h->g = g; h->n0 = n0; h->n1 = n1; h->er0 = er0; h->ec0 = ec0; h->nchunks = ec1 - ec0;
-                h->pc0 = pc0; h->pc1 = pc1;
-                const int ea = ec0 & ~1, na = n0 & ~7;
-                const unsigned lb = (unsigned)T * (unsigned)B;
-                const unsigned tb = (unsigned)(er1 - er0) * 64u, db = (unsigned)((ec1 - ea + 1) >> 1) * 16u;
-                const unsigned sb = (unsigned)((n1 - na + 7) >> 3) * 16u;
-                mbar_expect_tx(pairFull + buf, lb + tb + db + sb);
-                if (tb) bulk_g2s(meta + L.terms, P.ell_terms + (size_t)er0 * 32, tb, pairFull + buf);
-                if (db) bulk_g2s(meta + L.desc, P.ell_desc + ea, db, pairFull + buf);
-                bulk_g2s(meta + L.slots, P.node_slot + na, sb, pairFull + buf);
-                if (q == 0) { pdl_wait(); pdl_trigger(); }  // z comes from permute_kernel
-                bulk_g2s(smem_raw + L.leaf + (size_t)buf * L.leaf_bytes, A.z + ((size_t)g * P.ZG + (size_t)t * T) * R, lb, pairFull + buf);
-                if (q == 0) GT_PTRACE(true, kTraceItems - 1, 0);
+        // fetch_pair(q, blocking): lane 0 only.  Returns false (nothing issued) when the buffer of pair q is still in
+        // use and blocking is false.
+        auto fetch_pair = [&](int q, bool blocking) -> bool {
+            const int buf = q & 1;
+            const unsigned par = ((unsigned)(q >> 1) & 1u) ^ 1u;
+            if (!blocking && !mbar_test(pairEmpty + buf, par)) return false;
+            const int p = (int)blockIdx.x + q * G;
+            const int g = p / P.NT, t = p - g * P.NT;
+            unsigned char* meta = smem_raw + L.meta + (size_t)buf * L.meta_bytes;
+            // tile boundaries (independent loads, one round trip, requested before the wait for the buffers)
+            const int n0 = __ldg(P.tile_node_lo + t), n1 = __ldg(P.tile_node_lo + t + 1);
+            const int er0 = __ldg(P.ell_row_ptr + t), er1 = __ldg(P.ell_row_ptr + t + 1);
+            const int ec0 = __ldg(P.ell_chunk_ptr + t), ec1 = __ldg(P.ell_chunk_ptr + t + 1);
+            const int pc0 = __ldg(P.piece_ptr + t), pc1 = __ldg(P.piece_ptr + t + 1);
+            mbar_wait(pairEmpty + buf, par);  // the pair two back has been drained
+            PairHdr* h = reinterpret_cast<PairHdr*>(meta + L.hdr);
+            h->t = t; h->g = g; h->n0 = n0; h->n1 = n1; h->er0 = er0; h->ec0 = ec0; h->nchunks = ec1 - ec0;
+            h->pc0 = pc0; h->pc1 = pc1;
+            const int ea = ec0 & ~1, na = n0 & ~7;
+            const unsigned lb = (unsigned)T * (unsigned)B;
+            const unsigned tb = (unsigned)(er1 - er0) * 64u, db = (unsigned)((ec1 - ea + 1) >> 1) * 16u;
+            const unsigned sb = (unsigned)((n1 - na + 7) >> 3) * 16u;
+            mbar_expect_tx(pairFull + buf, lb + tb + db + sb);
+            if (tb) bulk_g2s(meta + L.terms, P.ell_terms + (size_t)er0 * 32, tb, pairFull + buf);
+            if (db) bulk_g2s(meta + L.desc, P.ell_desc + ea, db, pairFull + buf);
+            bulk_g2s(meta + L.slots, P.node_slot + na, sb, pairFull + buf);
+            if (q == 0) { pdl_wait(); pdl_trigger(); }  // z comes from the previous launch (permute_kernel or a rider)
+            bulk_g2s(smem_raw + L.leaf + (size_t)buf * L.leaf_bytes, A.z + ((size_t)g * P.ZG + (size_t)t * T) * R, lb, pairFull + buf);
+            if (q == 0) GT_PTRACE(true, kTraceItems - 1, 0);
+            return true;
+        };
+        int q_next = 0;  // lane 0: next pair to fetch
+        if (A.ride_rows > 0) {
+            // ---- rider (see ride_move): this warp's units are blockIdx.x, blockIdx.x + G, ... of the next launch's rows
+            uint64_t* rideFull = bars + 8;  // [kRideStages]
+            unsigned char* stage0 = smem_raw + L.ride;
+            const int in_size = A.in_type == GT_F64 ? 8 : (A.in_type == GT_F32 ? 4 : 2);
+            const int UP = ride_unit_positions(in_size, R);
+            const int V = (int)P.V;
+            const int units_per_group = (V + UP - 1) / UP;
+            const int total_units = ((A.ride_rows + R - 1) / R) * units_per_group;
+            const int my_units = (int)blockIdx.x < total_units ? (total_units - (int)blockIdx.x + G - 1) / G : 0;
+            const bool log_input = A.log_input != 0;
+            if (lane == 0) fetch_pair(q_next++, true);  // the first pair; executes griddepcontrol.wait
+            pdl_wait();  // every lane: ride_z was read by the launch before the previous one; the rows may be its output
+            auto unit_of = [&](int i, int& g, int& v0, int& ntok) {
+                const int u = (int)blockIdx.x + i * G;
+                g = u / units_per_group;
+                v0 = (u - g * units_per_group) * UP;
+                ntok = min(UP, V - v0);
+            };
+            auto row_ptr = [&](int g, int r, int v0) {
+                return static_cast<const unsigned char*>(A.ride_ws) + ((size_t)min(g * R + r, A.ride_rows - 1) * A.ld_ws + v0) * in_size;
+            };
+            auto fill = [&](int i) {  // lane 0: request unit i into its stage
+                int g, v0, ntok;
+                unit_of(i, g, v0, ntok);
+                unsigned char* st = stage0 + (size_t)(i % kRideStages) * kRideStageBytes;
+                uint64_t* bar = rideFull + (i % kRideStages);
+                const unsigned nb = (unsigned)(ntok * in_size) & ~15u, db = ((unsigned)ntok * 4u + 15u) & ~15u;
+                mbar_expect_tx(bar, R * nb + db);
+                if (nb)
+                    for (int r = 0; r < R; ++r) bulk_g2s(st + (size_t)r * UP * in_size, row_ptr(g, r, v0), nb, bar);
+                bulk_g2s(st + kRideRowBytes, P.leaf_dest + v0, db, bar);
+            };
+            // HBM reads take microseconds while the output stores saturate the memory system: the row segments are requested
+            // into L2 kRideAhead units ahead, so that the stage fills are L2 hits
+            auto prefetch = [&](int i) {  // lane 0
+                int g, v0, ntok;
+                unit_of(i, g, v0, ntok);
+                const unsigned nb = (unsigned)(ntok * in_size) & ~15u;
+                if (nb)
+                    for (int r = 0; r < R; ++r) bulk_prefetch_l2(row_ptr(g, r, v0), nb);
+            };
+            if (lane == 0) {
+                for (int i = 0; i < kRideAhead && i < my_units; ++i) prefetch(i);
+                for (int i = 0; i < kRideStages && i < my_units; ++i) fill(i);
             }
+            for (int i = 0; i < my_units; ++i) {
+                uint64_t* bar = rideFull + (i % kRideStages);
+                const unsigned par = (unsigned)(i / kRideStages) & 1u;
+                while (!mbar_test(bar, par)) {  // meanwhile the tile work's fetches keep their priority
+                    if (lane == 0 && q_next < my_pairs && fetch_pair(q_next, false)) ++q_next;
+                    __nanosleep(64);
+                }
+                GT_PTRACE(lane == 0, i, 5);  // unit i has landed
+                int g, v0, ntok;
+                unit_of(i, g, v0, ntok);
+                const unsigned char* st = stage0 + (size_t)(i % kRideStages) * kRideStageBytes;
+                VT* zg = A.ride_z + (size_t)g * P.ZG * R;
+                const int n_bulk = (int)(((unsigned)(ntok * in_size) & ~15u) / (unsigned)in_size);
+                for (int p0 = 0; p0 < ntok; p0 += 128) {
+                    if (dbg != 22)
+                    GT_IN_TYPE_SWITCH(A.in_type, {
+                        const IN_T* grow[R];
+                        for (int r = 0; r < R; ++r) grow[r] = reinterpret_cast<const IN_T*>(row_ptr(g, r, v0));
+                        ride_move<VT, IN_T, R>(st, UP, grow, n_bulk, p0, ntok, zg, log_input, lane);
+                    });
+                    if (lane == 0 && q_next < my_pairs && fetch_pair(q_next, false)) ++q_next;
+                    __syncwarp();
+                }
+                GT_PTRACE(lane == 0, i, 6);  // unit i has been moved
+                if (lane == 0) {
+                    if (i + kRideStages < my_units) fill(i + kRideStages);  // every lane is done with the stage
+                    if (i + kRideAhead < my_units) prefetch(i + kRideAhead);
+                }
+            }
+            GT_PTRACE(lane == 0, kTraceItems - 1, 1);  // rider done
         }
+        if (lane == 0)
+            for (; q_next < my_pairs; ++q_next) fetch_pair(q_next, true);
+        GT_PTRACE(lane == 0, kTraceItems - 1, 2);  // all pairs requested
     } else {
         if (warp < kComputeWarps) {
             // =========================== compute group ===========================================================
@@ -838,7 +984,7 @@ static DevicePlan* upload_plan(const Layout& L, const Plan& P, int device) {
     return d;
 }
 
-template <typename VT, int R> static size_t mass_smem(const PlanView& v) { return MassSmem(v, (int)sizeof(VT) * R).total; }
+template <typename VT, int R> static size_t mass_smem(const PlanView& v, bool with_ride) { return MassSmem(v, (int)sizeof(VT) * R, with_ride).total; }
 
 // Opt in to > 48 KB dynamic shared memory once per (kernel, device, size): the attribute call is kept off the
 // steady-state launch path (and out of CUDA graph captures).  Keyed by the kernel's address: instantiations
@@ -861,22 +1007,35 @@ template <typename K> static cudaError_t allow_smem(K kernel, size_t bytes) {
     return allow_smem_impl(reinterpret_cast<const void*>(kernel), bytes);
 }
 
-// Scratch layout for one chunk of `rows` rows (RG = row groups of R):
-//   z [RG][ZG slots][R] VT | part_sum [rows][n_pieces] VT | part_max likewise
+// Scratch layout for chunks of up to `cap` rows (RG = row groups of R):
+//   z[0], z[1]: [RG][ZG slots][R] VT each | part_sum [cap][n_pieces] VT | part_max likewise
+// Two staging buffers: chunk c of a call is reduced out of one while the rider of its tile kernel stages chunk c + 1
+// (or the first chunk of the caller's next batch) into the other.  The layout depends on the workspace size only, so
+// consecutive calls on one workspace agree on where the buffers are.
+constexpr int64_t kMaxChunkRows = 64;  // two staging buffers of 64 rows at 128k tokens (2 x 34 MB) stay in the 126 MB L2
 template <typename VT, int R> struct Scratch {
-    VT* z; VT* part_sum; VT* part_max;
+    VT* z[2]; VT* part_sum; VT* part_max;
     static size_t pad(size_t b) { return (b + 255) & ~size_t(255); }
     static size_t z_bytes(const PlanView& v, int64_t rows) { return pad((size_t)((rows + R - 1) / R) * (size_t)v.ZG * R * sizeof(VT)); }
-    Scratch(const PlanView& v, void* base, int64_t rows) {
+    Scratch(const PlanView& v, void* base, int64_t cap) {
         char* p = static_cast<char*>(base);
-        z = reinterpret_cast<VT*>(p);
-        p += z_bytes(v, rows);
+        for (int i = 0; i < 2; ++i) { z[i] = reinterpret_cast<VT*>(p); p += z_bytes(v, cap); }
         part_sum = reinterpret_cast<VT*>(p);
-        p += pad((size_t)rows * v.n_pieces * sizeof(VT));
+        p += pad((size_t)cap * v.n_pieces * sizeof(VT));
         part_max = reinterpret_cast<VT*>(p);
     }
-    static size_t total(const PlanView& v, int64_t rows) {
-        return z_bytes(v, rows) + 2 * pad((size_t)rows * v.n_pieces * sizeof(VT));
+    static size_t total(const PlanView& v, int64_t cap) {
+        return 2 * z_bytes(v, cap) + 2 * pad((size_t)cap * v.n_pieces * sizeof(VT));
+    }
+    // rows per chunk a workspace of `bytes` holds (0: not even one row)
+    static int64_t capacity(const PlanView& v, size_t bytes) {
+        int64_t lo = 0, hi = kMaxChunkRows;
+        if (const char* e = getenv("GT_CHUNK_ROWS")) { const long x = atol(e); if (x > 0) hi = x; }
+        while (lo < hi) {  // total() is monotone in the row count
+            const int64_t mid = (lo + hi + 1) / 2;
+            if (total(v, mid) <= bytes) lo = mid; else hi = mid - 1;
+        }
+        return lo;
     }
 };
 
@@ -889,6 +1048,8 @@ static int resident_ctas(const void* kernel, int threads, size_t smem) {
     auto it = cache.find(key);
     if (it != cache.end()) return it->second;
     int n = 0;
+    // the query honours the kernel's dynamic shared-memory limit: raise it first, or a size above it reports 0
+    if (allow_smem_impl(kernel, smem) != cudaSuccess) (void)cudaGetLastError();
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, threads, smem) != cudaSuccess || n < 1) {
         (void)cudaGetLastError();
         n = 1;
@@ -910,9 +1071,24 @@ static int sm_count() {
     return n;
 }
 
+// Can the tile kernel's rider stage rows of this type / alignment (bulk copies need 16-byte aligned row segments)?
+template <typename VT, int R> static bool ride_ok(const PlanView& v, const void* ws, int in_type, int64_t ld_ws) {
+    static const bool disabled = []() { const char* e = getenv("GT_NO_RIDE"); return e && *e && atoi(e) != 0; }();
+    if (disabled || !ws) return false;
+    const size_t in_size = in_type == GT_F64 ? 8 : in_type == GT_F32 ? 4 : 2;
+    if ((reinterpret_cast<uintptr_t>(ws) & 15) || ((size_t)ld_ws * in_size & 15)) return false;
+    // the rider's stages must not cost the kernel a resident CTA
+    const size_t with = mass_smem<VT, R>(v, true), without = mass_smem<VT, R>(v, false);
+    if (with > 227 * 1024) return false;
+    return resident_ctas(reinterpret_cast<const void*>(mass_kernel<VT, R>), kThreads, with) ==
+           resident_ctas(reinterpret_cast<const void*>(mass_kernel<VT, R>), kThreads, without);
+}
+
+// One chunk: [permute ->] tile kernel [+ rider staging `ride_rows` rows at `ride_ws` into `ride_z`] -> span kernel.
 template <typename VT, int R>
-static int launch_mass(const PlanView& v, const void* ws, int in_type, int64_t ld_ws, bool log_input, const Scratch<VT, R>& sc,
-                       VT* out_sum, VT* out_max, int64_t ld_out, int rows, unsigned ops, unsigned phases, cudaStream_t st) {
+static int launch_mass(const PlanView& v, const void* ws, int in_type, int64_t ld_ws, bool log_input, VT* z, const Scratch<VT, R>& sc,
+                       VT* out_sum, VT* out_max, int64_t ld_out, int rows, unsigned ops, unsigned phases, const void* ride_ws,
+                       int ride_rows, VT* ride_z, cudaStream_t st) {
     if (v.NT == 0) {  // empty vocabulary: the root is the only node and has no mass
         for (VT* out : {out_sum, out_max})
             if (out) GT_CUDA(cudaMemset2DAsync(out, (size_t)ld_out * sizeof(VT), 0, (size_t)v.N * sizeof(VT), (size_t)rows, st));
@@ -920,9 +1096,10 @@ static int launch_mass(const PlanView& v, const void* ws, int in_type, int64_t l
     }
     MassArgs<VT> A;
     A.ws = ws; A.in_type = in_type; A.log_input = log_input ? 1 : 0; A.ld_ws = ld_ws;
-    A.z = sc.z;
+    A.z = z;
     A.out_sum = out_sum; A.out_max = out_max; A.part_sum = sc.part_sum; A.part_max = sc.part_max;
     A.ld_out = ld_out; A.n_rows = rows; A.ops = ops;
+    A.ride_ws = ride_ws; A.ride_rows = ride_ws ? ride_rows : 0; A.ride_z = ride_z;
     const int RG = (rows + R - 1) / R;
     if (phases & GT_FLAG_PHASE_PERMUTE) {  // one warp per unit of 128 (fp64 rows: 64) positions of a row group
         const int64_t UT = in_type == GT_F64 ? kUnitTokens / 2 : kUnitTokens;
@@ -931,7 +1108,7 @@ static int launch_mass(const PlanView& v, const void* ws, int in_type, int64_t l
         GT_CUDA(launch_pdl(permute_kernel<VT, R>, dim3((unsigned)pgrid), dim3(kPermThreads), 0, st, v, A, (unsigned)units));
     }
     if (phases & GT_FLAG_PHASE_TILE) {
-        const size_t smem = mass_smem<VT, R>(v);
+        const size_t smem = mass_smem<VT, R>(v, A.ride_rows > 0);
         if (smem > 227 * 1024) {
             set_error("tile plan needs %zu bytes of shared memory per CTA (limit 232448): use a smaller tile", smem);
             return GT_ERR_LIMIT;
@@ -951,23 +1128,17 @@ static int launch_mass(const PlanView& v, const void* ws, int in_type, int64_t l
     return GT_OK;
 }
 
+// A batch is reduced in chunks of what the caller's scratch stages (at most kMaxChunkRows rows; a partial row group is
+// legal: the kernels alias the missing rows to the last valid one).  Chunk c lives in staging buffer (first + c) & 1:
+// the first chunk is staged by permute_kernel unless the previous call already did it (*stage_slot >= 0 on entry);
+// every later chunk -- and the first chunk of `next_ws`, the caller's next batch -- is staged by the rider of the tile
+// kernel before it whenever the rows qualify (ride_ok), by permute_kernel otherwise.
 template <typename VT, int R>
 static int reduce_typed(const PlanView& v, const void* ws, int in_type, int64_t n_rows, int64_t ld_ws, void* out_sum,
-                        void* out_max, int64_t ld_out, unsigned ops, unsigned flags, void* workspace,
-                        size_t workspace_bytes, cudaStream_t st) {
-    // rows per launch: what the caller's scratch can stage (whole row groups when it holds at least one; a partial row
-    // group is legal: the kernels alias the missing rows to the last valid one)
-    int64_t chunk = std::min<int64_t>(n_rows, 32768);
-    if (Scratch<VT, R>::total(v, chunk) > workspace_bytes) {
-        const size_t per_group = (size_t)v.ZG * R * sizeof(VT) + 2 * (size_t)R * v.n_pieces * sizeof(VT) + 1024;
-        chunk = std::min<int64_t>(chunk, (int64_t)(workspace_bytes / per_group) * R);
-        while (chunk > 0 && Scratch<VT, R>::total(v, chunk) > workspace_bytes) chunk -= R;
-        if (chunk <= 0) {  // less than a row group: row by row
-            chunk = R - 1;
-            while (chunk > 0 && Scratch<VT, R>::total(v, chunk) > workspace_bytes) --chunk;
-        }
-    }
-    if (chunk < 1) {
+                        void* out_max, int64_t ld_out, unsigned ops, unsigned flags, const void* next_ws, int64_t next_rows,
+                        int64_t next_ld_ws, int32_t* stage_slot, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+    const int64_t cap = Scratch<VT, R>::capacity(v, workspace_bytes);
+    if (cap < 1) {
         set_error("workspace too small: %zu bytes given, one row needs %zu", workspace_bytes, Scratch<VT, R>::total(v, 1));
         return GT_ERR_STATE;
     }
@@ -976,17 +1147,45 @@ static int reduce_typed(const PlanView& v, const void* ws, int in_type, int64_t 
         return GT_ERR_ARG;
     }
     const bool log_input = (flags & GT_FLAG_LOG_INPUT) != 0;
-    const unsigned phases = (flags & GT_FLAG_PHASE_MASK) ? (flags & GT_FLAG_PHASE_MASK) : GT_FLAG_PHASE_MASK;
+    const unsigned all = GT_FLAG_PHASE_MASK;
+    const unsigned phases = (flags & GT_FLAG_PHASE_MASK) ? (flags & GT_FLAG_PHASE_MASK) : all;
     const size_t in_size = in_type == GT_F64 ? 8 : in_type == GT_F32 ? 4 : 2;
-    for (int64_t r0 = 0; r0 < n_rows; r0 += chunk) {
-        const int rows = (int)std::min<int64_t>(chunk, n_rows - r0);
-        const Scratch<VT, R> sc(v, workspace, rows);
-        const void* wsr = static_cast<const char*>(ws) + (size_t)r0 * ld_ws * in_size;
-        const int rc = launch_mass<VT, R>(v, wsr, in_type, ld_ws, log_input, sc,
+    const Scratch<VT, R> sc(v, workspace, cap);
+    int slot = 0;
+    bool staged = false;  // the chunk about to be reduced already sits in z[slot]
+    if (stage_slot && (*stage_slot == 0 || *stage_slot == 1) && phases == all) { slot = *stage_slot; staged = true; }
+    if (stage_slot) *stage_slot = -1;
+    const bool pipelined = phases == all && v.NT > 0;
+    for (int64_t r0 = 0; r0 < n_rows; r0 += cap) {
+        const int rows = (int)std::min<int64_t>(cap, n_rows - r0);
+        const char* wsr = static_cast<const char*>(ws) + (size_t)r0 * ld_ws * in_size;
+        // what the rider of this chunk's tile kernel stages
+        const void* ride_ws = nullptr;
+        int ride_rows = 0;
+        bool ride_is_next_call = false;
+        if (pipelined) {
+            if (r0 + cap < n_rows) {
+                ride_ws = wsr + (size_t)cap * ld_ws * in_size;
+                ride_rows = (int)std::min<int64_t>(cap, n_rows - r0 - cap);
+                if (!ride_ok<VT, R>(v, ride_ws, in_type, ld_ws)) ride_ws = nullptr;
+            } else if (next_ws && next_rows > 0 && stage_slot && next_ld_ws == ld_ws) {
+                ride_ws = next_ws;
+                ride_rows = (int)std::min<int64_t>(cap, next_rows);
+                ride_is_next_call = true;
+                if (!ride_ok<VT, R>(v, ride_ws, in_type, ld_ws)) ride_ws = nullptr;
+            }
+        }
+        const unsigned ph = staged ? (phases & ~(unsigned)GT_FLAG_PHASE_PERMUTE) : phases;
+        const int rc = launch_mass<VT, R>(v, wsr, in_type, ld_ws, log_input, sc.z[slot], sc,
                                           (ops & GT_OP_SUM) ? static_cast<VT*>(out_sum) + (size_t)r0 * ld_out : nullptr,
                                           (ops & GT_OP_MAX) ? static_cast<VT*>(out_max) + (size_t)r0 * ld_out : nullptr, ld_out,
-                                          rows, ops, phases, st);
+                                          rows, ops, ph, ride_ws, ride_rows, sc.z[slot ^ 1], st);
         if (rc != GT_OK) return rc;
+        staged = ride_ws != nullptr;
+        if (staged) {
+            slot ^= 1;
+            if (ride_is_next_call) *stage_slot = slot;
+        }
     }
     return GT_OK;
 }
@@ -1106,14 +1305,15 @@ size_t gt_workspace_bytes(const gt_trie* t, int64_t max_rows) {
     return gt::Scratch<double, 2>::total(v, max_rows) + 256;
 }
 
-int gt_weight_reduce(const gt_trie* t, const void* ws, int in_type, int64_t n_rows, int64_t ld_ws, void* out_sum,
-                     void* out_max, int out_type, int64_t ld_out, unsigned ops, unsigned flags, void* workspace,
-                     size_t workspace_bytes, gt_stream stream) {
+int gt_weight_reduce_next(const gt_trie* t, const void* ws, int in_type, int64_t n_rows, int64_t ld_ws, void* out_sum,
+                          void* out_max, int out_type, int64_t ld_out, unsigned ops, unsigned flags, const void* next_ws,
+                          int64_t next_rows, int64_t next_ld_ws, int32_t* stage_slot, void* workspace, size_t workspace_bytes,
+                          gt_stream stream) {
     if (!t) { gt::set_error("gt_weight_reduce: null trie"); return GT_ERR_ARG; }
-    if (n_rows < 0 || !(ops & (GT_OP_SUM | GT_OP_MAX)) || (ops & ~(unsigned)(GT_OP_SUM | GT_OP_MAX))) {
+    if (n_rows < 0 || next_rows < 0 || !(ops & (GT_OP_SUM | GT_OP_MAX)) || (ops & ~(unsigned)(GT_OP_SUM | GT_OP_MAX))) {
         gt::set_error("gt_weight_reduce: bad n_rows / ops"); return GT_ERR_ARG;
     }
-    if (n_rows == 0) return GT_OK;
+    if (n_rows == 0) return GT_OK;  // *stage_slot is left as it is: nothing was consumed or staged
     if ((t->layout.V > 0 && !ws) || ((ops & GT_OP_SUM) && !out_sum) || ((ops & GT_OP_MAX) && !out_max)) {
         gt::set_error("gt_weight_reduce: null data pointer"); return GT_ERR_ARG;
     }
@@ -1121,7 +1321,7 @@ int gt_weight_reduce(const gt_trie* t, const void* ws, int in_type, int64_t n_ro
         gt::set_error("gt_weight_reduce: output row stride %lld exceeds 2^28 elements", (long long)ld_out);
         return GT_ERR_LIMIT;
     }
-    if (ld_ws < t->layout.V || ld_out < t->layout.N) {
+    if (ld_ws < t->layout.V || ld_out < t->layout.N || (next_ws && next_rows > 0 && next_ld_ws < t->layout.V)) {
         gt::set_error("gt_weight_reduce: row stride smaller than row length (ld_ws=%lld V=%lld ld_out=%lld N=%lld)",
                       (long long)ld_ws, (long long)t->layout.V, (long long)ld_out, (long long)t->layout.N);
         return GT_ERR_ARG;
@@ -1133,14 +1333,21 @@ int gt_weight_reduce(const gt_trie* t, const void* ws, int in_type, int64_t n_ro
     const gt::PlanView& v = it->second->view;
     if (!workspace || (reinterpret_cast<uintptr_t>(workspace) & 255)) { gt::set_error("gt_weight_reduce: workspace must be a 256-byte aligned device pointer"); return GT_ERR_ARG; }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-#define GT_REDUCE(VT, R) gt::reduce_typed<VT, R>(v, ws, in_type, n_rows, ld_ws, out_sum, out_max, ld_out, ops, flags, \
-                                                workspace, workspace_bytes, st)
+#define GT_REDUCE(VT, R) gt::reduce_typed<VT, R>(v, ws, in_type, n_rows, ld_ws, out_sum, out_max, ld_out, ops, flags, next_ws, next_rows, \
+                                                next_ld_ws, stage_slot, workspace, workspace_bytes, st)
     // 16-byte value slots: four fp32 rows or two fp64 rows per work item
     if (out_type == GT_F32) return GT_REDUCE(float, 4);
     if (out_type == GT_F64) return GT_REDUCE(double, 2);
 #undef GT_REDUCE
     gt::set_error("gt_weight_reduce: output type must be GT_F32 or GT_F64");
     return GT_ERR_ARG;
+}
+
+int gt_weight_reduce(const gt_trie* t, const void* ws, int in_type, int64_t n_rows, int64_t ld_ws, void* out_sum,
+                     void* out_max, int out_type, int64_t ld_out, unsigned ops, unsigned flags, void* workspace,
+                     size_t workspace_bytes, gt_stream stream) {
+    return gt_weight_reduce_next(t, ws, in_type, n_rows, ld_ws, out_sum, out_max, out_type, ld_out, ops, flags, nullptr, 0, 0, nullptr,
+                                 workspace, workspace_bytes, stream);
 }
 
 int gt_gather_nodes(const void* mass, int type, int64_t n_rows, int64_t n_nodes, int64_t ld_mass, const int32_t* node_ids,
