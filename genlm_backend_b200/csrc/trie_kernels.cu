@@ -335,14 +335,9 @@ constexpr int kTraceCtas = 512, kTraceItems = 32, kTraceEvents = 12;
 
 // Shared-memory carve-up of mass_kernel (all sections 128-byte aligned: the bank group of a slot is slot % 8 in
 // the leaf blocks and in the rest buffers alike).
-constexpr int kRideStages = 3;            // staged units of the rider (see below) per CTA
-constexpr int kRideAhead = 10;            // units requested into L2 ahead of their stage fill
-constexpr int kRideRowBytes = 4096;       // row data of one staged unit: R rows x unit positions x element size
-constexpr int kRideMaxUnit = 256;         // positions per unit at most (their leaf_dest entries: 1 KB)
-constexpr int kRideStageBytes = kRideRowBytes + kRideMaxUnit * 4;
 struct MassSmem {
-    size_t leaf, leaf_bytes, rest, rest_bytes, meta, meta_bytes, terms, desc, slots, hdr, bars, ride, total;
-    __host__ __device__ MassSmem(const PlanView& P, int slot_bytes, bool with_ride) {
+    size_t leaf, leaf_bytes, rest, rest_bytes, meta, meta_bytes, terms, desc, slots, hdr, bars, total;
+    __host__ __device__ MassSmem(const PlanView& P, int slot_bytes) {
         auto up = [](size_t x) { return (x + 127) & ~size_t(127); };
         size_t o = 0;
         leaf_bytes = up((size_t)P.T * slot_bytes);
@@ -358,7 +353,6 @@ struct MassSmem {
         meta_bytes = m;
         meta = o; o += 2 * meta_bytes;
         bars = o; o += 128;
-        ride = o; o += with_ride ? (size_t)kRideStages * kRideStageBytes : 0;
         total = o;
     }
 };
@@ -431,45 +425,60 @@ __device__ __forceinline__ void permute_unit(const PlanView& P, const MassArgs<V
         default: { using IN_T = __nv_bfloat16; __VA_ARGS__; } break;     \
     }
 
-// ---- rider: the permute of the *next* launch's rows, done by the tile kernel's producer warp --------------------------
+// ---- rider: the permute of the *next* launch's rows, done inside the tile kernel ----------------------------------------
 // The tile kernel is bound by how fast its output stores drain to HBM; its producer warp issues a few bulk copies per
 // pair and is otherwise idle.  When the caller knows the rows of the next launch (the next chunk of a large batch, or
-// the next batch of a stream: gt_weight_reduce_next), that warp stages them into the other staging buffer meanwhile:
-// HBM reads and L2-resident scattered stores riding under an HBM-write-bound kernel.  The kernel boundary publishes
-// the staged rows, so no fence or flag is needed.  Unit = (row group, kRideUnit positions): the R row segments and
-// their leaf_dest entries arrive in shared memory by bulk copies (two stages, one unit ahead); the warp then moves 32
-// positions per step: R conflict-free shared-memory loads, one 16-byte scattered store.  Needs 16-byte aligned rows.
-__host__ __device__ inline int ride_unit_positions(int in_size, int R) {
-    const int u = kRideRowBytes / (R * in_size);
-    return u < kRideMaxUnit ? u : kRideMaxUnit;
-}
-// positions [p0, min(p0 + 128, ntok)) of a staged unit: lane l takes p0 + l + 32 j, j < 4, all loads before the stores
-template <typename VT, typename IN_T, int R>
-__device__ __forceinline__ void ride_move(const unsigned char* stage, int unit_pos, const IN_T* const (&grow)[R], int n_bulk, int p0, int ntok,
-                                          VT* zg, bool log_input, int lane) {
-    using RV = RowVec<VT, R>;
-    const IN_T* srow = reinterpret_cast<const IN_T*>(stage);
-    const int* sdest = reinterpret_cast<const int*>(stage + kRideRowBytes);
-    int d[4];
-    IN_T x[4][R];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const int p = min(p0 + lane + 32 * j, ntok - 1);
-        d[j] = sdest[p];
-#pragma unroll
-        for (int r = 0; r < R; ++r)  // the last few positions of a row whose length is not a multiple of 16 bytes are not covered by the bulk copy
-            x[j][r] = p < n_bulk ? srow[r * unit_pos + p] : grow[r][p];
+// the next batch of a stream: gt_weight_reduce_next), that warp stages them into the other staging buffer meanwhile --
+// HBM reads and L2-resident scattered stores riding under an HBM-write-bound kernel -- and every other warp of the
+// CTA joins in once it has finished its own share of the tile work.  The kernel boundary publishes the staged rows:
+// no fence or flag.  A CTA's units (permute_unit's) are blockIdx.x, blockIdx.x + grid, ...; its warps claim them from
+// a shared-memory counter.  HBM reads take microseconds while the output stores saturate the memory system, so a
+// unit's row segments are requested into L2 kRideAhead claims before they are loaded.
+constexpr int kRideAhead = 12;
+template <typename VT, int R> struct Rider {
+    const PlanView& P;
+    MassArgs<VT> RA;  // the staging job phrased as a permute launch
+    int* next;        // shared-memory claim counter
+    int my_units, n_units, G, UT, in_size;
+    __device__ __forceinline__ Rider(const PlanView& P_, const MassArgs<VT>& A, int* next_, int grid) : P(P_), RA(A), next(next_), G(grid) {
+        RA.ws = A.ride_ws; RA.n_rows = A.ride_rows; RA.z = A.ride_z;
+        UT = perm_unit_tokens_rt(A.in_type);
+        in_size = A.in_type == GT_F64 ? 8 : (A.in_type == GT_F32 ? 4 : 2);
+        n_units = (int)((P.V + UT - 1) / UT);
+        const int total = ((A.ride_rows + R - 1) / R) * n_units;
+        my_units = (int)blockIdx.x < total ? (total - (int)blockIdx.x + G - 1) / G : 0;
     }
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        if (p0 + lane + 32 * j < ntok) {
-            RV y;
-#pragma unroll
-            for (int r = 0; r < R; ++r) y.v[r] = convert_in<VT, IN_T>(x[j][r], log_input);
-            y.store(zg + (size_t)d[j] * R);
+    __device__ __forceinline__ int claim(int lane) const {
+        int i = 0;
+        if (lane == 0) i = atomicAdd(next, 1);
+        return __shfl_sync(0xffffffffu, i, 0);
+    }
+    // lanes 0 .. 4R-1: one 128-byte line each of unit i's R row segments
+    __device__ __forceinline__ void prefetch(int i, int lane) const {
+        if (i >= my_units || lane >= 4 * R) return;
+        const unsigned w = blockIdx.x + (unsigned)i * (unsigned)G;
+        const int g = (int)(w / (unsigned)n_units), v0 = (int)(w - (unsigned)g * (unsigned)n_units) * UT;
+        const int r = lane >> 2;
+        const int e = v0 + (lane & 3) * (128 / in_size);  // first element of this lane's line
+        if (e < (int)P.V) {
+            const unsigned char* p = static_cast<const unsigned char*>(RA.ws) + ((size_t)min(g * R + r, RA.n_rows - 1) * RA.ld_ws + e) * in_size;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
         }
     }
-}
+    __device__ __forceinline__ void unit(int i, int lane) const {
+        const unsigned w = blockIdx.x + (unsigned)i * (unsigned)G;
+        GT_IN_TYPE_SWITCH(RA.in_type, (permute_unit<VT, IN_T, R>(P, RA, w, n_units, lane)));
+    }
+    // a warp that has nothing else left to do: units until none is left
+    __device__ __noinline__ void help(int lane) const {
+        pdl_wait();
+        for (;;) {
+            const int i = claim(lane);
+            if (i >= my_units) break;
+            unit(i, lane);
+        }
+    }
+};
 
 constexpr int kPermThreads = 256;
 template <typename VT, int R>
@@ -568,12 +577,13 @@ __global__ void __launch_bounds__(kThreads, 2) mass_kernel(PlanView P, MassArgs<
     constexpr int B = (int)sizeof(VT) * R;  // bytes per slot
     static_assert(B == 16, "value slots are 16 bytes");
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const MassSmem L(P, B, A.ride_rows > 0);
+    const MassSmem L(P, B);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + L.bars);
     uint64_t* pairFull = bars;       // [2]
     uint64_t* pairEmpty = bars + 2;  // [2]
     uint64_t* full = bars + 4;       // [2] rest buffer filled by the compute group
     uint64_t* empty = bars + 6;      // [2] rest buffer drained by the emit group
+    int* ride_next = reinterpret_cast<int*>(bars + 8);  // rider: next unit of this CTA to claim
 
     const int T = P.T;
     const int n_rows = A.n_rows;
@@ -591,7 +601,7 @@ __global__ void __launch_bounds__(kThreads, 2) mass_kernel(PlanView P, MassArgs<
         mbar_init(pairEmpty, kEmitThreads); mbar_init(pairEmpty + 1, kEmitThreads);
         mbar_init(full, kComputeThreads); mbar_init(full + 1, kComputeThreads);
         mbar_init(empty, kEmitThreads); mbar_init(empty + 1, kEmitThreads);
-        for (int i = 0; i < kRideStages; ++i) mbar_init(bars + 8 + i, 1);
+        *ride_next = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -634,79 +644,18 @@ __global__ void __launch_bounds__(kThreads, 2) mass_kernel(PlanView P, MassArgs<
         };
         int q_next = 0;  // lane 0: next pair to fetch
         if (A.ride_rows > 0) {
-            // ---- rider (see ride_move): this warp's units are blockIdx.x, blockIdx.x + G, ... of the next launch's rows
-            uint64_t* rideFull = bars + 8;  // [kRideStages]
-            unsigned char* stage0 = smem_raw + L.ride;
-            const int in_size = A.in_type == GT_F64 ? 8 : (A.in_type == GT_F32 ? 4 : 2);
-            const int UP = ride_unit_positions(in_size, R);
-            const int V = (int)P.V;
-            const int units_per_group = (V + UP - 1) / UP;
-            const int total_units = ((A.ride_rows + R - 1) / R) * units_per_group;
-            const int my_units = (int)blockIdx.x < total_units ? (total_units - (int)blockIdx.x + G - 1) / G : 0;
-            const bool log_input = A.log_input != 0;
+            // ---- rider: units claimed one at a time; between units lane 0 keeps the tile work's fetches going
+            const Rider<VT, R> rider(P, A, ride_next, G);
             if (lane == 0) fetch_pair(q_next++, true);  // the first pair; executes griddepcontrol.wait
             pdl_wait();  // every lane: ride_z was read by the launch before the previous one; the rows may be its output
-            auto unit_of = [&](int i, int& g, int& v0, int& ntok) {
-                const int u = (int)blockIdx.x + i * G;
-                g = u / units_per_group;
-                v0 = (u - g * units_per_group) * UP;
-                ntok = min(UP, V - v0);
-            };
-            auto row_ptr = [&](int g, int r, int v0) {
-                return static_cast<const unsigned char*>(A.ride_ws) + ((size_t)min(g * R + r, A.ride_rows - 1) * A.ld_ws + v0) * in_size;
-            };
-            auto fill = [&](int i) {  // lane 0: request unit i into its stage
-                int g, v0, ntok;
-                unit_of(i, g, v0, ntok);
-                unsigned char* st = stage0 + (size_t)(i % kRideStages) * kRideStageBytes;
-                uint64_t* bar = rideFull + (i % kRideStages);
-                const unsigned nb = (unsigned)(ntok * in_size) & ~15u, db = ((unsigned)ntok * 4u + 15u) & ~15u;
-                mbar_expect_tx(bar, R * nb + db);
-                if (nb)
-                    for (int r = 0; r < R; ++r) bulk_g2s(st + (size_t)r * UP * in_size, row_ptr(g, r, v0), nb, bar);
-                bulk_g2s(st + kRideRowBytes, P.leaf_dest + v0, db, bar);
-            };
-            // HBM reads take microseconds while the output stores saturate the memory system: the row segments are requested
-            // into L2 kRideAhead units ahead, so that the stage fills are L2 hits
-            auto prefetch = [&](int i) {  // lane 0
-                int g, v0, ntok;
-                unit_of(i, g, v0, ntok);
-                const unsigned nb = (unsigned)(ntok * in_size) & ~15u;
-                if (nb)
-                    for (int r = 0; r < R; ++r) bulk_prefetch_l2(row_ptr(g, r, v0), nb);
-            };
-            if (lane == 0) {
-                for (int i = 0; i < kRideAhead && i < my_units; ++i) prefetch(i);
-                for (int i = 0; i < kRideStages && i < my_units; ++i) fill(i);
-            }
-            for (int i = 0; i < my_units; ++i) {
-                uint64_t* bar = rideFull + (i % kRideStages);
-                const unsigned par = (unsigned)(i / kRideStages) & 1u;
-                while (!mbar_test(bar, par)) {  // meanwhile the tile work's fetches keep their priority
-                    if (lane == 0 && q_next < my_pairs && fetch_pair(q_next, false)) ++q_next;
-                    __nanosleep(64);
-                }
-                GT_PTRACE(lane == 0, i, 5);  // unit i has landed
-                int g, v0, ntok;
-                unit_of(i, g, v0, ntok);
-                const unsigned char* st = stage0 + (size_t)(i % kRideStages) * kRideStageBytes;
-                VT* zg = A.ride_z + (size_t)g * P.ZG * R;
-                const int n_bulk = (int)(((unsigned)(ntok * in_size) & ~15u) / (unsigned)in_size);
-                for (int p0 = 0; p0 < ntok; p0 += 128) {
-                    if (dbg != 22)
-                    GT_IN_TYPE_SWITCH(A.in_type, {
-                        const IN_T* grow[R];
-                        for (int r = 0; r < R; ++r) grow[r] = reinterpret_cast<const IN_T*>(row_ptr(g, r, v0));
-                        ride_move<VT, IN_T, R>(st, UP, grow, n_bulk, p0, ntok, zg, log_input, lane);
-                    });
-                    if (lane == 0 && q_next < my_pairs && fetch_pair(q_next, false)) ++q_next;
-                    __syncwarp();
-                }
-                GT_PTRACE(lane == 0, i, 6);  // unit i has been moved
-                if (lane == 0) {
-                    if (i + kRideStages < my_units) fill(i + kRideStages);  // every lane is done with the stage
-                    if (i + kRideAhead < my_units) prefetch(i + kRideAhead);
-                }
+            for (int i = 0; i < kRideAhead; ++i) rider.prefetch(i, lane);
+            for (;;) {
+                const int i = rider.claim(lane);
+                if (i >= rider.my_units) break;
+                rider.prefetch(i + kRideAhead, lane);
+                if (dbg != 22) rider.unit(i, lane);
+                if (lane == 0 && q_next < my_pairs && fetch_pair(q_next, false)) ++q_next;
+                __syncwarp();
             }
             GT_PTRACE(lane == 0, kTraceItems - 1, 1);  // rider done
         }
@@ -752,6 +701,7 @@ __global__ void __launch_bounds__(kThreads, 2) mass_kernel(PlanView P, MassArgs<
                     mbar_arrive(full + (k & 1));  // this thread's share of the value array is complete
                 }
             }
+            if (A.ride_rows > 0) Rider<VT, R>(P, A, ride_next, G).help(lane);
         } else if (warp < kProducerWarp) {
             // =========================== emit group ==============================================================
             const int gtid = threadIdx.x - kComputeThreads;
@@ -834,6 +784,7 @@ __global__ void __launch_bounds__(kThreads, 2) mass_kernel(PlanView P, MassArgs<
                 }
                 mbar_arrive(pairEmpty + buf);  // ... nor the pair's leaf block and metadata
             }
+            if (A.ride_rows > 0) Rider<VT, R>(P, A, ride_next, G).help(lane);
         }
     }
 
@@ -984,7 +935,7 @@ static DevicePlan* upload_plan(const Layout& L, const Plan& P, int device) {
     return d;
 }
 
-template <typename VT, int R> static size_t mass_smem(const PlanView& v, bool with_ride) { return MassSmem(v, (int)sizeof(VT) * R, with_ride).total; }
+template <typename VT, int R> static size_t mass_smem(const PlanView& v) { return MassSmem(v, (int)sizeof(VT) * R).total; }
 
 // Opt in to > 48 KB dynamic shared memory once per (kernel, device, size): the attribute call is kept off the
 // steady-state launch path (and out of CUDA graph captures).  Keyed by the kernel's address: instantiations
@@ -1071,17 +1022,10 @@ static int sm_count() {
     return n;
 }
 
-// Can the tile kernel's rider stage rows of this type / alignment (bulk copies need 16-byte aligned row segments)?
-template <typename VT, int R> static bool ride_ok(const PlanView& v, const void* ws, int in_type, int64_t ld_ws) {
+// The rider (staging of the next rows inside the tile kernel) can be switched off for A/B timing: GT_NO_RIDE=1.
+static bool ride_enabled() {
     static const bool disabled = []() { const char* e = getenv("GT_NO_RIDE"); return e && *e && atoi(e) != 0; }();
-    if (disabled || !ws) return false;
-    const size_t in_size = in_type == GT_F64 ? 8 : in_type == GT_F32 ? 4 : 2;
-    if ((reinterpret_cast<uintptr_t>(ws) & 15) || ((size_t)ld_ws * in_size & 15)) return false;
-    // the rider's stages must not cost the kernel a resident CTA
-    const size_t with = mass_smem<VT, R>(v, true), without = mass_smem<VT, R>(v, false);
-    if (with > 227 * 1024) return false;
-    return resident_ctas(reinterpret_cast<const void*>(mass_kernel<VT, R>), kThreads, with) ==
-           resident_ctas(reinterpret_cast<const void*>(mass_kernel<VT, R>), kThreads, without);
+    return !disabled;
 }
 
 // One chunk: [permute ->] tile kernel [+ rider staging `ride_rows` rows at `ride_ws` into `ride_z`] -> span kernel.
@@ -1108,7 +1052,7 @@ static int launch_mass(const PlanView& v, const void* ws, int in_type, int64_t l
         GT_CUDA(launch_pdl(permute_kernel<VT, R>, dim3((unsigned)pgrid), dim3(kPermThreads), 0, st, v, A, (unsigned)units));
     }
     if (phases & GT_FLAG_PHASE_TILE) {
-        const size_t smem = mass_smem<VT, R>(v, A.ride_rows > 0);
+        const size_t smem = mass_smem<VT, R>(v);
         if (smem > 227 * 1024) {
             set_error("tile plan needs %zu bytes of shared memory per CTA (limit 232448): use a smaller tile", smem);
             return GT_ERR_LIMIT;
@@ -1132,7 +1076,7 @@ static int launch_mass(const PlanView& v, const void* ws, int in_type, int64_t l
 // legal: the kernels alias the missing rows to the last valid one).  Chunk c lives in staging buffer (first + c) & 1:
 // the first chunk is staged by permute_kernel unless the previous call already did it (*stage_slot >= 0 on entry);
 // every later chunk -- and the first chunk of `next_ws`, the caller's next batch -- is staged by the rider of the tile
-// kernel before it whenever the rows qualify (ride_ok), by permute_kernel otherwise.
+// kernel before it (GT_NO_RIDE=1: by permute_kernel).
 template <typename VT, int R>
 static int reduce_typed(const PlanView& v, const void* ws, int in_type, int64_t n_rows, int64_t ld_ws, void* out_sum,
                         void* out_max, int64_t ld_out, unsigned ops, unsigned flags, const void* next_ws, int64_t next_rows,
@@ -1163,16 +1107,14 @@ static int reduce_typed(const PlanView& v, const void* ws, int in_type, int64_t 
         const void* ride_ws = nullptr;
         int ride_rows = 0;
         bool ride_is_next_call = false;
-        if (pipelined) {
+        if (pipelined && ride_enabled()) {
             if (r0 + cap < n_rows) {
                 ride_ws = wsr + (size_t)cap * ld_ws * in_size;
                 ride_rows = (int)std::min<int64_t>(cap, n_rows - r0 - cap);
-                if (!ride_ok<VT, R>(v, ride_ws, in_type, ld_ws)) ride_ws = nullptr;
             } else if (next_ws && next_rows > 0 && stage_slot && next_ld_ws == ld_ws) {
                 ride_ws = next_ws;
                 ride_rows = (int)std::min<int64_t>(cap, next_rows);
                 ride_is_next_call = true;
-                if (!ride_ok<VT, R>(v, ride_ws, in_type, ld_ws)) ride_ws = nullptr;
             }
         }
         const unsigned ph = staged ? (phases & ~(unsigned)GT_FLAG_PHASE_PERMUTE) : phases;
