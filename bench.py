@@ -47,9 +47,6 @@ def parse_args():
     ap.add_argument("--sets", type=int, default=4, help="rotating buffer sets (each 33 MB in + 176 MB out)")
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 10)")
     ap.add_argument("--no-graph", action="store_true")
-    ap.add_argument("--no-pipeline", action="store_true",
-                    help="every step stages its own rows with the permute kernel (default: each step's tile kernel stages the "
-                         "next step's rows, gt_weight_reduce_next)")
     ap.add_argument("--min-ms", type=float, default=50.0, help="the K timed steps are repeated until this much device time has passed")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-sampler", action="store_true", help="skip the secondary sampler-kernel measurement")
@@ -291,39 +288,24 @@ def run_ours(args):
     set_bytes = B * V * 4 + 2 * B * N * 4
     l2_bytes = torch.cuda.get_device_properties(dev).L2_cache_size
 
-    pipelined = not args.no_pipeline
+    def step(k, phases=0, ops=("sum", "max")):
+        eng.reduce(ws_sets[k], ops, out_sum=sum_sets[k], out_max=max_sets[k], phases=phases)
 
-    def step(k, phases=0, ops=("sum", "max"), nxt=None):
-        eng.reduce(ws_sets[k], ops, out_sum=sum_sets[k], out_max=max_sets[k], phases=phases, next_ws=nxt)
-
-    # kernels per step: tile kernel (both reductions; its producer warps stage the next step's rows) + span kernel;
-    # unpipelined steps start with the permute kernel
-    launches_per_step = (1 if pipelined else 2) + (1 if info["n_span"] > 0 else 0)
+    # kernels per step: permute kernel + tile kernel (both reductions in one launch) + span kernel
+    launches_per_step = 2 + (1 if info["n_span"] > 0 else 0)
 
     # warm-up (also sets kernel attributes, allocates the scratch) ------------------------------------------------
     for i in range(W):
-        step(i % nsets, nxt=ws_sets[(i + 1) % nsets] if pipelined else None)
+        step(i % nsets)
     torch.cuda.synchronize()
 
     # The timed loop replays ONE CUDA graph that holds exactly K consecutive steps of a stream of batches rotating over
-    # the buffer sets, as a serving loop issues them.  Pipelined (default): step i names batch i + 1, whose rows its tile
-    # kernel stages (the last step names the first batch of the next replay).
+    # the buffer sets, as a serving loop issues them.
     def capture(n):
-        chain = pipelined and n % 2 == 0  # the staging buffers alternate: an even step count returns to the entry state
-        eng._staged.clear()
-        if chain:  # entry state of every replay: batch 0 staged by the step before
-            step(nsets - 1, nxt=ws_sets[0])
-            torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
             for i in range(n):
-                last = i == n - 1
-                nxt = None
-                if pipelined and (not last or chain):
-                    nxt = ws_sets[0] if last else ws_sets[(i + 1) % nsets]
-                step(i % nsets, nxt=nxt)
-        if not chain:
-            eng._staged.clear()
+                step(i % nsets)
         return g
 
     graph = None if args.no_graph else capture(K)
@@ -332,7 +314,7 @@ def run_ours(args):
         """Enqueue exactly K steps, rotating over the buffer sets."""
         if graph is None:
             for i in range(K):
-                step(i % nsets, nxt=ws_sets[(i + 1) % nsets] if pipelined and i + 1 < K else None)
+                step(i % nsets)
         else:
             graph.replay()
 
@@ -364,7 +346,6 @@ def run_ours(args):
     barrier()
     ms_total = max_over_ranks(ev0.elapsed_time(ev1)) / reps
     value = world * B * K / (ms_total / 1e3)
-    eng._staged.clear()
 
     # per-kernel timing for the roofline (one op, one phase at a time), same buffers ----------------------------------
     def time_phase(phases, ops, iters):
@@ -478,8 +459,7 @@ def run_ours(args):
             "parallelism": f"rows sharded, {world} independent GPU(s), no collective",
             "l2_policy": f"rotating {nsets} buffer sets of {set_bytes / 1e6:.0f} MB ({nsets * set_bytes / 1e6:.0f} MB total) "
                          f"vs L2 {l2_bytes / 1e6:.0f} MB",
-            "launch": (f"one CUDA graph of the {K} steps, replayed {reps}x ({ms_total * reps:.1f} ms timed)" if graph is not None else f"direct launches, {reps} repetitions")
-                      + ("; pipelined: each step's tile kernel stages the next step's rows (gt_weight_reduce_next), no permute kernel in steady state" if pipelined else "; unpipelined: permute kernel per step"),
+            "launch": (f"one CUDA graph of the {K} steps, replayed {reps}x ({ms_total * reps:.1f} ms timed)" if graph is not None else f"direct launches, {reps} repetitions"),
             "timed_repeats": reps,
             "tile_leaves": info["tile_leaves"], "n_span": info["n_span"],
         },

@@ -50,9 +50,6 @@ SIGNATURES = {
     "gt_workspace_bytes": (c_size_t, [c_void_p, c_int64]),
     "gt_weight_reduce": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int64, c_void_p, c_void_p, c_int, c_int64,
                                  c_uint, c_uint, c_void_p, c_size_t, c_void_p]),
-    "gt_weight_reduce_next": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int64, c_void_p, c_void_p, c_int, c_int64,
-                                      c_uint, c_uint, c_void_p, c_int64, c_int64, ctypes.POINTER(c_int32), c_void_p, c_size_t,
-                                      c_void_p]),
     "gt_gather_nodes": (c_int, [c_void_p, c_int, c_int64, c_int64, c_int64, c_void_p, c_int64, c_int64, c_void_p, c_uint,
                                 c_void_p, c_int64, c_void_p]),
     "gt_subtree_token_mask": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p]),

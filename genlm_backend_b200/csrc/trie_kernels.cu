@@ -189,24 +189,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t* b, unsigned parity) {
         __nanosleep(40);
     }
 }
-// one non-blocking look at the barrier's phase
-__device__ __forceinline__ bool mbar_test(uint64_t* b, unsigned parity) {
-    unsigned done;
-    asm volatile("{\n.reg .pred p;\nmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
-                 : "=r"(done) : "r"((unsigned)__cvta_generic_to_shared(b)), "r"(parity) : "memory");
-    return done != 0;
-}
 // bytes: multiple of 16; both addresses 16-byte aligned
 __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, unsigned bytes, uint64_t* b) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                      (unsigned)__cvta_generic_to_shared(smem_dst)),
                  "l"(gsrc), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(b))
                  : "memory");
-}
-
-// fire-and-forget request to bring [gsrc, gsrc + bytes) into L2 (bytes: multiple of 16; gsrc 16-byte aligned)
-__device__ __forceinline__ void bulk_prefetch_l2(const void* gsrc, unsigned bytes) {
-    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gsrc), "r"(bytes) : "memory");
 }
 
 // Device twin of gt::swizzle_slot (trie_internal.h) for slots below 2T; B = bytes per slot.
@@ -373,9 +361,6 @@ template <typename VT> struct MassArgs {
     int64_t ld_out;
     int n_rows;
     unsigned ops;
-    // rider: while this launch reduces its rows, its producer warps stage `ride_rows` rows starting at `ride_ws`
-    // (same type, stride and log flag as ws) into the other staging buffer `ride_z` for the next launch (0: none)
-    const void* ride_ws; int ride_rows; VT* ride_z;
 };
 
 // ---- permute ---------------------------------------------------------------------------------------------------
@@ -417,68 +402,13 @@ __device__ __forceinline__ void permute_unit(const PlanView& P, const MassArgs<V
 }
 
 // Input-type dispatch (one switch per warp; the loops inside are type-specific).
-#define GT_IN_TYPE_SWITCH(in_type, ...)                                  \
-    switch (in_type) {                                                   \
-        case GT_F32: { using IN_T = float; __VA_ARGS__; } break;         \
-        case GT_F64: { using IN_T = double; __VA_ARGS__; } break;        \
-        case GT_F16: { using IN_T = __half; __VA_ARGS__; } break;        \
-        default: { using IN_T = __nv_bfloat16; __VA_ARGS__; } break;     \
+#define GT_IN_TYPE_SWITCH(in_type, CALL)                          \
+    switch (in_type) {                                            \
+        case GT_F32: { using IN_T = float; CALL; } break;         \
+        case GT_F64: { using IN_T = double; CALL; } break;        \
+        case GT_F16: { using IN_T = __half; CALL; } break;        \
+        default: { using IN_T = __nv_bfloat16; CALL; } break;     \
     }
-
-// ---- rider: the permute of the *next* launch's rows, done inside the tile kernel ----------------------------------------
-// The tile kernel is bound by how fast its output stores drain to HBM; its producer warp issues a few bulk copies per
-// pair and is otherwise idle.  When the caller knows the rows of the next launch (the next chunk of a large batch, or
-// the next batch of a stream: gt_weight_reduce_next), that warp stages them into the other staging buffer meanwhile --
-// HBM reads and L2-resident scattered stores riding under an HBM-write-bound kernel -- and every other warp of the
-// CTA joins in once it has finished its own share of the tile work.  The kernel boundary publishes the staged rows:
-// no fence or flag.  A CTA's units (permute_unit's) are blockIdx.x, blockIdx.x + grid, ...; its warps claim them from
-// a shared-memory counter.  HBM reads take microseconds while the output stores saturate the memory system, so a
-// unit's row segments are requested into L2 kRideAhead claims before they are loaded.
-constexpr int kRideAhead = 12;
-template <typename VT, int R> struct Rider {
-    const PlanView& P;
-    MassArgs<VT> RA;  // the staging job phrased as a permute launch
-    int* next;        // shared-memory claim counter
-    int my_units, n_units, G, UT, in_size;
-    __device__ __forceinline__ Rider(const PlanView& P_, const MassArgs<VT>& A, int* next_, int grid) : P(P_), RA(A), next(next_), G(grid) {
-        RA.ws = A.ride_ws; RA.n_rows = A.ride_rows; RA.z = A.ride_z;
-        UT = perm_unit_tokens_rt(A.in_type);
-        in_size = A.in_type == GT_F64 ? 8 : (A.in_type == GT_F32 ? 4 : 2);
-        n_units = (int)((P.V + UT - 1) / UT);
-        const int total = ((A.ride_rows + R - 1) / R) * n_units;
-        my_units = (int)blockIdx.x < total ? (total - (int)blockIdx.x + G - 1) / G : 0;
-    }
-    __device__ __forceinline__ int claim(int lane) const {
-        int i = 0;
-        if (lane == 0) i = atomicAdd(next, 1);
-        return __shfl_sync(0xffffffffu, i, 0);
-    }
-    // lanes 0 .. 4R-1: one 128-byte line each of unit i's R row segments
-    __device__ __forceinline__ void prefetch(int i, int lane) const {
-        if (i >= my_units || lane >= 4 * R) return;
-        const unsigned w = blockIdx.x + (unsigned)i * (unsigned)G;
-        const int g = (int)(w / (unsigned)n_units), v0 = (int)(w - (unsigned)g * (unsigned)n_units) * UT;
-        const int r = lane >> 2;
-        const int e = v0 + (lane & 3) * (128 / in_size);  // first element of this lane's line
-        if (e < (int)P.V) {
-            const unsigned char* p = static_cast<const unsigned char*>(RA.ws) + ((size_t)min(g * R + r, RA.n_rows - 1) * RA.ld_ws + e) * in_size;
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-        }
-    }
-    __device__ __forceinline__ void unit(int i, int lane) const {
-        const unsigned w = blockIdx.x + (unsigned)i * (unsigned)G;
-        GT_IN_TYPE_SWITCH(RA.in_type, (permute_unit<VT, IN_T, R>(P, RA, w, n_units, lane)));
-    }
-    // a warp that has nothing else left to do: units until none is left
-    __device__ __noinline__ void help(int lane) const {
-        pdl_wait();
-        for (;;) {
-            const int i = claim(lane);
-            if (i >= my_units) break;
-            unit(i, lane);
-        }
-    }
-};
 
 constexpr int kPermThreads = 256;
 template <typename VT, int R>
@@ -583,7 +513,6 @@ __global__ void __launch_bounds__(kThreads, 2) mass_kernel(PlanView P, MassArgs<
     uint64_t* pairEmpty = bars + 2;  // [2]
     uint64_t* full = bars + 4;       // [2] rest buffer filled by the compute group
     uint64_t* empty = bars + 6;      // [2] rest buffer drained by the emit group
-    int* ride_next = reinterpret_cast<int*>(bars + 8);  // rider: next unit of this CTA to claim
 
     const int T = P.T;
     const int n_rows = A.n_rows;
@@ -601,7 +530,6 @@ __global__ void __launch_bounds__(kThreads, 2) mass_kernel(PlanView P, MassArgs<
         mbar_init(pairEmpty, kEmitThreads); mbar_init(pairEmpty + 1, kEmitThreads);
         mbar_init(full, kComputeThreads); mbar_init(full + 1, kComputeThreads);
         mbar_init(empty, kEmitThreads); mbar_init(empty + 1, kEmitThreads);
-        *ride_next = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -611,57 +539,34 @@ __global__ void __launch_bounds__(kThreads, 2) mass_kernel(PlanView P, MassArgs<
         // =========================== producer: one thread fetches pair after pair ====================================
         // Plan metadata may be fetched while the permute kernel is still running (programmatic dependent launch); the
         // leaf blocks may not: griddepcontrol.wait precedes the first one.
-        // fetch_pair(q, blocking): lane 0 only.  Returns false (nothing issued) when the buffer of pair q is still in
-        // use and blocking is false.
-        auto fetch_pair = [&](int q, bool blocking) -> bool {
-            const int buf = q & 1;
-            const unsigned par = ((unsigned)(q >> 1) & 1u) ^ 1u;
-            if (!blocking && !mbar_test(pairEmpty + buf, par)) return false;
-            const int p = (int)blockIdx.x + q * G;
-            const int g = p / P.NT, t = p - g * P.NT;
-            unsigned char* meta = smem_raw + L.meta + (size_t)buf * L.meta_bytes;
-            // tile boundaries (independent loads, one round trip, requested before the wait for the buffers)
-            const int n0 = __ldg(P.tile_node_lo + t), n1 = __ldg(P.tile_node_lo + t + 1);
-            const int er0 = __ldg(P.ell_row_ptr + t), er1 = __ldg(P.ell_row_ptr + t + 1);
-            const int ec0 = __ldg(P.ell_chunk_ptr + t), ec1 = __ldg(P.ell_chunk_ptr + t + 1);
-            const int pc0 = __ldg(P.piece_ptr + t), pc1 = __ldg(P.piece_ptr + t + 1);
-            mbar_wait(pairEmpty + buf, par);  // the pair two back has been drained
-            PairHdr* h = reinterpret_cast<PairHdr*>(meta + L.hdr);
-            h->t = t; h->g = g; h->n0 = n0; h->n1 = n1; h->er0 = er0; h->ec0 = ec0; h->nchunks = ec1 - ec0;
-            h->pc0 = pc0; h->pc1 = pc1;
-            const int ea = ec0 & ~1, na = n0 & ~7;
-            const unsigned lb = (unsigned)T * (unsigned)B;
-            const unsigned tb = (unsigned)(er1 - er0) * 64u, db = (unsigned)((ec1 - ea + 1) >> 1) * 16u;
-            const unsigned sb = (unsigned)((n1 - na + 7) >> 3) * 16u;
-            mbar_expect_tx(pairFull + buf, lb + tb + db + sb);
-            if (tb) bulk_g2s(meta + L.terms, P.ell_terms + (size_t)er0 * 32, tb, pairFull + buf);
-            if (db) bulk_g2s(meta + L.desc, P.ell_desc + ea, db, pairFull + buf);
-            bulk_g2s(meta + L.slots, P.node_slot + na, sb, pairFull + buf);
-            if (q == 0) { pdl_wait(); pdl_trigger(); }  // z comes from the previous launch (permute_kernel or a rider)
-            bulk_g2s(smem_raw + L.leaf + (size_t)buf * L.leaf_bytes, A.z + ((size_t)g * P.ZG + (size_t)t * T) * R, lb, pairFull + buf);
-            if (q == 0) GT_PTRACE(true, kTraceItems - 1, 0);
-            return true;
-        };
-        int q_next = 0;  // lane 0: next pair to fetch
-        if (A.ride_rows > 0) {
-            // ---- rider: units claimed one at a time; between units lane 0 keeps the tile work's fetches going
-            const Rider<VT, R> rider(P, A, ride_next, G);
-            if (lane == 0) fetch_pair(q_next++, true);  // the first pair; executes griddepcontrol.wait
-            pdl_wait();  // every lane: ride_z was read by the launch before the previous one; the rows may be its output
-            for (int i = 0; i < kRideAhead; ++i) rider.prefetch(i, lane);
-            for (;;) {
-                const int i = rider.claim(lane);
-                if (i >= rider.my_units) break;
-                rider.prefetch(i + kRideAhead, lane);
-                if (dbg != 22) rider.unit(i, lane);
-                if (lane == 0 && q_next < my_pairs && fetch_pair(q_next, false)) ++q_next;
-                __syncwarp();
+        if (lane == 0) {
+            for (int q = 0; q < my_pairs; ++q) {
+                const int p = (int)blockIdx.x + q * G;
+                const int g = p / P.NT, t = p - g * P.NT;
+                const int buf = q & 1;
+                unsigned char* meta = smem_raw + L.meta + (size_t)buf * L.meta_bytes;
+                // tile boundaries (independent loads, one round trip, requested before the wait for the buffers)
+                const int n0 = __ldg(P.tile_node_lo + t), n1 = __ldg(P.tile_node_lo + t + 1);
+                const int er0 = __ldg(P.ell_row_ptr + t), er1 = __ldg(P.ell_row_ptr + t + 1);
+                const int ec0 = __ldg(P.ell_chunk_ptr + t), ec1 = __ldg(P.ell_chunk_ptr + t + 1);
+                const int pc0 = __ldg(P.piece_ptr + t), pc1 = __ldg(P.piece_ptr + t + 1);
+                mbar_wait(pairEmpty + buf, ((unsigned)(q >> 1) & 1u) ^ 1u);  // the pair two back has been drained
+                PairHdr* h = reinterpret_cast<PairHdr*>(meta + L.hdr);
+                h->t = t; h->g = g; h->n0 = n0; h->n1 = n1; h->er0 = er0; h->ec0 = ec0; h->nchunks = ec1 - ec0;
+                h->pc0 = pc0; h->pc1 = pc1;
+                const int ea = ec0 & ~1, na = n0 & ~7;
+                const unsigned lb = (unsigned)T * (unsigned)B;
+                const unsigned tb = (unsigned)(er1 - er0) * 64u, db = (unsigned)((ec1 - ea + 1) >> 1) * 16u;
+                const unsigned sb = (unsigned)((n1 - na + 7) >> 3) * 16u;
+                mbar_expect_tx(pairFull + buf, lb + tb + db + sb);
+                if (tb) bulk_g2s(meta + L.terms, P.ell_terms + (size_t)er0 * 32, tb, pairFull + buf);
+                if (db) bulk_g2s(meta + L.desc, P.ell_desc + ea, db, pairFull + buf);
+                bulk_g2s(meta + L.slots, P.node_slot + na, sb, pairFull + buf);
+                if (q == 0) { pdl_wait(); pdl_trigger(); }  // z comes from permute_kernel
+                bulk_g2s(smem_raw + L.leaf + (size_t)buf * L.leaf_bytes, A.z + ((size_t)g * P.ZG + (size_t)t * T) * R, lb, pairFull + buf);
+                if (q == 0) GT_PTRACE(true, kTraceItems - 1, 0);
             }
-            GT_PTRACE(lane == 0, kTraceItems - 1, 1);  // rider done
         }
-        if (lane == 0)
-            for (; q_next < my_pairs; ++q_next) fetch_pair(q_next, true);
-        GT_PTRACE(lane == 0, kTraceItems - 1, 2);  // all pairs requested
     } else {
         if (warp < kComputeWarps) {
             // =========================== compute group ===========================================================
@@ -701,7 +606,6 @@ __global__ void __launch_bounds__(kThreads, 2) mass_kernel(PlanView P, MassArgs<
                     mbar_arrive(full + (k & 1));  // this thread's share of the value array is complete
                 }
             }
-            if (A.ride_rows > 0) Rider<VT, R>(P, A, ride_next, G).help(lane);
         } else if (warp < kProducerWarp) {
             // =========================== emit group ==============================================================
             const int gtid = threadIdx.x - kComputeThreads;
@@ -784,7 +688,6 @@ __global__ void __launch_bounds__(kThreads, 2) mass_kernel(PlanView P, MassArgs<
                 }
                 mbar_arrive(pairEmpty + buf);  // ... nor the pair's leaf block and metadata
             }
-            if (A.ride_rows > 0) Rider<VT, R>(P, A, ride_next, G).help(lane);
         }
     }
 
@@ -958,35 +861,22 @@ template <typename K> static cudaError_t allow_smem(K kernel, size_t bytes) {
     return allow_smem_impl(reinterpret_cast<const void*>(kernel), bytes);
 }
 
-// Scratch layout for chunks of up to `cap` rows (RG = row groups of R):
-//   z[0], z[1]: [RG][ZG slots][R] VT each | part_sum [cap][n_pieces] VT | part_max likewise
-// Two staging buffers: chunk c of a call is reduced out of one while the rider of its tile kernel stages chunk c + 1
-// (or the first chunk of the caller's next batch) into the other.  The layout depends on the workspace size only, so
-// consecutive calls on one workspace agree on where the buffers are.
-constexpr int64_t kMaxChunkRows = 64;  // two staging buffers of 64 rows at 128k tokens (2 x 34 MB) stay in the 126 MB L2
+// Scratch layout for one chunk of `rows` rows (RG = row groups of R):
+//   z [RG][ZG slots][R] VT | part_sum [rows][n_pieces] VT | part_max likewise
 template <typename VT, int R> struct Scratch {
-    VT* z[2]; VT* part_sum; VT* part_max;
+    VT* z; VT* part_sum; VT* part_max;
     static size_t pad(size_t b) { return (b + 255) & ~size_t(255); }
     static size_t z_bytes(const PlanView& v, int64_t rows) { return pad((size_t)((rows + R - 1) / R) * (size_t)v.ZG * R * sizeof(VT)); }
-    Scratch(const PlanView& v, void* base, int64_t cap) {
+    Scratch(const PlanView& v, void* base, int64_t rows) {
         char* p = static_cast<char*>(base);
-        for (int i = 0; i < 2; ++i) { z[i] = reinterpret_cast<VT*>(p); p += z_bytes(v, cap); }
+        z = reinterpret_cast<VT*>(p);
+        p += z_bytes(v, rows);
         part_sum = reinterpret_cast<VT*>(p);
-        p += pad((size_t)cap * v.n_pieces * sizeof(VT));
+        p += pad((size_t)rows * v.n_pieces * sizeof(VT));
         part_max = reinterpret_cast<VT*>(p);
     }
-    static size_t total(const PlanView& v, int64_t cap) {
-        return 2 * z_bytes(v, cap) + 2 * pad((size_t)cap * v.n_pieces * sizeof(VT));
-    }
-    // rows per chunk a workspace of `bytes` holds (0: not even one row)
-    static int64_t capacity(const PlanView& v, size_t bytes) {
-        int64_t lo = 0, hi = kMaxChunkRows;
-        if (const char* e = getenv("GT_CHUNK_ROWS")) { const long x = atol(e); if (x > 0) hi = x; }
-        while (lo < hi) {  // total() is monotone in the row count
-            const int64_t mid = (lo + hi + 1) / 2;
-            if (total(v, mid) <= bytes) lo = mid; else hi = mid - 1;
-        }
-        return lo;
+    static size_t total(const PlanView& v, int64_t rows) {
+        return z_bytes(v, rows) + 2 * pad((size_t)rows * v.n_pieces * sizeof(VT));
     }
 };
 
@@ -999,8 +889,6 @@ static int resident_ctas(const void* kernel, int threads, size_t smem) {
     auto it = cache.find(key);
     if (it != cache.end()) return it->second;
     int n = 0;
-    // the query honours the kernel's dynamic shared-memory limit: raise it first, or a size above it reports 0
-    if (allow_smem_impl(kernel, smem) != cudaSuccess) (void)cudaGetLastError();
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, threads, smem) != cudaSuccess || n < 1) {
         (void)cudaGetLastError();
         n = 1;
@@ -1022,17 +910,9 @@ static int sm_count() {
     return n;
 }
 
-// The rider (staging of the next rows inside the tile kernel) can be switched off for A/B timing: GT_NO_RIDE=1.
-static bool ride_enabled() {
-    static const bool disabled = []() { const char* e = getenv("GT_NO_RIDE"); return e && *e && atoi(e) != 0; }();
-    return !disabled;
-}
-
-// One chunk: [permute ->] tile kernel [+ rider staging `ride_rows` rows at `ride_ws` into `ride_z`] -> span kernel.
 template <typename VT, int R>
-static int launch_mass(const PlanView& v, const void* ws, int in_type, int64_t ld_ws, bool log_input, VT* z, const Scratch<VT, R>& sc,
-                       VT* out_sum, VT* out_max, int64_t ld_out, int rows, unsigned ops, unsigned phases, const void* ride_ws,
-                       int ride_rows, VT* ride_z, cudaStream_t st) {
+static int launch_mass(const PlanView& v, const void* ws, int in_type, int64_t ld_ws, bool log_input, const Scratch<VT, R>& sc,
+                       VT* out_sum, VT* out_max, int64_t ld_out, int rows, unsigned ops, unsigned phases, cudaStream_t st) {
     if (v.NT == 0) {  // empty vocabulary: the root is the only node and has no mass
         for (VT* out : {out_sum, out_max})
             if (out) GT_CUDA(cudaMemset2DAsync(out, (size_t)ld_out * sizeof(VT), 0, (size_t)v.N * sizeof(VT), (size_t)rows, st));
@@ -1040,10 +920,9 @@ static int launch_mass(const PlanView& v, const void* ws, int in_type, int64_t l
     }
     MassArgs<VT> A;
     A.ws = ws; A.in_type = in_type; A.log_input = log_input ? 1 : 0; A.ld_ws = ld_ws;
-    A.z = z;
+    A.z = sc.z;
     A.out_sum = out_sum; A.out_max = out_max; A.part_sum = sc.part_sum; A.part_max = sc.part_max;
     A.ld_out = ld_out; A.n_rows = rows; A.ops = ops;
-    A.ride_ws = ride_ws; A.ride_rows = ride_ws ? ride_rows : 0; A.ride_z = ride_z;
     const int RG = (rows + R - 1) / R;
     if (phases & GT_FLAG_PHASE_PERMUTE) {  // one warp per unit of 128 (fp64 rows: 64) positions of a row group
         const int64_t UT = in_type == GT_F64 ? kUnitTokens / 2 : kUnitTokens;
@@ -1072,17 +951,23 @@ static int launch_mass(const PlanView& v, const void* ws, int in_type, int64_t l
     return GT_OK;
 }
 
-// A batch is reduced in chunks of what the caller's scratch stages (at most kMaxChunkRows rows; a partial row group is
-// legal: the kernels alias the missing rows to the last valid one).  Chunk c lives in staging buffer (first + c) & 1:
-// the first chunk is staged by permute_kernel unless the previous call already did it (*stage_slot >= 0 on entry);
-// every later chunk -- and the first chunk of `next_ws`, the caller's next batch -- is staged by the rider of the tile
-// kernel before it (GT_NO_RIDE=1: by permute_kernel).
 template <typename VT, int R>
 static int reduce_typed(const PlanView& v, const void* ws, int in_type, int64_t n_rows, int64_t ld_ws, void* out_sum,
-                        void* out_max, int64_t ld_out, unsigned ops, unsigned flags, const void* next_ws, int64_t next_rows,
-                        int64_t next_ld_ws, int32_t* stage_slot, void* workspace, size_t workspace_bytes, cudaStream_t st) {
-    const int64_t cap = Scratch<VT, R>::capacity(v, workspace_bytes);
-    if (cap < 1) {
+                        void* out_max, int64_t ld_out, unsigned ops, unsigned flags, void* workspace,
+                        size_t workspace_bytes, cudaStream_t st) {
+    // rows per launch: what the caller's scratch can stage (whole row groups when it holds at least one; a partial row
+    // group is legal: the kernels alias the missing rows to the last valid one)
+    int64_t chunk = std::min<int64_t>(n_rows, 32768);
+    if (Scratch<VT, R>::total(v, chunk) > workspace_bytes) {
+        const size_t per_group = (size_t)v.ZG * R * sizeof(VT) + 2 * (size_t)R * v.n_pieces * sizeof(VT) + 1024;
+        chunk = std::min<int64_t>(chunk, (int64_t)(workspace_bytes / per_group) * R);
+        while (chunk > 0 && Scratch<VT, R>::total(v, chunk) > workspace_bytes) chunk -= R;
+        if (chunk <= 0) {  // less than a row group: row by row
+            chunk = R - 1;
+            while (chunk > 0 && Scratch<VT, R>::total(v, chunk) > workspace_bytes) --chunk;
+        }
+    }
+    if (chunk < 1) {
         set_error("workspace too small: %zu bytes given, one row needs %zu", workspace_bytes, Scratch<VT, R>::total(v, 1));
         return GT_ERR_STATE;
     }
@@ -1091,43 +976,17 @@ static int reduce_typed(const PlanView& v, const void* ws, int in_type, int64_t 
         return GT_ERR_ARG;
     }
     const bool log_input = (flags & GT_FLAG_LOG_INPUT) != 0;
-    const unsigned all = GT_FLAG_PHASE_MASK;
-    const unsigned phases = (flags & GT_FLAG_PHASE_MASK) ? (flags & GT_FLAG_PHASE_MASK) : all;
+    const unsigned phases = (flags & GT_FLAG_PHASE_MASK) ? (flags & GT_FLAG_PHASE_MASK) : GT_FLAG_PHASE_MASK;
     const size_t in_size = in_type == GT_F64 ? 8 : in_type == GT_F32 ? 4 : 2;
-    const Scratch<VT, R> sc(v, workspace, cap);
-    int slot = 0;
-    bool staged = false;  // the chunk about to be reduced already sits in z[slot]
-    if (stage_slot && (*stage_slot == 0 || *stage_slot == 1) && phases == all) { slot = *stage_slot; staged = true; }
-    if (stage_slot) *stage_slot = -1;
-    const bool pipelined = phases == all && v.NT > 0;
-    for (int64_t r0 = 0; r0 < n_rows; r0 += cap) {
-        const int rows = (int)std::min<int64_t>(cap, n_rows - r0);
-        const char* wsr = static_cast<const char*>(ws) + (size_t)r0 * ld_ws * in_size;
-        // what the rider of this chunk's tile kernel stages
-        const void* ride_ws = nullptr;
-        int ride_rows = 0;
-        bool ride_is_next_call = false;
-        if (pipelined && ride_enabled()) {
-            if (r0 + cap < n_rows) {
-                ride_ws = wsr + (size_t)cap * ld_ws * in_size;
-                ride_rows = (int)std::min<int64_t>(cap, n_rows - r0 - cap);
-            } else if (next_ws && next_rows > 0 && stage_slot && next_ld_ws == ld_ws) {
-                ride_ws = next_ws;
-                ride_rows = (int)std::min<int64_t>(cap, next_rows);
-                ride_is_next_call = true;
-            }
-        }
-        const unsigned ph = staged ? (phases & ~(unsigned)GT_FLAG_PHASE_PERMUTE) : phases;
-        const int rc = launch_mass<VT, R>(v, wsr, in_type, ld_ws, log_input, sc.z[slot], sc,
+    for (int64_t r0 = 0; r0 < n_rows; r0 += chunk) {
+        const int rows = (int)std::min<int64_t>(chunk, n_rows - r0);
+        const Scratch<VT, R> sc(v, workspace, rows);
+        const void* wsr = static_cast<const char*>(ws) + (size_t)r0 * ld_ws * in_size;
+        const int rc = launch_mass<VT, R>(v, wsr, in_type, ld_ws, log_input, sc,
                                           (ops & GT_OP_SUM) ? static_cast<VT*>(out_sum) + (size_t)r0 * ld_out : nullptr,
                                           (ops & GT_OP_MAX) ? static_cast<VT*>(out_max) + (size_t)r0 * ld_out : nullptr, ld_out,
-                                          rows, ops, ph, ride_ws, ride_rows, sc.z[slot ^ 1], st);
+                                          rows, ops, phases, st);
         if (rc != GT_OK) return rc;
-        staged = ride_ws != nullptr;
-        if (staged) {
-            slot ^= 1;
-            if (ride_is_next_call) *stage_slot = slot;
-        }
     }
     return GT_OK;
 }
@@ -1247,15 +1106,14 @@ size_t gt_workspace_bytes(const gt_trie* t, int64_t max_rows) {
     return gt::Scratch<double, 2>::total(v, max_rows) + 256;
 }
 
-int gt_weight_reduce_next(const gt_trie* t, const void* ws, int in_type, int64_t n_rows, int64_t ld_ws, void* out_sum,
-                          void* out_max, int out_type, int64_t ld_out, unsigned ops, unsigned flags, const void* next_ws,
-                          int64_t next_rows, int64_t next_ld_ws, int32_t* stage_slot, void* workspace, size_t workspace_bytes,
-                          gt_stream stream) {
+int gt_weight_reduce(const gt_trie* t, const void* ws, int in_type, int64_t n_rows, int64_t ld_ws, void* out_sum,
+                     void* out_max, int out_type, int64_t ld_out, unsigned ops, unsigned flags, void* workspace,
+                     size_t workspace_bytes, gt_stream stream) {
     if (!t) { gt::set_error("gt_weight_reduce: null trie"); return GT_ERR_ARG; }
-    if (n_rows < 0 || next_rows < 0 || !(ops & (GT_OP_SUM | GT_OP_MAX)) || (ops & ~(unsigned)(GT_OP_SUM | GT_OP_MAX))) {
+    if (n_rows < 0 || !(ops & (GT_OP_SUM | GT_OP_MAX)) || (ops & ~(unsigned)(GT_OP_SUM | GT_OP_MAX))) {
         gt::set_error("gt_weight_reduce: bad n_rows / ops"); return GT_ERR_ARG;
     }
-    if (n_rows == 0) return GT_OK;  // *stage_slot is left as it is: nothing was consumed or staged
+    if (n_rows == 0) return GT_OK;
     if ((t->layout.V > 0 && !ws) || ((ops & GT_OP_SUM) && !out_sum) || ((ops & GT_OP_MAX) && !out_max)) {
         gt::set_error("gt_weight_reduce: null data pointer"); return GT_ERR_ARG;
     }
@@ -1263,7 +1121,7 @@ int gt_weight_reduce_next(const gt_trie* t, const void* ws, int in_type, int64_t
         gt::set_error("gt_weight_reduce: output row stride %lld exceeds 2^28 elements", (long long)ld_out);
         return GT_ERR_LIMIT;
     }
-    if (ld_ws < t->layout.V || ld_out < t->layout.N || (next_ws && next_rows > 0 && next_ld_ws < t->layout.V)) {
+    if (ld_ws < t->layout.V || ld_out < t->layout.N) {
         gt::set_error("gt_weight_reduce: row stride smaller than row length (ld_ws=%lld V=%lld ld_out=%lld N=%lld)",
                       (long long)ld_ws, (long long)t->layout.V, (long long)ld_out, (long long)t->layout.N);
         return GT_ERR_ARG;
@@ -1275,21 +1133,14 @@ int gt_weight_reduce_next(const gt_trie* t, const void* ws, int in_type, int64_t
     const gt::PlanView& v = it->second->view;
     if (!workspace || (reinterpret_cast<uintptr_t>(workspace) & 255)) { gt::set_error("gt_weight_reduce: workspace must be a 256-byte aligned device pointer"); return GT_ERR_ARG; }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-#define GT_REDUCE(VT, R) gt::reduce_typed<VT, R>(v, ws, in_type, n_rows, ld_ws, out_sum, out_max, ld_out, ops, flags, next_ws, next_rows, \
-                                                next_ld_ws, stage_slot, workspace, workspace_bytes, st)
+#define GT_REDUCE(VT, R) gt::reduce_typed<VT, R>(v, ws, in_type, n_rows, ld_ws, out_sum, out_max, ld_out, ops, flags, \
+                                                workspace, workspace_bytes, st)
     // 16-byte value slots: four fp32 rows or two fp64 rows per work item
     if (out_type == GT_F32) return GT_REDUCE(float, 4);
     if (out_type == GT_F64) return GT_REDUCE(double, 2);
 #undef GT_REDUCE
     gt::set_error("gt_weight_reduce: output type must be GT_F32 or GT_F64");
     return GT_ERR_ARG;
-}
-
-int gt_weight_reduce(const gt_trie* t, const void* ws, int in_type, int64_t n_rows, int64_t ld_ws, void* out_sum,
-                     void* out_max, int out_type, int64_t ld_out, unsigned ops, unsigned flags, void* workspace,
-                     size_t workspace_bytes, gt_stream stream) {
-    return gt_weight_reduce_next(t, ws, in_type, n_rows, ld_ws, out_sum, out_max, out_type, ld_out, ops, flags, nullptr, 0, 0, nullptr,
-                                 workspace, workspace_bytes, stream);
 }
 
 int gt_gather_nodes(const void* mass, int type, int64_t n_rows, int64_t n_nodes, int64_t ld_mass, const int32_t* node_ids,

@@ -50,7 +50,6 @@ class TrieEngine:
         self.nnz = int(lib.gt_num_reach(handle))
         self._uploaded = set()
         self._workspaces = {}
-        self._staged = {}  # (device, stream) -> (signature of the batch staged by the previous call, staging buffer)
 
     def __del__(self):
         h = getattr(self, "_handle", None)
@@ -116,13 +115,7 @@ class TrieEngine:
             # allocated on `stream` (the caller made it current), so a later reuse of the block is ordered after our kernels
             buf = torch.empty(max(need, 4096), dtype=torch.uint8, device=torch.device("cuda", index))
             self._workspaces[key] = buf
-            self._staged.pop(key, None)  # whatever an earlier call staged went with the old buffer
         return buf
-
-    @staticmethod
-    def _signature(ws, log_input, out_dtype):
-        # identifies "the same rows, unchanged": torch bumps _version on every in-place write it knows of
-        return (ws.data_ptr(), tuple(ws.shape), tuple(ws.stride()), ws.dtype, ws._version, bool(log_input), out_dtype)
 
     def row_stride(self, dtype=torch.float32):
         """Row stride (elements) of the output slabs the engine allocates: N rounded up to a whole number of
@@ -136,16 +129,11 @@ class TrieEngine:
         ld = self.row_stride(dtype)
         return torch.empty((max(B, 1), ld), dtype=dtype, device=device)[:B, : self.N]
 
-    def reduce(self, ws, ops, out_dtype=torch.float32, log_input=False, out_sum=None, out_max=None, phases=0, next_ws=None):
+    def reduce(self, ws, ops, out_dtype=torch.float32, log_input=False, out_sum=None, out_max=None, phases=0):
         """Launch the mass kernels for a ``[B, V]`` CUDA tensor on its device's current stream.
 
         Returns ``(out_sum, out_max)`` device tensors of shape ``[B, N]`` (``None`` for an op not asked for).
         Nothing is synchronised here.
-
-        ``next_ws``: the batch the caller will pass to the next ``reduce`` on this stream (same dtype, row stride and
-        flags).  Its first rows are staged while this batch's tile kernel runs (``gt_weight_reduce_next``), so the next
-        call skips its permute kernel.  The hint is safe to get wrong: a call whose rows are not the staged ones
-        (other tensor, or written to since) stages them itself.
         """
         require_cuda()
         if not (isinstance(ws, torch.Tensor) and ws.is_cuda and ws.dim() == 2):
@@ -182,31 +170,17 @@ class TrieEngine:
         ld_ws = ws.stride(0) if B > 1 else max(self.V, 1)
         with torch.cuda.device(index):
             stream = torch.cuda.current_stream(index).cuda_stream
-            work = self._workspace(index, stream, max(B, next_ws.shape[0] if next_ws is not None else 0))
-            key = (index, int(stream or 0))
-            staged = self._staged.pop(key, None)
-            slot = ctypes.c_int32(-1)
-            if staged is not None and not phases and staged[0] == self._signature(ws, log_input, out_dtype):
-                slot.value = staged[1]
-            nxt = None
-            if (next_ws is not None and not phases and isinstance(next_ws, torch.Tensor) and next_ws.is_cuda and next_ws.dim() == 2
-                    and next_ws.device == ws.device and next_ws.dtype == ws.dtype and next_ws.shape[1] == self.V
-                    and next_ws.shape[0] > 0 and (next_ws.stride(1) == 1 or self.V <= 1)
-                    and (next_ws.stride(0) if next_ws.shape[0] > 1 else ld_ws) == ld_ws):
-                nxt = next_ws
+            work = self._workspace(index, stream, B)
             check(
-                lib.gt_weight_reduce_next(
+                lib.gt_weight_reduce(
                     self._handle, ws.data_ptr(), _IN_TYPES[ws.dtype], B, ld_ws,
                     out_sum.data_ptr() if out_sum is not None else None,
                     out_max.data_ptr() if out_max is not None else None,
                     _OUT_TYPES[out_dtype], ld_out, opmask, (_lib.GT_FLAG_LOG_INPUT if log_input else 0) | int(phases),
-                    nxt.data_ptr() if nxt is not None else None, nxt.shape[0] if nxt is not None else 0, ld_ws,
-                    ctypes.byref(slot), work.data_ptr(), work.numel(), stream,
+                    work.data_ptr(), work.numel(), stream,
                 ),
                 "gt_weight_reduce",
             )
-            if nxt is not None and slot.value >= 0:
-                self._staged[key] = (self._signature(nxt, log_input, out_dtype), slot.value)
         return out_sum, out_max
 
     # ---- read-outs that keep the [B, N] slab on the GPU --------------------------------------------------------

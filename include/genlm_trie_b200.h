@@ -159,22 +159,6 @@ int gt_weight_reduce(const gt_trie* t, const void* ws, int in_type, int64_t n_ro
                      void* out_sum, void* out_max, int out_type, int64_t ld_out, unsigned ops,
                      unsigned flags, void* workspace, size_t workspace_bytes, gt_stream stream);
 
-/* Pipelined form for a stream of batches (and what gt_weight_reduce uses between the chunks of one large batch).
- * The workspace holds two staging buffers.  While the tile kernel reduces the last chunk of `ws`, its otherwise idle
- * producer warps stage the first chunk of `next_ws` -- the batch the caller will pass next, same element type, flags
- * and row stride (next_ld_ws == ld_ws), rows 16-byte aligned -- into the other buffer, so the next call starts with its
- * tile kernel instead of the permute kernel.
- *   stage_slot  in:  0 / 1 = the first chunk of `ws` was staged into that buffer by the previous call on this
- *                    workspace (which named `ws`, unchanged since, as its next_ws); -1 = nothing is staged
- *               out: the buffer holding the first chunk of next_ws, or -1 when nothing was staged (no next_ws, rows
- *                    not aligned, a phase-restricted call ...).  NULL: no pipelining across calls.
- * The caller passes the value back unchanged with the next call on the same workspace (same pointer and size) and
- * stream.  Results are identical to gt_weight_reduce's. */
-int gt_weight_reduce_next(const gt_trie* t, const void* ws, int in_type, int64_t n_rows, int64_t ld_ws,
-                          void* out_sum, void* out_max, int out_type, int64_t ld_out, unsigned ops,
-                          unsigned flags, const void* next_ws, int64_t next_rows, int64_t next_ld_ws,
-                          int32_t* stage_slot, void* workspace, size_t workspace_bytes, gt_stream stream);
-
 /* ---- SMC row op: masked logsumexp + one categorical draw per row ------------------------- */
 
 #define GT_MASK_NONE 0

@@ -304,10 +304,9 @@ def test_rows_of_any_alignment(V, dtype):
 @pytest.mark.parametrize("V,B,dtype", [(4100, 200, torch.float32), (4104, 131, torch.bfloat16), (4104, 150, torch.float16),
                                        (4098, 140, torch.float64), (20480, 129, torch.float32), (4099, 140, torch.float32),
                                        (4101, 133, torch.float32)])
-def test_chunk_pipeline_rider(V, B, dtype):
-    """Batches above one chunk (64 rows): the tile kernel of chunk c stages chunk c + 1 (the *rider*; rows that are 16-byte
-    aligned) or permute_kernel does (V = 4099: unaligned rows).  V = 4101: a row tail the rider's bulk copies do not
-    cover.  Both reductions, partial last chunk and row group, against the oracle."""
+def test_batches_above_the_scratch_rows(V, B, dtype):
+    """Batches larger than the engine's scratch (64 rows of staging): processed chunk by chunk on the C side.  Aligned and
+    unaligned rows, every input type, both reductions, partial last chunk and row group, against the oracle."""
     trie = ParallelTokenCharacterTrie(synth_vocab(V, seed=V % 11))
     o = oracle_for(trie)
     pad = (-V) % 8 if V == 4101 else 0  # row stride 4104 elements: aligned rows whose length is not a multiple of 16 bytes
@@ -325,42 +324,3 @@ def test_chunk_pipeline_rider(V, B, dtype):
         r, z = rel_err(h64, o.weight_sum(back))
         assert r <= 1e-12 and z == 0.0
         assert np.array_equal(seq.batch_weight_max(back), o.weight_max(back))
-
-
-def test_next_batch_hint_pipelines_calls():
-    """gt_weight_reduce_next across calls: the rows named as `next_ws` are staged by the current call's tile kernel; a
-    wrong hint, rows written to after the hint, another batch size and log rows all give the plain results."""
-    V = 8200
-    trie = ParallelTokenCharacterTrie(synth_vocab(V, seed=4))
-    eng, o = trie._engine, oracle_for(trie)
-    batches = [torch.tensor(dirichlet_rows(b, V, alpha=0.4, seed=40 + i)).cuda() for i, b in enumerate([64, 64, 30, 70, 64, 5])]
-    want = [(o.weight_sum(x.cpu().numpy()), o.weight_max(x.cpu().numpy()).astype(np.float32)) for x in batches]
-
-    def check(i, got):
-        r, z = rel_err(got[0].cpu().numpy(), want[i][0])
-        assert r <= SUM_RTOL and z == 0.0, (i, r, z)
-        assert np.array_equal(got[1].cpu().numpy(), want[i][1]), i
-
-    stream = torch.cuda.current_stream().cuda_stream
-    key = (0, int(stream or 0))
-    for i, x in enumerate(batches):  # a stream of batches, each naming its successor
-        nxt = batches[i + 1] if i + 1 < len(batches) else None
-        got = eng.reduce(x, ("sum", "max"), next_ws=nxt)
-        assert (key in eng._staged) == (nxt is not None), i  # aligned fp32 rows: the rider staged them
-        check(i, got)
-    # wrong hint: batch 2 announced, batch 3 passed
-    check(0, eng.reduce(batches[0], ("sum", "max"), next_ws=batches[2]))
-    check(3, eng.reduce(batches[3], ("sum", "max")))
-    # rows written to after they were staged
-    x = batches[1].clone()
-    check(0, eng.reduce(batches[0], ("sum", "max"), next_ws=x))
-    x.mul_(2.0)
-    got = eng.reduce(x, ("sum", "max"))
-    r, z = rel_err(got[0].cpu().numpy(), 2.0 * want[1][0])
-    assert r <= SUM_RTOL and z == 0.0
-    assert np.array_equal(got[1].cpu().numpy(), 2.0 * want[1][1])
-    # one reduction only, and a hint on a single-op call
-    s_only = eng.reduce(batches[0], ("sum",), next_ws=batches[1])[0]
-    m_only = eng.reduce(batches[1], ("max",))[1]
-    assert rel_err(s_only.cpu().numpy(), want[0][0])[0] <= SUM_RTOL
-    assert np.array_equal(m_only.cpu().numpy(), want[1][1])

@@ -19,7 +19,7 @@ from genlm_backend_b200 import ParallelTokenCharacterTrie, _lib
 from genlm_backend_b200.synthetic import synth_vocab, dirichlet_rows
 
 mode = sys.argv[1] if len(sys.argv) > 1 else "all"
-PH = {"all": 0, "ride": 0, "permute": _lib.GT_FLAG_PHASE_PERMUTE, "tile": _lib.GT_FLAG_PHASE_TILE}[mode]
+PH = {"all": 0, "permute": _lib.GT_FLAG_PHASE_PERMUTE, "tile": _lib.GT_FLAG_PHASE_TILE}[mode]
 V, B = 128256, 64
 trie = ParallelTokenCharacterTrie(synth_vocab(V))
 eng = trie._engine
@@ -35,7 +35,7 @@ dims = (ctypes.c_int32 * 3)()
 n = _lib.lib.gt_debug_read_trace(eng._handle, 0, None, 0, dims)
 buf = np.zeros(n, dtype=np.int64)
 _lib.lib.gt_debug_read_trace(eng._handle, 0, buf.ctypes.data, n, dims)  # clears: drop the warm-up launches
-eng.reduce(ws[0], ("sum", "max"), out_sum=osum[0], out_max=omax[0], phases=PH, next_ws=ws[1] if mode == "ride" else None)
+eng.reduce(ws[0], ("sum", "max"), out_sum=osum[0], out_max=omax[0], phases=PH)
 torch.cuda.synchronize()
 _lib.lib.gt_debug_read_trace(eng._handle, 0, buf.ctypes.data, n, dims)
 tr = buf.reshape(dims[0], dims[1], dims[2]).astype(np.float64)
@@ -61,7 +61,7 @@ for name, (a, b) in {"C wait rest buffer": (0, 1), "C pyramid": (1, 2), "C barri
     stats(name + " (first item)", dur(a, b, slice(0, 1)))
     stats(name + " (later items)", dur(a, b, slice(1, -1)))
 print("start-up (cycles since CTA start)")
-for name, ev in {"first pair fetched": 0, "rider done": 1, "all pairs requested": 2}.items():
+for name, ev in {"first pair fetched": 0}.items():
     x = tr[:, -1, ev]
     stats(name, (x - start)[live & (x > 0)])
 x = tr[:, 0, 1]
@@ -80,9 +80,3 @@ print("CTA 10 item timeline (cycles since CTA start): ev0 ev1 ev2 ev3 ev4 | ev8 
 for k in range(dims[1] - 1):
     if tr[c, k, 4] > 0 or tr[c, k, 10] > 0:
         print("  item", k, " ".join(f"{int(tr[c, k, e] - start[c]):7d}" for e in (0, 1, 2, 3, 4, 8, 9, 10)))
-
-if mode == "ride":
-    print("CTA 10 rider units (cycles since CTA start): landed, moved")
-    for k in range(dims[1] - 1):
-        if tr[c, k, 5] > 0:
-            print("  unit", k, int(tr[c, k, 5] - start[c]), int(tr[c, k, 6] - start[c]))
