@@ -52,6 +52,7 @@ SIGNATURES = {
                                  c_uint, c_uint, c_void_p, c_size_t, c_void_p]),
     "gt_gather_nodes": (c_int, [c_void_p, c_int, c_int64, c_int64, c_int64, c_void_p, c_int64, c_int64, c_void_p, c_uint,
                                 c_void_p, c_int64, c_void_p]),
+    "gt_download_rows": (c_int, [c_void_p, c_size_t, c_void_p, c_size_t, c_size_t, c_int64, c_void_p]),
     "gt_subtree_token_mask": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p]),
     "gt_lse_sample": (c_int, [c_void_p, c_int, c_int64, c_int64, c_int64, c_void_p, c_int, c_int64, c_float,
                               c_uint64, c_uint64, c_void_p, c_void_p, c_void_p]),

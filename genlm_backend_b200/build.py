@@ -70,7 +70,7 @@ def build(force=False, verbose=False):
     if failed:
         raise RuntimeError("nvcc failed building " + LIB_NAME)
     tmp = LIB_PATH + ".tmp"
-    link = [nvcc, "-shared", "-o", tmp] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static"]
+    link = [nvcc, "-shared", "-o", tmp] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static", "-ldl"]
     r = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout)

@@ -466,6 +466,7 @@ template <typename IN_T, int MK> static int launch_sampler_mk(const SampleArgs& 
     // 2-byte rows under an additive fp32 mask move twice as many mask bytes as row bytes per group and measured faster
     // with two wide CTAs per SM (40 vs 51 us); every other combination prefers four CTAs of kSThreads
     constexpr int NT = (sizeof(IN_T) == 2 && MK == GT_MASK_ADD_F32) ? 2 * kSThreads : kSThreads;
+    gt::NvtxRange nv("gt:lse_sample");
     lse_sample_kernel<IN_T, MK, NT><<<grid, NT, 0, st>>>(A);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { set_error("lse_sample launch failed: %s", cudaGetErrorString(e)); return GT_ERR_CUDA; }

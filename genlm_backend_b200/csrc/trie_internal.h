@@ -10,9 +10,20 @@
 
 #include "../../include/genlm_trie_b200.h"
 
+#include <nvtx3/nvToolsExt.h>  // header-only; a no-op unless a profiler injects itself (trace ranges)
+
 namespace gt {
 
 void set_error(const char* fmt, ...);
+
+// NVTX range around a host-side launch group: shows up as gt:permute / gt:tile / gt:span / gt:lse_sample in Nsight
+// timelines (the kernels themselves are asynchronous; the range marks where they were enqueued).
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+    NvtxRange(const NvtxRange&) = delete;
+    NvtxRange& operator=(const NvtxRange&) = delete;
+};
 
 // Host layout in the reference's node-id space (post-order, root = N-1).
 struct Layout {

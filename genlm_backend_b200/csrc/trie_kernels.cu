@@ -928,6 +928,7 @@ static int launch_mass(const PlanView& v, const void* ws, int in_type, int64_t l
         const int64_t UT = in_type == GT_F64 ? kUnitTokens / 2 : kUnitTokens;
         const int64_t units = (int64_t)RG * ((v.V + UT - 1) / UT);
         const int64_t pgrid = (units + kPermThreads / 32 - 1) / (kPermThreads / 32);
+        NvtxRange nv("gt:permute");
         GT_CUDA(launch_pdl(permute_kernel<VT, R>, dim3((unsigned)pgrid), dim3(kPermThreads), 0, st, v, A, (unsigned)units));
     }
     if (phases & GT_FLAG_PHASE_TILE) {
@@ -941,11 +942,13 @@ static int launch_mass(const PlanView& v, const void* ws, int in_type, int64_t l
         const int64_t pairs = (int64_t)v.NT * RG;
         const int slots = sm_count() * resident_ctas(reinterpret_cast<const void*>(mass_kernel<VT, R>), kThreads, smem);
         const unsigned grid = (unsigned)std::min<int64_t>(pairs, slots);
+        NvtxRange nv("gt:tile");
         GT_CUDA(launch_pdl(mass_kernel<VT, R>, dim3(grid), dim3(kThreads), smem, st, v, A));
     }
     if (v.n_span > 0 && (phases & GT_FLAG_PHASE_SPAN)) {
         const int nops = (ops == (unsigned)(GT_OP_SUM | GT_OP_MAX)) ? 2 : 1;
         dim3 sgrid((unsigned)((v.n_span + 255) / 256), (unsigned)std::min(rows, 4096), (unsigned)nops);
+        NvtxRange nv("gt:span");
         GT_CUDA(launch_pdl(span_kernel<VT>, sgrid, dim3(256), 0, st, v, A));
     }
     return GT_OK;
@@ -1133,6 +1136,7 @@ int gt_weight_reduce(const gt_trie* t, const void* ws, int in_type, int64_t n_ro
     const gt::PlanView& v = it->second->view;
     if (!workspace || (reinterpret_cast<uintptr_t>(workspace) & 255)) { gt::set_error("gt_weight_reduce: workspace must be a 256-byte aligned device pointer"); return GT_ERR_ARG; }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    gt::NvtxRange nv("gt:weight_reduce");
 #define GT_REDUCE(VT, R) gt::reduce_typed<VT, R>(v, ws, in_type, n_rows, ld_ws, out_sum, out_max, ld_out, ops, flags, \
                                                 workspace, workspace_bytes, st)
     // 16-byte value slots: four fp32 rows or two fp64 rows per work item
@@ -1141,6 +1145,16 @@ int gt_weight_reduce(const gt_trie* t, const void* ws, int in_type, int64_t n_ro
 #undef GT_REDUCE
     gt::set_error("gt_weight_reduce: output type must be GT_F32 or GT_F64");
     return GT_ERR_ARG;
+}
+
+int gt_download_rows(void* dst_host, size_t dst_pitch, const void* src_dev, size_t src_pitch, size_t width_bytes, int64_t n_rows,
+                     gt_stream stream) {
+    if (n_rows < 0 || dst_pitch < width_bytes || src_pitch < width_bytes) { gt::set_error("gt_download_rows: bad size / pitch"); return GT_ERR_ARG; }
+    if (n_rows == 0 || width_bytes == 0) return GT_OK;
+    if (!dst_host || !src_dev) { gt::set_error("gt_download_rows: null pointer"); return GT_ERR_ARG; }
+    GT_CUDA(cudaMemcpy2DAsync(dst_host, dst_pitch, src_dev, src_pitch, width_bytes, (size_t)n_rows, cudaMemcpyDeviceToHost,
+                              static_cast<cudaStream_t>(stream)));
+    return GT_OK;
 }
 
 int gt_gather_nodes(const void* mass, int type, int64_t n_rows, int64_t n_nodes, int64_t ld_mass, const int32_t* node_ids,

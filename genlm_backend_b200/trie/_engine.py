@@ -183,6 +183,20 @@ class TrieEngine:
             )
         return out_sum, out_max
 
+    def download(self, dev_out, host_out, stream):
+        """Pitched D2H copy (``gt_download_rows``) of a ``[rows, N]`` device result (row stride = the slab's padded
+        stride) into a C-contiguous ``[rows, N]`` page-locked host tensor, on ``stream``.  The caller keeps both alive
+        until it has synchronised the stream."""
+        rows = dev_out.shape[0]
+        if rows == 0 or self.N == 0:
+            return
+        es = dev_out.element_size()
+        check(
+            lib.gt_download_rows(host_out.data_ptr(), host_out.stride(0) * es if rows > 1 else self.N * es, dev_out.data_ptr(),
+                                 dev_out.stride(0) * es if rows > 1 else self.N * es, self.N * es, rows, stream.cuda_stream),
+            "gt_download_rows",
+        )
+
     # ---- read-outs that keep the [B, N] slab on the GPU --------------------------------------------------------
     def gather_nodes(self, mass, node_ids, normalizer=None, log=False):
         """``out[b, k] = mass[b, node_ids[b, k]]`` (``node_ids`` 1-D: shared by all rows), optionally divided by

@@ -75,7 +75,17 @@ def _encode_vocabulary(decode):
 
 
 class TokenCharacterTrie:
-    """A trie data structure for efficient token-to-character mapping."""
+    """A trie data structure for efficient token-to-character mapping.
+
+    Deviations from the reference class, all on inputs its own tests do not use:
+
+    * there is no CPU path: ``weight_sum`` / ``weight_max`` raise without a CUDA device (the reference's numba loops run
+      anywhere); building the trie and every layout attribute work on any host;
+    * ``weight_max`` is a true maximum (identity ``-inf``): the reference's numba loop starts every internal node at 0
+      (``base.py:387-393``), so it clamps negative weights -- e.g. log-weights -- at 0 where this class returns their
+      maximum.  For non-negative weights (probabilities) the results are identical, bit for bit;
+    * an empty vocabulary gives mass 0 at the root for both reductions.
+    """
 
     def __init__(self, decode):
         """
@@ -201,7 +211,14 @@ class TokenCharacterTrie:
     def _reduce64(self, rows, op):
         ws = self._rows_to_device(rows)
         out_sum, out_max = self._engine.reduce(ws, (op,), out_dtype=torch.float64)
-        return (out_sum if op == "sum" else out_max).cpu().numpy()
+        out = out_sum if op == "sum" else out_max
+        # C-contiguous float64 [B, N] like the reference's arrays: one pitched copy out of the padded device slab
+        host = torch.empty((out.shape[0], self._engine.N), dtype=torch.float64, pin_memory=out.shape[0] > 0)
+        if out.shape[0]:
+            stream = torch.cuda.current_stream(out.device.index)
+            self._engine.download(out, host, stream)
+            stream.synchronize()
+        return host.numpy()
 
     def weight_sum(self, ws):
         """Sum of the weights of all tokens below each node.  Returns ``float64[num_nodes]``."""

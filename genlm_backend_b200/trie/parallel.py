@@ -21,6 +21,8 @@ from ..sharding import row_blocks
 _PIPE_ROWS = 32
 _PIPE_FIRST = 8
 _PIPE_SLOTS = 3
+# batches of at most this many rows take the single-stream latency path
+_SMALL_BATCH = 8
 
 
 def _pipe_slices(lo, hi):
@@ -191,22 +193,49 @@ class ParallelTokenCharacterTrie(TokenCharacterTrie):
             ev.synchronize()  # the H2D copy that last read this buffer has finished
         return buf, ev
 
-    def _batch_to_host(self, ws, ops, log_input=False):
-        """Run ``ops`` over the batch and return host arrays.  Rows are split contiguously over the configured
-        GPUs; on each GPU slices of ``_PIPE_ROWS`` rows flow H2D -> kernels -> D2H on rotating streams so the
-        copies overlap the kernels and each other.  Results land in pinned host memory that the returned
-        numpy arrays own."""
+    def _small_to_host(self, ws, host_rows, ops, log_input, as_rows):
+        """Latency path for a handful of rows: the caller's current stream only (no pipeline streams, no events), cached
+        device scratch, one H2D copy, the three kernels, one pitched D2H copy per reduction, one stream synchronisation."""
+        index = self._device_list()[0]
+        dev = torch.device("cuda", index)
+        N = len(self)
+        with torch.cuda.device(index):
+            st = torch.cuda.current_stream(index)
+            if host_rows is not None:
+                ws = torch.stack(host_rows)
+            if not ws.is_cuda or ws.device != dev:
+                ws = ws.to(dev, non_blocking=True)
+            B = ws.shape[0]
+            o_sum, o_max = self._engine.reduce(ws, ops, log_input=log_input)
+            outs = {}
+            for op, o in (("sum", o_sum), ("max", o_max)):
+                if o is not None:
+                    outs[op] = torch.empty((B, N), dtype=torch.float32, pin_memory=True)
+                    self._engine.download(o, outs[op], st)
+            st.synchronize()
+        if as_rows:
+            return {op: list(o.numpy()) for op, o in outs.items()}
+        return {op: o.numpy() for op, o in outs.items()}
+
+    def _batch_to_host(self, ws, ops, log_input=False, as_rows=False):
+        """Run ``ops`` over the batch and return host arrays: C-contiguous float32 ``[B, N]`` like the reference's
+        ``.cpu().numpy()`` (``parallel.py:103,145``), or with ``as_rows`` a list of ``B`` row arrays (what the async
+        wrapper hands to its futures).  Rows are split contiguously over the configured GPUs; on each GPU slices of
+        ``_PIPE_ROWS`` rows flow H2D -> kernels -> D2H on rotating streams so the copies overlap the kernels and each
+        other.  Results land in page-locked host memory owned by the returned arrays (torch's caching host allocator
+        recycles it when they are dropped): one ``[B, N]`` block, or with ``as_rows`` one block per slice, so that a row
+        kept by a caller holds on to at most ``_PIPE_ROWS`` rows."""
         host_rows = self._host_rows(ws)
         if host_rows is None:
             ws = self._as_batch(ws)
         B, N = (len(host_rows) if host_rows is not None else ws.shape[0]), len(self)
         devices = self._device_list()
-        # pinned host slabs with the device slabs' padded row stride, so every D2H copy is one flat contiguous
-        # transfer; callers get the [B, N] view (each row is a contiguous float32 array)
-        ld = self._engine.row_stride(torch.float32)
-        outs = {op: torch.empty((B, ld), dtype=torch.float32, pin_memory=True) for op in ops}
         if B == 0:
-            return {op: o.numpy()[:, :N] for op, o in outs.items()}
+            return {op: ([] if as_rows else np.empty((0, N), dtype=np.float32)) for op in ops}
+        if B <= _SMALL_BATCH:
+            return self._small_to_host(ws, host_rows, ops, log_input, as_rows)
+        whole = None if as_rows else {op: torch.empty((B, N), dtype=torch.float32, pin_memory=True) for op in ops}
+        row_lists = {op: [None] * B for op in ops} if as_rows else None
         used = []
         keep = []
         for index, (lo, hi) in zip(devices, row_blocks(B, len(devices))):
@@ -230,20 +259,38 @@ class ParallelTokenCharacterTrie(TokenCharacterTrie):
                         if chunk.device != dev:
                             chunk = chunk.to(dev, non_blocking=True)
                     o_sum, o_max = self._engine.reduce(chunk, ops, log_input=log_input)
-                    if o_sum is not None:
-                        outs["sum"][r0:r1].copy_(o_sum._base[: r1 - r0], non_blocking=True)
-                    if o_max is not None:
-                        outs["max"][r0:r1].copy_(o_max._base[: r1 - r0], non_blocking=True)
+                    for op, o in (("sum", o_sum), ("max", o_max)):
+                        if o is None:
+                            continue
+                        if as_rows:
+                            slab = torch.empty((r1 - r0, N), dtype=torch.float32, pin_memory=True)
+                            row_lists[op][r0:r1] = list(slab.numpy())
+                        else:
+                            slab = whole[op][r0:r1]
+                        self._engine.download(o, slab, st)
+                        keep.append(slab)
                     keep.append((chunk, o_sum, o_max))
             used.extend(streams)
         for st in used:
             st.synchronize()
         del keep
-        return {op: o.numpy()[:, :N] for op, o in outs.items()}
+        if as_rows:
+            return row_lists
+        return {op: o.numpy() for op, o in whole.items()}
+
+    def _single(self, ws, op):
+        """One weight vector (anything ``_preprocess_ws`` takes) through the small-batch latency path: a ``[1, V]`` view
+        instead of a stacked copy, no staging on ``self.device`` first."""
+        if not isinstance(ws, torch.Tensor):
+            ws = torch.tensor(ws, dtype=torch.float32)
+        assert ws.dim() == 1 and ws.shape[0] == len(self.decode), [ws.shape[0], len(self.decode)]
+        if ws.dtype not in (torch.float32, torch.float16, torch.bfloat16):
+            ws = ws.to(torch.float32)
+        return self._batch_to_host(ws.reshape(1, -1), (op,))[op][0]
 
     def weight_sum(self, ws):
         """Node sums for one weight vector -> ``float32[num_nodes]`` (``parallel.py:77-90``)."""
-        return self.batch_weight_sum(self._preprocess_ws([ws]))[0]
+        return self._single(ws, "sum")
 
     def batch_weight_sum(self, ws):
         """Node sums for a batch -> ``float32[batch, num_nodes]`` numpy array (``parallel.py:92-103``)."""
@@ -251,11 +298,17 @@ class ParallelTokenCharacterTrie(TokenCharacterTrie):
 
     def weight_max(self, ws):
         """Node maxima for one weight vector -> ``float32[num_nodes]`` (``parallel.py:105-118``)."""
-        return self.batch_weight_max(self._preprocess_ws([ws]))[0]
+        return self._single(ws, "max")
 
     def batch_weight_max(self, ws):
         """Node maxima for a batch -> ``float32[batch, num_nodes]`` numpy array (``parallel.py:120-145``)."""
         return self._batch_to_host(ws, ("max",))["max"]
+
+    def batch_weight_rows(self, ws, op):
+        """``batch_weight_sum`` / ``batch_weight_max`` (``op`` = ``"sum"`` / ``"max"``) as a list of per-row float32
+        arrays: the form ``AsyncTokenCharacterTrie`` hands to its futures.  The rows live in page-locked blocks of at most
+        ``_PIPE_ROWS`` rows, so a caller that keeps one row does not keep the whole batch's results alive."""
+        return self._batch_to_host(ws, (op,), as_rows=True)[op]
 
     def batch_weight_sum_max(self, ws, log_input=False):
         """Both reductions from one staging pass -> ``(sums, maxes)`` numpy arrays."""

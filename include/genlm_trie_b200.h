@@ -150,7 +150,7 @@ size_t gt_workspace_bytes(const gt_trie* t, int64_t max_rows);
  *   out_sum / out_max   device pointers (one may be NULL when the op is not requested), row stride
  *            ld_out elements, type out_type (GT_F32 or GT_F64)
  *   ops      GT_OP_SUM | GT_OP_MAX
- *   workspace  device scratch, see gt_workspace_bytes / gt_workspace_init
+ *   workspace  device scratch, see gt_workspace_bytes
  * Numerics: every node is a sum of non-negative terms (aligned leaf blocks; no prefix differences).  With
  * out_type GT_F32 the terms inside a tile of 1024 leaves are added pairwise in fp32 and the per-tile pieces of a
  * node that spans tiles in fp64, rounded once (measured <= 2e-7 relative to the fp64 reference); with GT_F64
@@ -186,6 +186,13 @@ int gt_lse_sample(const void* logp, int in_type, int64_t n_rows, int64_t n_vocab
 int gt_gather_nodes(const void* mass, int type, int64_t n_rows, int64_t n_nodes, int64_t ld_mass,
                     const int32_t* node_ids, int64_t n_ids, int64_t ids_ld, const int32_t* norm_node,
                     unsigned flags, void* out, int64_t ld_out, gt_stream stream);
+
+/* The copy the reference ends on (parallel.py:103,145: masses.cpu().numpy()): n_rows rows of width_bytes each from a
+ * device slab whose rows are src_pitch bytes apart (the engine pads rows to whole 128-byte lines) into host memory
+ * whose rows are dst_pitch bytes apart -- a C-contiguous [n_rows, N] array when dst_pitch == width_bytes.  One pitched
+ * DMA on `stream` (cudaMemcpy2DAsync); dst_host should be page-locked for the copy to be asynchronous. */
+int gt_download_rows(void* dst_host, size_t dst_pitch, const void* src_dev, size_t src_pitch, size_t width_bytes,
+                     int64_t n_rows, gt_stream stream);
 
 /* mask_bits[b, i/32] bit i%32 = 1 iff item i's leaf lies in the subtree of node nodes[b] -- column nodes[b] of the
  * reference's reachability matrix M (parallel.py:33-64) as a keep-bitmask in gt_lse_sample's GT_MASK_BITS_U32 layout

@@ -324,3 +324,34 @@ def test_batches_above_the_scratch_rows(V, B, dtype):
         r, z = rel_err(h64, o.weight_sum(back))
         assert r <= 1e-12 and z == 0.0
         assert np.array_equal(seq.batch_weight_max(back), o.weight_max(back))
+
+
+@pytest.mark.parametrize("B", [1, 5, 9, 40, 100])
+def test_host_results_are_c_contiguous(B):
+    """The reference returns ``masses.cpu().numpy()``: C-contiguous [B, N] arrays (parallel.py:103,145).  Ours come out of
+    row-padded device slabs through one pitched copy per slice; B <= 8 takes the single-stream latency path."""
+    V = 3001
+    par = ParallelTokenCharacterTrie(synth_vocab(V, seed=2))
+    seq = TokenCharacterTrie(synth_vocab(V, seed=2))
+    o = oracle_for(par)
+    ws = dirichlet_rows(B, V, alpha=0.3, seed=B)
+    want_s, want_m = o.weight_sum(ws), o.weight_max(ws)
+    for x in (torch.tensor(ws), torch.tensor(ws).cuda(), [torch.tensor(w) for w in ws]):
+        for got, want, exact in ((par.batch_weight_sum(x), want_s, False), (par.batch_weight_max(x), want_m, True)):
+            assert got.flags["C_CONTIGUOUS"] and got.shape == (B, len(par)) and got.dtype == np.float32
+            if exact:
+                assert np.array_equal(got, want.astype(np.float32))
+            else:
+                r, z = rel_err(got, want)
+                assert r <= SUM_RTOL and z == 0.0
+    s64 = seq.batch_weight_sum(ws)
+    assert s64.flags["C_CONTIGUOUS"] and s64.dtype == np.float64 and rel_err(s64, want_s)[0] <= 1e-12
+    both = par.batch_weight_sum_max(torch.tensor(ws))
+    assert both[0].flags["C_CONTIGUOUS"] and both[1].flags["C_CONTIGUOUS"]
+    rows = par.batch_weight_rows(torch.tensor(ws), "sum")
+    assert len(rows) == B and all(r.flags["C_CONTIGUOUS"] and r.shape == (len(par),) for r in rows)
+    assert max(r.base.shape[0] if r.base is not None and r.base.ndim == 2 else 1 for r in rows) <= 32  # a kept row pins <= 32 rows
+    assert rel_err(np.stack(rows), want_s)[0] <= SUM_RTOL
+    one = par.weight_sum(torch.tensor(ws[0]))
+    assert one.flags["C_CONTIGUOUS"] and one.shape == (len(par),) and rel_err(one, want_s[0])[0] <= SUM_RTOL
+    assert np.array_equal(par.weight_max(ws[0].tolist()), want_m[0].astype(np.float32))
