@@ -198,13 +198,22 @@ template <typename IN_T, int MK> struct RowView {
     }
 };
 
-// Online (max, sum of 2^((y - max) * SC)) update with N more values.
+// max that returns NaN when either operand is NaN (fmaxf would drop it)
+__device__ __forceinline__ float fmax_nan(float a, float b) {
+    float r;
+    asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+    return r;
+}
+
+// Online (max, sum of 2^((y - max) * SC)) update with N more values.  A NaN among them makes s NaN for good, also while
+// the running max is still -inf (a NaN logit at an allowed position of an otherwise masked stretch): torch's logsumexp
+// gives NaN for such a row and multinomial raises.
 template <int N> __device__ __forceinline__ void online_update(const float (&y)[N], float SC, float& m, float& s) {
     float gm = y[0];
 #pragma unroll
-    for (int k = 1; k < N; ++k) gm = fmaxf(gm, y[k]);
-    if (gm > m) {  // rare once the running max has settled
-        s *= fast_exp2((m - gm) * SC);  // m = -inf: s is still 0
+    for (int k = 1; k < N; ++k) gm = fmax_nan(gm, y[k]);
+    if (!(gm <= m)) {  // a larger value (rare once the running max has settled) or a NaN
+        s *= fast_exp2((m - gm) * SC);  // m = -inf: s is still 0; gm = NaN: s becomes NaN
         m = gm;
     }
     if (m > -INFINITY) {
@@ -406,7 +415,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) lse_sample_kernel(SampleArgs A)
                 online_update<EPV>(y, SC, m, s);
             }
         }
-        // A NaN element poisons s (fmaxf ignores it, so m stays finite): logZ becomes NaN, tok = -1.
+        // A NaN element has made this thread's s (and possibly m) NaN: logZ becomes NaN, tok = -1.
 
         // ---- block reduction (fp64) ------------------------------------------------------------------
         float wm = m;
@@ -421,7 +430,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) lse_sample_kernel(SampleArgs A)
         }
         __syncthreads();
         const float M = s_M;
-        s_mass[tid] = (m > -INFINITY) ? (double)s * exp2((double)(m - M) * (double)SC) : 0.0;
+        s_mass[tid] = (s != s || m != m) ? (double)NAN : (m > -INFINITY) ? (double)s * exp2((double)(m - M) * (double)SC) : 0.0;
         __syncthreads();
 
         if (warp == 0) {
@@ -440,7 +449,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) lse_sample_kernel(SampleArgs A)
             if (lane == 0) {
                 s_pick = pick;
                 s_resid = before < 0.0 ? -1.0 : u * tot - before;
-                A.logZ[b] = (M == -INFINITY) ? -INFINITY : (float)((double)M * (double)rv.unit() + log(tot));
+                A.logZ[b] = (tot != tot) ? NAN : (M == -INFINITY) ? -INFINITY : (float)((double)M * (double)rv.unit() + log(tot));
             }
         }
         __syncthreads();
