@@ -7,6 +7,7 @@
 #include <vector>
 #include <map>
 #include <memory>
+#include <mutex>
 
 #include "../../include/genlm_trie_b200.h"
 
@@ -125,6 +126,8 @@ struct gt_trie {
     gt::Layout layout;
     std::unique_ptr<gt::Plan> plan;
     std::map<int, gt::DevicePlan*> dev;  // device ordinal -> resident metadata
+    std::mutex mu;                       // guards plan / dev while gt_plan / gt_upload build them (several host threads
+                                         // may bring up different devices of one trie; the launch paths only read)
     ~gt_trie();
 };
 

@@ -15,9 +15,10 @@
 //                   shuffles) and the multi-term ranges (ELL-packed term lists); emit warps stream the tile's node-id
 //                   interval out with coalesced stores and write the spanning-node pieces;
 //   span_kernel     the few nodes whose leaf range crosses tiles, reduced from their pieces (fp64 for sums).
-// (A fused variant with permute warps inside mass_kernel was built and measured in round 2: publishing permuted row
-// groups to other SMs needs a device-scope fence, which takes ~10 us on an SM saturated with output stores, so the
-// permute could not stay ahead of its consumers; see profiles/README.md.)
+// (Variants that hide the permute inside mass_kernel were built and measured in round 2 and are not here: publishing
+// permuted row groups to other SMs of the same launch needs a device-scope fence, which takes ~10 us on an SM saturated
+// with output stores; staging the *next* launch's rows from the producer warp works but one warp per CTA is 2.5x too
+// slow, and rider code in the other warps costs the tile work 9 us of register allocation; profiles/r02_experiments.md.)
 #include <cuda_runtime.h>
 #include <cuda_fp16.h>
 #include <cuda_bf16.h>
@@ -302,7 +303,10 @@ constexpr int kComputeWarps = GT_COMPUTE_WARPS, kEmitWarps = GT_EMIT_WARPS;
 constexpr int kProducerWarp = kComputeWarps + kEmitWarps;  // one warp: lane 0 issues every bulk copy
 static_assert(kProducerWarp + 1 == kThreads / 32, "compute + emit + producer warps fill the CTA");
 constexpr int kComputeThreads = 32 * kComputeWarps, kEmitThreads = 32 * kEmitWarps;
-constexpr int kUnitTokens = 128;  // vocabulary positions per permute unit (64 for fp64 rows)
+#ifndef GT_PERM_UT
+#define GT_PERM_UT 128
+#endif
+constexpr int kUnitTokens = GT_PERM_UT;  // vocabulary positions per permute unit (half for fp64 rows)
 
 #ifndef GT_ELL_BATCH
 #define GT_ELL_BATCH 4
@@ -410,9 +414,15 @@ __device__ __forceinline__ void permute_unit(const PlanView& P, const MassArgs<V
         default: { using IN_T = __nv_bfloat16; CALL; } break;     \
     }
 
-constexpr int kPermThreads = 256;
+#ifndef GT_PERM_THREADS
+#define GT_PERM_THREADS 256
+#endif
+#ifndef GT_PERM_MINB
+#define GT_PERM_MINB 1
+#endif
+constexpr int kPermThreads = GT_PERM_THREADS;
 template <typename VT, int R>
-__global__ void __launch_bounds__(kPermThreads) permute_kernel(PlanView P, MassArgs<VT> A, unsigned total_units) {
+__global__ void __launch_bounds__(kPermThreads, GT_PERM_MINB) permute_kernel(PlanView P, MassArgs<VT> A, unsigned total_units) {
     pdl_wait();  // the rows may come from the previous kernel of the stream; z may still be read by the previous call
     pdl_trigger();
     const unsigned w = blockIdx.x * (kPermThreads / 32) + (threadIdx.x >> 5);
@@ -1055,11 +1065,16 @@ extern "C" {
 
 int gt_upload(gt_trie* t, int device) {
     if (!t) { gt::set_error("gt_upload: null trie"); return GT_ERR_ARG; }
-    if (t->dev.count(device)) return GT_OK;
+    {
+        std::lock_guard<std::mutex> lock(t->mu);
+        if (t->dev.count(device)) return GT_OK;
+    }
     if (!t->plan) {
-        const int rc = gt_plan(t, 0);
+        const int rc = gt_plan(t, 0);  // takes the lock itself
         if (rc != GT_OK) return rc;
     }
+    std::lock_guard<std::mutex> lock(t->mu);
+    if (t->dev.count(device)) return GT_OK;  // another thread brought the device up meanwhile
     gt::DevicePlan* d = gt::upload_plan(t->layout, *t->plan, device);
     if (!d) return GT_ERR_CUDA;
     t->dev[device] = d;

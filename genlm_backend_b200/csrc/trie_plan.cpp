@@ -290,6 +290,7 @@ extern "C" {
 int gt_plan(gt_trie* t, int32_t tile_leaves) {
     if (!t) { gt::set_error("gt_plan: null trie"); return GT_ERR_ARG; }
     auto env_int = [](const char* name, int dflt) { const char* s = getenv(name); return s && *s ? atoi(s) : dflt; };
+    std::lock_guard<std::mutex> lock(t->mu);
     if (t->plan && tile_leaves <= 0) tile_leaves = t->plan->T;
     if (tile_leaves <= 0) tile_leaves = env_int("GT_TILE_LEAVES", 1024);
     if (t->plan) {

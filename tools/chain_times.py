@@ -81,7 +81,7 @@ def split_time(parts, per_graph=4, steps=400):
             st = streams[si]
             st.wait_event(fork)
             with torch.cuda.stream(st):
-                eng.reduce(ws[k][lo:hi], ("sum", "max"), out_sum=osum[k][lo:hi], out_max=omax[k][lo:hi], slot=si)
+                eng.reduce(ws[k][lo:hi], ("sum", "max"), out_sum=osum[k][lo:hi], out_max=omax[k][lo:hi])
             join = torch.cuda.Event()
             join.record(st)
             cur.wait_event(join)
