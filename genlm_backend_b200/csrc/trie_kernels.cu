@@ -871,22 +871,44 @@ template <typename K> static cudaError_t allow_smem(K kernel, size_t bytes) {
     return allow_smem_impl(reinterpret_cast<const void*>(kernel), bytes);
 }
 
-// Scratch layout for one chunk of `rows` rows (RG = row groups of R):
-//   z [RG][ZG slots][R] VT | part_sum [rows][n_pieces] VT | part_max likewise
+// Scratch layout: a batch is reduced in *chunks* of at most kMaxChunkRows rows (what the staging buffer holds), and the
+// pieces of spanning nodes are collected over a *span group* of up to kMaxSpanRows rows, so that span_kernel runs once
+// per span group instead of once per chunk (it costs ~6 us in the chain for 2.5 us of work: it cannot become resident
+// before the tile kernel's CTAs leave).
+//   z [chunk row groups][ZG slots][R] VT | part_sum [span rows][n_pieces] VT | part_max likewise
+constexpr int64_t kMaxChunkRows = 64;    // 34 MB of staging at 128k tokens: stays in the 126 MB L2 between permute and tile kernel
+constexpr int64_t kMaxSpanRows = 1024;   // 9.9 MB of pieces per reduction at 128k tokens
 template <typename VT, int R> struct Scratch {
     VT* z; VT* part_sum; VT* part_max;
+    int64_t chunk_rows, span_rows;  // capacities
     static size_t pad(size_t b) { return (b + 255) & ~size_t(255); }
     static size_t z_bytes(const PlanView& v, int64_t rows) { return pad((size_t)((rows + R - 1) / R) * (size_t)v.ZG * R * sizeof(VT)); }
-    Scratch(const PlanView& v, void* base, int64_t rows) {
+    static size_t part_bytes(const PlanView& v, int64_t rows) { return pad((size_t)rows * v.n_pieces * sizeof(VT)); }
+    static size_t total(const PlanView& v, int64_t chunk, int64_t span) { return z_bytes(v, chunk) + 2 * part_bytes(v, span); }
+    static int64_t max_chunk() {
+        static const int64_t n = []() { const char* e = getenv("GT_CHUNK_ROWS"); const long x = e ? atol(e) : 0; return x > 0 ? (int64_t)x : kMaxChunkRows; }();
+        return n;
+    }
+    // what a workspace of `bytes` holds (chunk_rows = 0: not even one row)
+    Scratch(const PlanView& v, void* base, size_t bytes) {
+        int64_t lo = 0, hi = max_chunk();
+        while (lo < hi) {  // total() is monotone in the row count
+            const int64_t mid = (lo + hi + 1) / 2;
+            if (total(v, mid, mid) <= bytes) lo = mid; else hi = mid - 1;
+        }
+        chunk_rows = lo;
+        lo = chunk_rows; hi = std::max<int64_t>(chunk_rows, kMaxSpanRows);
+        while (lo < hi) {
+            const int64_t mid = (lo + hi + 1) / 2;
+            if (total(v, chunk_rows, mid) <= bytes) lo = mid; else hi = mid - 1;
+        }
+        span_rows = lo;
         char* p = static_cast<char*>(base);
         z = reinterpret_cast<VT*>(p);
-        p += z_bytes(v, rows);
+        p += z_bytes(v, chunk_rows);
         part_sum = reinterpret_cast<VT*>(p);
-        p += pad((size_t)rows * v.n_pieces * sizeof(VT));
+        p += part_bytes(v, span_rows);
         part_max = reinterpret_cast<VT*>(p);
-    }
-    static size_t total(const PlanView& v, int64_t rows) {
-        return z_bytes(v, rows) + 2 * pad((size_t)rows * v.n_pieces * sizeof(VT));
     }
 };
 
@@ -920,18 +942,14 @@ static int sm_count() {
     return n;
 }
 
+// One chunk: permute -> tile kernel.  part_sum / part_max: where this chunk's rows start in the span group's piece arrays.
 template <typename VT, int R>
-static int launch_mass(const PlanView& v, const void* ws, int in_type, int64_t ld_ws, bool log_input, const Scratch<VT, R>& sc,
+static int launch_mass(const PlanView& v, const void* ws, int in_type, int64_t ld_ws, bool log_input, VT* z, VT* part_sum, VT* part_max,
                        VT* out_sum, VT* out_max, int64_t ld_out, int rows, unsigned ops, unsigned phases, cudaStream_t st) {
-    if (v.NT == 0) {  // empty vocabulary: the root is the only node and has no mass
-        for (VT* out : {out_sum, out_max})
-            if (out) GT_CUDA(cudaMemset2DAsync(out, (size_t)ld_out * sizeof(VT), 0, (size_t)v.N * sizeof(VT), (size_t)rows, st));
-        return GT_OK;
-    }
     MassArgs<VT> A;
     A.ws = ws; A.in_type = in_type; A.log_input = log_input ? 1 : 0; A.ld_ws = ld_ws;
-    A.z = sc.z;
-    A.out_sum = out_sum; A.out_max = out_max; A.part_sum = sc.part_sum; A.part_max = sc.part_max;
+    A.z = z;
+    A.out_sum = out_sum; A.out_max = out_max; A.part_sum = part_sum; A.part_max = part_max;
     A.ld_out = ld_out; A.n_rows = rows; A.ops = ops;
     const int RG = (rows + R - 1) / R;
     if (phases & GT_FLAG_PHASE_PERMUTE) {  // one warp per unit of 128 (fp64 rows: 64) positions of a row group
@@ -955,12 +973,21 @@ static int launch_mass(const PlanView& v, const void* ws, int in_type, int64_t l
         NvtxRange nv("gt:tile");
         GT_CUDA(launch_pdl(mass_kernel<VT, R>, dim3(grid), dim3(kThreads), smem, st, v, A));
     }
-    if (v.n_span > 0 && (phases & GT_FLAG_PHASE_SPAN)) {
-        const int nops = (ops == (unsigned)(GT_OP_SUM | GT_OP_MAX)) ? 2 : 1;
-        dim3 sgrid((unsigned)((v.n_span + 255) / 256), (unsigned)std::min(rows, 4096), (unsigned)nops);
-        NvtxRange nv("gt:span");
-        GT_CUDA(launch_pdl(span_kernel<VT>, sgrid, dim3(256), 0, st, v, A));
-    }
+    return GT_OK;
+}
+
+// The spanning nodes of the `rows` rows whose pieces start at part_sum / part_max and whose outputs start at out_sum / out_max.
+template <typename VT>
+static int launch_span(const PlanView& v, VT* part_sum, VT* part_max, VT* out_sum, VT* out_max, int64_t ld_out, int rows, unsigned ops,
+                       cudaStream_t st) {
+    if (v.n_span <= 0 || rows <= 0) return GT_OK;
+    MassArgs<VT> A{};
+    A.out_sum = out_sum; A.out_max = out_max; A.part_sum = part_sum; A.part_max = part_max;
+    A.ld_out = ld_out; A.n_rows = rows; A.ops = ops;
+    const int nops = (ops == (unsigned)(GT_OP_SUM | GT_OP_MAX)) ? 2 : 1;
+    dim3 sgrid((unsigned)((v.n_span + 255) / 256), (unsigned)std::min(rows, 4096), (unsigned)nops);
+    NvtxRange nv("gt:span");
+    GT_CUDA(launch_pdl(span_kernel<VT>, sgrid, dim3(256), 0, st, v, A));
     return GT_OK;
 }
 
@@ -968,38 +995,43 @@ template <typename VT, int R>
 static int reduce_typed(const PlanView& v, const void* ws, int in_type, int64_t n_rows, int64_t ld_ws, void* out_sum,
                         void* out_max, int64_t ld_out, unsigned ops, unsigned flags, void* workspace,
                         size_t workspace_bytes, cudaStream_t st) {
-    // rows per launch: what the caller's scratch can stage (whole row groups when it holds at least one; a partial row
-    // group is legal: the kernels alias the missing rows to the last valid one)
-    int64_t chunk = std::min<int64_t>(n_rows, 32768);
-    if (Scratch<VT, R>::total(v, chunk) > workspace_bytes) {
-        const size_t per_group = (size_t)v.ZG * R * sizeof(VT) + 2 * (size_t)R * v.n_pieces * sizeof(VT) + 1024;
-        chunk = std::min<int64_t>(chunk, (int64_t)(workspace_bytes / per_group) * R);
-        while (chunk > 0 && Scratch<VT, R>::total(v, chunk) > workspace_bytes) chunk -= R;
-        if (chunk <= 0) {  // less than a row group: row by row
-            chunk = R - 1;
-            while (chunk > 0 && Scratch<VT, R>::total(v, chunk) > workspace_bytes) --chunk;
-        }
-    }
-    if (chunk < 1) {
-        set_error("workspace too small: %zu bytes given, one row needs %zu", workspace_bytes, Scratch<VT, R>::total(v, 1));
-        return GT_ERR_STATE;
-    }
     if (in_type != GT_F32 && in_type != GT_F64 && in_type != GT_F16 && in_type != GT_BF16) {
         set_error("unknown input type %d", in_type);
         return GT_ERR_ARG;
     }
+    VT* osum = (ops & GT_OP_SUM) ? static_cast<VT*>(out_sum) : nullptr;
+    VT* omax = (ops & GT_OP_MAX) ? static_cast<VT*>(out_max) : nullptr;
+    if (v.NT == 0) {  // empty vocabulary: the root is the only node and has no mass
+        for (VT* out : {osum, omax})
+            if (out) GT_CUDA(cudaMemset2DAsync(out, (size_t)ld_out * sizeof(VT), 0, (size_t)v.N * sizeof(VT), (size_t)n_rows, st));
+        return GT_OK;
+    }
+    // rows per launch: what the caller's scratch can stage (a partial row group is legal: the kernels alias the missing
+    // rows to the last valid one)
+    const Scratch<VT, R> sc(v, workspace, workspace_bytes);
+    if (sc.chunk_rows < 1) {
+        set_error("workspace too small: %zu bytes given, one row needs %zu", workspace_bytes, Scratch<VT, R>::total(v, 1, 1));
+        return GT_ERR_STATE;
+    }
     const bool log_input = (flags & GT_FLAG_LOG_INPUT) != 0;
     const unsigned phases = (flags & GT_FLAG_PHASE_MASK) ? (flags & GT_FLAG_PHASE_MASK) : GT_FLAG_PHASE_MASK;
     const size_t in_size = in_type == GT_F64 ? 8 : in_type == GT_F32 ? 4 : 2;
-    for (int64_t r0 = 0; r0 < n_rows; r0 += chunk) {
-        const int rows = (int)std::min<int64_t>(chunk, n_rows - r0);
-        const Scratch<VT, R> sc(v, workspace, rows);
-        const void* wsr = static_cast<const char*>(ws) + (size_t)r0 * ld_ws * in_size;
-        const int rc = launch_mass<VT, R>(v, wsr, in_type, ld_ws, log_input, sc,
-                                          (ops & GT_OP_SUM) ? static_cast<VT*>(out_sum) + (size_t)r0 * ld_out : nullptr,
-                                          (ops & GT_OP_MAX) ? static_cast<VT*>(out_max) + (size_t)r0 * ld_out : nullptr, ld_out,
-                                          rows, ops, phases, st);
-        if (rc != GT_OK) return rc;
+    for (int64_t s0 = 0; s0 < n_rows; s0 += sc.span_rows) {  // span groups
+        const int64_t s1 = std::min<int64_t>(n_rows, s0 + sc.span_rows);
+        for (int64_t r0 = s0; r0 < s1; r0 += sc.chunk_rows) {  // chunks
+            const int rows = (int)std::min<int64_t>(sc.chunk_rows, s1 - r0);
+            const void* wsr = static_cast<const char*>(ws) + (size_t)r0 * ld_ws * in_size;
+            const size_t poff = (size_t)(r0 - s0) * v.n_pieces;
+            const int rc = launch_mass<VT, R>(v, wsr, in_type, ld_ws, log_input, sc.z, sc.part_sum + poff, sc.part_max + poff,
+                                              osum ? osum + (size_t)r0 * ld_out : nullptr, omax ? omax + (size_t)r0 * ld_out : nullptr,
+                                              ld_out, rows, ops, phases, st);
+            if (rc != GT_OK) return rc;
+        }
+        if (phases & GT_FLAG_PHASE_SPAN) {
+            const int rc = launch_span<VT>(v, sc.part_sum, sc.part_max, osum ? osum + (size_t)s0 * ld_out : nullptr,
+                                           omax ? omax + (size_t)s0 * ld_out : nullptr, ld_out, (int)(s1 - s0), ops, st);
+            if (rc != GT_OK) return rc;
+        }
     }
     return GT_OK;
 }
@@ -1121,7 +1153,9 @@ size_t gt_workspace_bytes(const gt_trie* t, int64_t max_rows) {
     if (!t || !t->plan || max_rows <= 0) return 0;
     gt::PlanView v{};
     v.ZG = (int64_t)t->plan->NT * t->plan->T; v.n_pieces = t->plan->n_pieces;
-    return gt::Scratch<double, 2>::total(v, max_rows) + 256;
+    // staging for one chunk + the pieces of one span group, sized for the fp64 pipeline (the fp32 one needs half)
+    return gt::Scratch<double, 2>::total(v, std::min<int64_t>(max_rows, gt::Scratch<double, 2>::max_chunk()),
+                                         std::min<int64_t>(max_rows, gt::kMaxSpanRows)) + 256;
 }
 
 int gt_weight_reduce(const gt_trie* t, const void* ws, int in_type, int64_t n_rows, int64_t ld_ws, void* out_sum,

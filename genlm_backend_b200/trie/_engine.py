@@ -22,9 +22,10 @@ _IN_TYPES = {
 _OUT_TYPES = {torch.float32: _lib.GT_F32, torch.float64: _lib.GT_F64}
 OPS = {"sum": _lib.GT_OP_SUM, "max": _lib.GT_OP_MAX}
 
-# rows whose staging scratch we keep per stream (the C side processes larger batches in chunks of this many rows):
-# 64 rows of staging are 34 MB at 128k tokens and stay in L2 between the permute warps and the copy engine
-_WORKSPACE_ROWS = int(os.environ.get("GT_WORKSPACE_ROWS", "64"))
+# rows the per-stream scratch is sized for: gt_workspace_bytes caps the staging part at one 64-row chunk (34 MB at 128k
+# tokens: it stays in L2 between the permute and the tile kernel) and keeps spanning-node pieces for up to 1,024 rows, so
+# that one span kernel serves a whole large batch
+_WORKSPACE_ROWS = int(os.environ.get("GT_WORKSPACE_ROWS", "1024"))
 _MAX_WORKSPACES = 16  # per engine: (device, stream) pairs we keep scratch for
 
 

@@ -121,9 +121,11 @@ int64_t gt_export_plan_array(const gt_trie* t, const char* name, void* dst, int6
  * Returns the element count, or -1 when no trace buffer exists.  tools/trace_tile.py prints the phase durations. */
 int64_t gt_debug_read_trace(const gt_trie* t, int device, long long* dst, int64_t capacity, int32_t dims[3]);
 
-/* Caller-owned scratch needed to process up to max_rows rows per launch (larger batches are processed in
- * chunks of what the scratch holds).  One call at a time may use a workspace: calls that share one must be
- * ordered (same stream).  The pointer must be 256-byte aligned. */
+/* Caller-owned scratch for batches of up to max_rows rows: the staging buffer of one chunk (at most 64 rows: it
+ * should stay L2-resident between the permute and the tile kernel) plus the spanning-node pieces of min(max_rows, 1024)
+ * rows, so that the span kernel runs once per 1,024 rows.  Larger batches, or a smaller workspace, are processed in
+ * as many chunks / span groups as it takes (any size that holds one row works).  One call at a time may use a
+ * workspace: calls that share one must be ordered (same stream).  The pointer must be 256-byte aligned. */
 size_t gt_workspace_bytes(const gt_trie* t, int64_t max_rows);
 
 /* ---- trie mass kernels -------------------------------------------------------------------- */

@@ -303,10 +303,11 @@ def test_rows_of_any_alignment(V, dtype):
 
 @pytest.mark.parametrize("V,B,dtype", [(4100, 200, torch.float32), (4104, 131, torch.bfloat16), (4104, 150, torch.float16),
                                        (4098, 140, torch.float64), (20480, 129, torch.float32), (4099, 140, torch.float32),
-                                       (4101, 133, torch.float32)])
+                                       (4101, 133, torch.float32), (2050, 1100, torch.float32)])
 def test_batches_above_the_scratch_rows(V, B, dtype):
-    """Batches larger than the engine's scratch (64 rows of staging): processed chunk by chunk on the C side.  Aligned and
-    unaligned rows, every input type, both reductions, partial last chunk and row group, against the oracle."""
+    """Batches larger than the engine's scratch (64 rows of staging, spanning-node pieces of 1,024 rows): processed chunk
+    by chunk on the C side, one span kernel per span group (B = 1,100: two span groups).  Aligned and unaligned rows,
+    every input type, both reductions, partial last chunk and row group, against the oracle."""
     trie = ParallelTokenCharacterTrie(synth_vocab(V, seed=V % 11))
     o = oracle_for(trie)
     pad = (-V) % 8 if V == 4101 else 0  # row stride 4104 elements: aligned rows whose length is not a multiple of 16 bytes
