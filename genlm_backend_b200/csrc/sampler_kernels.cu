@@ -359,7 +359,13 @@ __global__ void __launch_bounds__(NT, 1024 / NT) lse_sample_kernel(SampleArgs A)
         float m = -INFINITY, s = 0.f;
         // groups in flight per thread: 64 bytes of row (+ mask words); one group for 2-byte rows under an additive mask,
         // whose 32 mask bytes per group would otherwise push the loop into spills
-        constexpr int U = (EPV >= 8 && MK == GT_MASK_ADD_F32) ? 1 : (EPV >= 8 || MK == GT_MASK_ADD_F32) ? 2 : 4;
+#ifndef GT_S_U2B
+#define GT_S_U2B 2
+#endif
+#ifndef GT_S_UH2B
+#define GT_S_UH2B GT_S_U2B
+#endif
+        constexpr int U = (EPV >= 8 && MK == GT_MASK_ADD_F32) ? 1 : EPV >= 8 ? GT_S_U2B : MK == GT_MASK_ADD_F32 ? 2 : 4;
         const int g_lo = rv.phase ? 1 : 0, g_hi = (rv.phase + rv.V) / EPV;  // interior groups: [g_lo, g_hi)
         const int g0 = tid < g_lo ? tid + NT : tid;
         const int cnt = g0 < g_hi ? (g_hi - 1 - g0) / NT + 1 : 0;
@@ -376,7 +382,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) lse_sample_kernel(SampleArgs A)
                 const bool more = r + 1 < rounds;
                 // the (max, sum) update runs over UH groups at a time: all of the round's values at once is the
                 // cheapest, half a round keeps the byte-mask variant inside the register budget of 2 CTAs per SM
-                constexpr int UH = (MK == GT_MASK_BOOL_U8 && U == 4) ? 2 : U;
+                constexpr int UH = (EPV >= 8 && MK != GT_MASK_ADD_F32) ? (GT_S_UH2B < U ? GT_S_UH2B : U) : (MK == GT_MASK_BOOL_U8 && U == 4) ? 2 : U;
 #pragma unroll
                 for (int h = 0; h < U; h += UH) {
                     float y[UH * EPV];
