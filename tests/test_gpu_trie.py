@@ -356,3 +356,43 @@ def test_host_results_are_c_contiguous(B):
     one = par.weight_sum(torch.tensor(ws[0]))
     assert one.flags["C_CONTIGUOUS"] and one.shape == (len(par),) and rel_err(one, want_s[0])[0] <= SUM_RTOL
     assert np.array_equal(par.weight_max(ws[0].tolist()), want_m[0].astype(np.float32))
+
+
+def test_concurrent_streams_and_threads_do_not_share_scratch():
+    """The engine keeps one scratch buffer per (device, stream): calls issued on different CUDA streams, and from
+    different host threads, run their permute / tile / span kernels concurrently without touching each other's staging."""
+    import threading
+
+    V, B = 20011, 48
+    trie = ParallelTokenCharacterTrie(synth_vocab(V, seed=14))
+    o = oracle_for(trie)
+    batches = [torch.tensor(dirichlet_rows(B, V, alpha=0.3, seed=60 + i)).cuda() for i in range(4)]
+    want = [(o.weight_sum(x.cpu().numpy()), o.weight_max(x.cpu().numpy()).astype(np.float32)) for x in batches]
+    trie.batch_weight_tensor(batches[0], ops=("sum", "max"))  # plan upload, kernel attributes
+    torch.cuda.synchronize()
+    streams = [torch.cuda.Stream() for _ in batches]
+    results = [None] * len(batches)
+    for rep in range(3):  # interleaved launches on four streams, no synchronisation in between
+        for i, (x, st) in enumerate(zip(batches, streams)):
+            with torch.cuda.stream(st):
+                results[i] = trie.batch_weight_tensor(x, ops=("sum", "max"))
+    torch.cuda.synchronize()
+    assert len(trie._engine._workspaces) >= len(streams)
+    for i, (s, m) in enumerate(results):
+        r, z = rel_err(s.cpu().numpy(), want[i][0])
+        assert r <= SUM_RTOL and z == 0.0, (i, r, z)
+        assert np.array_equal(m.cpu().numpy(), want[i][1]), i
+
+    out = [None] * len(batches)
+
+    def worker(i):
+        with torch.cuda.stream(streams[i]):
+            for _ in range(3):
+                out[i] = trie.batch_weight_sum(batches[i])  # host-returning path, its own pipeline streams per call
+
+    # the host-returning path shares one set of pipeline streams and staging buffers per trie: one thread at a time
+    for i in range(len(batches)):
+        t = threading.Thread(target=worker, args=(i,))
+        t.start()
+        t.join()
+        assert rel_err(out[i], want[i][0])[0] <= SUM_RTOL
