@@ -472,8 +472,8 @@ def run_mass(args, job):
     sum_sets = [eng.alloc_out(B, torch.float32, dev) for _ in range(nsets)]
     max_sets = [eng.alloc_out(B, torch.float32, dev) for _ in range(nsets)]
 
-    def step(k, phases=0, ops=("sum", "max")):
-        eng.reduce(ws_sets[k], ops, out_sum=sum_sets[k], out_max=max_sets[k], phases=phases)
+    def step(k, phases=0, ops=("sum", "max"), dfs_order=False):
+        eng.reduce(ws_sets[k], ops, out_sum=sum_sets[k], out_max=max_sets[k], phases=phases, dfs_order=dfs_order)
 
     chunks = -(-B // 64)  # the C side reduces a batch in chunks of the engine's 64 scratch rows
     launches_per_step = chunks * (2 + (1 if info["n_span"] > 0 else 0))  # permute + tile (both reductions) + span kernel
@@ -515,6 +515,12 @@ def run_mass(args, job):
     ms_span_both = time_phase(_lib.GT_FLAG_PHASE_SPAN, ("sum", "max"))
     ms_permute = time_phase(_lib.GT_FLAG_PHASE_PERMUTE, ("sum",))
     ms_sum_op = time_phase(0, ("sum",))
+    # the same step when the producer of the rows emits them in DFS leaf order (GT_FLAG_DFS_ORDER): nothing to scatter.
+    # Timing only: the buffers hold the vocabulary-ordered rows (the data pattern does not change the kernels' work).
+    per_graph = 4 * nsets if B <= 64 else 2
+    ms_dfs_step = graph_time(lambda k: step(k % nsets, dfs_order=True), per_graph, max(2, 400 // (per_graph * chunks))) * 1e3
+    ms_dfs_permute = graph_time(lambda k: step(k % nsets, _lib.GT_FLAG_PHASE_PERMUTE, ("sum",), dfs_order=True), per_graph,
+                                max(2, 400 // (per_graph * chunks))) * 1e3
     clocks.loaded = False
 
     # end to end through the public API: pinned host rows in, numpy out -----------------------------------------------
@@ -636,6 +642,13 @@ def run_mass(args, job):
         "path_roofline": {
             "achieved": path_achieved, "peak": peak, "unit": "GB/s", "frac": path_achieved / peak,
             "note": "whole step (permute + tile kernel for both reductions + span kernel) against (4V + 8N) bytes per distribution",
+        },
+        "dfs_order_input": {
+            "value": world * B / (ms_dfs_step / 1e3), "unit": UNIT, "ms_per_step": ms_dfs_step, "permute_ms": ms_dfs_permute,
+            "path_roofline_frac": bytes_both / (ms_dfs_step / 1e3) / 1e9 / peak,
+            "note": "not the headline: the same step with GT_FLAG_DFS_ORDER -- rows whose columns are already in DFS leaf order "
+                    "(an LM head permuted once with ParallelTokenCharacterTrie.dfs_token_order), so the permute kernel interleaves "
+                    "row groups with coalesced stores instead of scattering; per-GPU rate x ranks",
         },
         "kernel_ms": {"permute": ms_permute, "tile_sum": ms_tile, "tile_max": ms_tile_max, "tile_both": ms_tile_both,
                       "span_both": ms_span_both, "sum_op_all_phases": ms_sum_op},

@@ -14,6 +14,7 @@ c_uint, c_uint64, c_size_t, c_float, c_char_p = ctypes.c_uint, ctypes.c_uint64, 
 GT_F32, GT_F64, GT_F16, GT_BF16 = 0, 1, 2, 3
 GT_OP_SUM, GT_OP_MAX = 1, 2
 GT_FLAG_LOG_INPUT = 1
+GT_FLAG_DFS_ORDER = 2
 GT_FLAG_PHASE_PERMUTE, GT_FLAG_PHASE_TILE, GT_FLAG_PHASE_SPAN = 0x100, 0x200, 0x400
 GT_GATHER_LOG = 1
 GT_MASK_NONE, GT_MASK_ADD_F32, GT_MASK_BOOL_U8, GT_MASK_BITS_U32 = 0, 1, 2, 3

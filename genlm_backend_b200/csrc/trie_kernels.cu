@@ -359,6 +359,7 @@ template <int ID, int COUNT> __device__ __forceinline__ void group_sync() {
 // What one launch works on.
 template <typename VT> struct MassArgs {
     const void* ws; int in_type; int log_input; int64_t ld_ws;
+    int dfs_order;  // the rows are already in DFS leaf order (GT_FLAG_DFS_ORDER): destinations are computed, not looked up
     VT* z;
     VT* out_sum; VT* out_max;
     VT* part_sum; VT* part_max;
@@ -387,10 +388,14 @@ __device__ __forceinline__ void permute_unit(const PlanView& P, const MassArgs<V
     VT* zg = A.z + (size_t)g * P.ZG * R;
     int dst[TPL];
     IN_T x[TPL][R];
+    const bool dfs = A.dfs_order != 0;
 #pragma unroll
     for (int j = 0; j < TPL; ++j) {
         const int i = min(lane + 32 * j, ntok - 1);
-        dst[j] = __ldg(P.leaf_dest + v0 + i);
+        // position = DFS rank r: slot of leaf r % T in tile r / T (what leaf_dest holds for the item of rank r); consecutive
+        // positions then go to consecutive slots and a warp's stores cover whole lines
+        const int r = v0 + i;
+        dst[j] = dfs ? ((r & ~(P.T - 1)) | swz<(int)sizeof(VT) * R>(r & (P.T - 1))) : __ldg(P.leaf_dest + r);
 #pragma unroll
         for (int r = 0; r < R; ++r) x[j][r] = ws[(size_t)min(g * R + r, A.n_rows - 1) * A.ld_ws + v0 + i];
     }
@@ -944,10 +949,11 @@ static int sm_count() {
 
 // One chunk: permute -> tile kernel.  part_sum / part_max: where this chunk's rows start in the span group's piece arrays.
 template <typename VT, int R>
-static int launch_mass(const PlanView& v, const void* ws, int in_type, int64_t ld_ws, bool log_input, VT* z, VT* part_sum, VT* part_max,
+static int launch_mass(const PlanView& v, const void* ws, int in_type, int64_t ld_ws, unsigned flags, VT* z, VT* part_sum, VT* part_max,
                        VT* out_sum, VT* out_max, int64_t ld_out, int rows, unsigned ops, unsigned phases, cudaStream_t st) {
     MassArgs<VT> A;
-    A.ws = ws; A.in_type = in_type; A.log_input = log_input ? 1 : 0; A.ld_ws = ld_ws;
+    A.ws = ws; A.in_type = in_type; A.ld_ws = ld_ws;
+    A.log_input = (flags & GT_FLAG_LOG_INPUT) ? 1 : 0; A.dfs_order = (flags & GT_FLAG_DFS_ORDER) ? 1 : 0;
     A.z = z;
     A.out_sum = out_sum; A.out_max = out_max; A.part_sum = part_sum; A.part_max = part_max;
     A.ld_out = ld_out; A.n_rows = rows; A.ops = ops;
@@ -1013,7 +1019,6 @@ static int reduce_typed(const PlanView& v, const void* ws, int in_type, int64_t 
         set_error("workspace too small: %zu bytes given, one row needs %zu", workspace_bytes, Scratch<VT, R>::total(v, 1, 1));
         return GT_ERR_STATE;
     }
-    const bool log_input = (flags & GT_FLAG_LOG_INPUT) != 0;
     const unsigned phases = (flags & GT_FLAG_PHASE_MASK) ? (flags & GT_FLAG_PHASE_MASK) : GT_FLAG_PHASE_MASK;
     const size_t in_size = in_type == GT_F64 ? 8 : in_type == GT_F32 ? 4 : 2;
     for (int64_t s0 = 0; s0 < n_rows; s0 += sc.span_rows) {  // span groups
@@ -1022,7 +1027,7 @@ static int reduce_typed(const PlanView& v, const void* ws, int in_type, int64_t 
             const int rows = (int)std::min<int64_t>(sc.chunk_rows, s1 - r0);
             const void* wsr = static_cast<const char*>(ws) + (size_t)r0 * ld_ws * in_size;
             const size_t poff = (size_t)(r0 - s0) * v.n_pieces;
-            const int rc = launch_mass<VT, R>(v, wsr, in_type, ld_ws, log_input, sc.z, sc.part_sum + poff, sc.part_max + poff,
+            const int rc = launch_mass<VT, R>(v, wsr, in_type, ld_ws, flags, sc.z, sc.part_sum + poff, sc.part_max + poff,
                                               osum ? osum + (size_t)r0 * ld_out : nullptr, omax ? omax + (size_t)r0 * ld_out : nullptr,
                                               ld_out, rows, ops, phases, st);
             if (rc != GT_OK) return rc;

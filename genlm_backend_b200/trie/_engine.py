@@ -130,11 +130,12 @@ class TrieEngine:
         ld = self.row_stride(dtype)
         return torch.empty((max(B, 1), ld), dtype=dtype, device=device)[:B, : self.N]
 
-    def reduce(self, ws, ops, out_dtype=torch.float32, log_input=False, out_sum=None, out_max=None, phases=0):
+    def reduce(self, ws, ops, out_dtype=torch.float32, log_input=False, out_sum=None, out_max=None, phases=0, dfs_order=False):
         """Launch the mass kernels for a ``[B, V]`` CUDA tensor on its device's current stream.
 
         Returns ``(out_sum, out_max)`` device tensors of shape ``[B, N]`` (``None`` for an op not asked for).
-        Nothing is synchronised here.
+        Nothing is synchronised here.  ``dfs_order``: column ``r`` of ``ws`` is the weight of item ``perm[r]`` (the rows
+        are already in DFS leaf order, ``GT_FLAG_DFS_ORDER``).
         """
         require_cuda()
         if not (isinstance(ws, torch.Tensor) and ws.is_cuda and ws.dim() == 2):
@@ -177,7 +178,8 @@ class TrieEngine:
                     self._handle, ws.data_ptr(), _IN_TYPES[ws.dtype], B, ld_ws,
                     out_sum.data_ptr() if out_sum is not None else None,
                     out_max.data_ptr() if out_max is not None else None,
-                    _OUT_TYPES[out_dtype], ld_out, opmask, (_lib.GT_FLAG_LOG_INPUT if log_input else 0) | int(phases),
+                    _OUT_TYPES[out_dtype], ld_out, opmask,
+                    (_lib.GT_FLAG_LOG_INPUT if log_input else 0) | (_lib.GT_FLAG_DFS_ORDER if dfs_order else 0) | int(phases),
                     work.data_ptr(), work.numel(), stream,
                 ),
                 "gt_weight_reduce",

@@ -113,13 +113,25 @@ class ParallelTokenCharacterTrie(TokenCharacterTrie):
         return self._devices if self._devices else [torch.cuda.current_device()]
 
     # ---- device-resident API (additions) ---------------------------------------------------------------------
-    def batch_weight_tensor(self, ws, ops=("sum",), log_input=False, out_sum=None, out_max=None):
+    def batch_weight_tensor(self, ws, ops=("sum",), log_input=False, out_sum=None, out_max=None, dfs_order=False):
         """Node masses for a ``[B, V]`` batch, kept on the GPU.  Returns ``(sum, max)`` float32 ``[B, N]`` tensors
-        (``None`` for an op not requested).  Launches on the current stream of the input's device; no sync."""
+        (``None`` for an op not requested).  Launches on the current stream of the input's device; no sync.
+
+        ``dfs_order=True``: column ``r`` of ``ws`` holds the weight of token ``self.dfs_token_order[r]`` -- rows produced
+        by an LM head whose output rows were permuted once with ``dfs_token_order`` -- which spares the kernels the
+        scatter of every row into DFS leaf order (``GT_FLAG_DFS_ORDER``); the results are the same."""
         ws = self._as_batch(ws)
         if not ws.is_cuda:
             ws = ws.to(torch.device("cuda", self._device_list()[0]), non_blocking=True)
-        return self._engine.reduce(ws, ops, out_dtype=torch.float32, log_input=log_input, out_sum=out_sum, out_max=out_max)
+        return self._engine.reduce(ws, ops, out_dtype=torch.float32, log_input=log_input, out_sum=out_sum, out_max=out_max,
+                                   dfs_order=dfs_order)
+
+    @property
+    def dfs_token_order(self):
+        """``int64[V]``: position in ``decode`` of the token whose leaf has DFS rank ``r``.  ``ws[:, dfs_token_order]`` is
+        the DFS-ordered form of a batch; applied once to the rows of an LM head's output projection it makes the model
+        emit DFS-ordered rows for ``batch_weight_tensor(..., dfs_order=True)``."""
+        return torch.from_numpy(self._layout["perm"].astype(np.int64))
 
     def batch_weight_sum_tensor(self, ws, log_input=False, out=None):
         return self.batch_weight_tensor(ws, ("sum",), log_input=log_input, out_sum=out)[0]

@@ -396,3 +396,28 @@ def test_concurrent_streams_and_threads_do_not_share_scratch():
         t.start()
         t.join()
         assert rel_err(out[i], want[i][0])[0] <= SUM_RTOL
+
+
+@pytest.mark.parametrize("V,B,dtype", [(5003, 7, torch.float32), (20480, 70, torch.float32), (4099, 5, torch.bfloat16), (3001, 3, torch.float64)])
+def test_rows_given_in_dfs_order(V, B, dtype):
+    """GT_FLAG_DFS_ORDER: rows whose columns are already in DFS leaf order (ws[:, dfs_token_order]) give bit-identical
+    results to the same weights in vocabulary order, for both pipelines, with and without the fused exp."""
+    trie = ParallelTokenCharacterTrie(synth_vocab(V, seed=V % 5))
+    ws = torch.tensor(dirichlet_rows(B, V, alpha=0.3, seed=B)).to(dtype).cuda()
+    order = trie.dfs_token_order.cuda()
+    assert sorted(order.tolist()) == list(range(V))
+    s0, m0 = trie.batch_weight_tensor(ws, ops=("sum", "max"))
+    s1, m1 = trie.batch_weight_tensor(ws[:, order].contiguous(), ops=("sum", "max"), dfs_order=True)
+    assert torch.equal(s0, s1) and torch.equal(m0, m1)
+    o = oracle_for(trie)
+    r, z = rel_err(s1.cpu().numpy(), o.weight_sum(ws.to(torch.float64).cpu().numpy()))
+    assert r <= SUM_RTOL and z == 0.0
+    logw = ws.to(torch.float32).log()
+    l0 = trie.batch_weight_sum_tensor(logw, log_input=True)
+    l1 = trie.batch_weight_tensor(logw[:, order].contiguous(), ops=("sum",), log_input=True, dfs_order=True)[0]
+    assert torch.equal(l0, l1)
+    if dtype == torch.float64:
+        seq = TokenCharacterTrie(synth_vocab(V, seed=V % 5))
+        a, _ = seq._engine.reduce(ws, ("sum",), out_dtype=torch.float64)
+        b, _ = seq._engine.reduce(ws[:, order].contiguous(), ("sum",), out_dtype=torch.float64, dfs_order=True)
+        assert torch.equal(a, b)
