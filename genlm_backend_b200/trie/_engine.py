@@ -51,6 +51,7 @@ class TrieEngine:
         self.nnz = int(lib.gt_num_reach(handle))
         self._uploaded = set()
         self._workspaces = {}
+        self._ld32 = None
 
     def __del__(self):
         h = getattr(self, "_handle", None)
@@ -185,6 +186,33 @@ class TrieEngine:
                 "gt_weight_reduce",
             )
         return out_sum, out_max
+
+    def reduce_raw(self, ws, opmask, log_input, index, stream_ptr):
+        """``reduce`` without the checks, for the few-row latency path: ``ws`` is a contiguous float32 / fp16 / bf16
+        ``[B, V]`` tensor on device ``index``, which is the current device; launches on the raw stream ``stream_ptr``.
+        Returns the padded ``[B, row_stride]`` float32 slabs ``(sum, max)`` (``None`` for an op not in ``opmask``)."""
+        B = ws.shape[0]
+        if index not in self._uploaded:
+            self.ensure_device(index)
+        ld = self._ld32
+        if ld is None:
+            ld = self._ld32 = self.row_stride(torch.float32)
+        out_sum = torch.empty((B, ld), dtype=torch.float32, device=ws.device) if opmask & 1 else None
+        out_max = torch.empty((B, ld), dtype=torch.float32, device=ws.device) if opmask & 2 else None
+        work = self._workspace(index, stream_ptr, B)
+        rc = lib.gt_weight_reduce(
+            self._handle, ws.data_ptr(), _IN_TYPES[ws.dtype], B, self.V,
+            out_sum.data_ptr() if out_sum is not None else None, out_max.data_ptr() if out_max is not None else None,
+            _lib.GT_F32, ld, opmask, _lib.GT_FLAG_LOG_INPUT if log_input else 0, work.data_ptr(), work.numel(), stream_ptr)
+        if rc:
+            check(rc, "gt_weight_reduce")
+        return out_sum, out_max
+
+    def download_raw(self, slab, host_out, stream_ptr):
+        """Pitched D2H copy of a padded float32 slab from ``reduce_raw`` into a C-contiguous ``[B, N]`` pinned tensor."""
+        rc = lib.gt_download_rows(host_out.data_ptr(), self.N * 4, slab.data_ptr(), slab.stride(0) * 4, self.N * 4, slab.shape[0], stream_ptr)
+        if rc:
+            check(rc, "gt_download_rows")
 
     def download(self, dev_out, host_out, stream):
         """Pitched D2H copy (``gt_download_rows``) of a ``[rows, N]`` device result (row stride = the slab's padded

@@ -207,24 +207,35 @@ class ParallelTokenCharacterTrie(TokenCharacterTrie):
 
     def _small_to_host(self, ws, host_rows, ops, log_input, as_rows):
         """Latency path for a handful of rows: the caller's current stream only (no pipeline streams, no events), cached
-        device scratch, one H2D copy, the three kernels, one pitched D2H copy per reduction, one stream synchronisation."""
+        device scratch, one H2D copy, the three kernels, one pitched D2H copy per reduction, one stream synchronisation;
+        the engine is called through its check-free entry points (everything was validated on the way here)."""
         index = self._device_list()[0]
-        dev = torch.device("cuda", index)
         N = len(self)
-        with torch.cuda.device(index):
+        switch = torch.cuda.current_device() != index
+        if switch:
+            prev = torch.cuda.current_device()
+            torch.cuda.set_device(index)
+        try:
             st = torch.cuda.current_stream(index)
             if host_rows is not None:
                 ws = torch.stack(host_rows)
-            if not ws.is_cuda or ws.device != dev:
-                ws = ws.to(dev, non_blocking=True)
+            if not ws.is_cuda or ws.device.index != index:
+                ws = ws.to(torch.device("cuda", index), non_blocking=True)
+            if ws.stride(-1) != 1 or (ws.shape[0] > 1 and ws.stride(0) != ws.shape[1]):
+                ws = ws.contiguous()
             B = ws.shape[0]
-            o_sum, o_max = self._engine.reduce(ws, ops, log_input=log_input)
+            opmask = (1 if "sum" in ops else 0) | (2 if "max" in ops else 0)
+            sp = st.cuda_stream
+            slabs = self._engine.reduce_raw(ws, opmask, log_input, index, sp)
             outs = {}
-            for op, o in (("sum", o_sum), ("max", o_max)):
+            for op, o in zip(("sum", "max"), slabs):
                 if o is not None:
-                    outs[op] = torch.empty((B, N), dtype=torch.float32, pin_memory=True)
-                    self._engine.download(o, outs[op], st)
+                    h = outs[op] = torch.empty((B, N), dtype=torch.float32, pin_memory=True)
+                    self._engine.download_raw(o, h, sp)
             st.synchronize()
+        finally:
+            if switch:
+                torch.cuda.set_device(prev)
         if as_rows:
             return {op: list(o.numpy()) for op, o in outs.items()}
         return {op: o.numpy() for op, o in outs.items()}
