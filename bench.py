@@ -21,7 +21,9 @@ over ranks.
                  scatter_reduce amax, parallel.py:92-145) on the same B200, device-resident and end to end
   sampler        the SMC row op (configs[3] per-GPU share) with `reference` = the batched torch idiom of README.md:82-87
 
-Other workloads (BASELINE.json configs[2..4]; one JSON line each, same contract):
+Other workloads (BASELINE.json configs[0], [2..4]; one JSON line each, same contract):
+  cfg0           weight_sum + weight_max of ONE distribution at the GPT-2-sized vocabulary (50,257 tokens): call latency of
+                 both trie classes; the reference arm is the single-threaded CPU loop (what numba runs for one row)
   async1024      AsyncTokenCharacterTrie, 1,024 concurrent weight_sum requests at 128,256 tokens, requests sharded over ranks
   smc4096        fused masked logsumexp + multinomial, 4,096 particles x 128,256 tokens, particles sharded over ranks
   cfg5           batch_weight_sum + batch_weight_max at 151,665 tokens, 8,192 rows over 8 GPUs (1,024 per GPU),
@@ -51,7 +53,7 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "async1024", "smc4096", "cfg5"])
+    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg0", "async1024", "smc4096", "cfg5"])
     ap.add_argument("--vocab", type=int, default=0, help="0 = the workload's vocabulary (128256; cfg5: 151665)")
     ap.add_argument("--batch", type=int, default=0, help="rows per GPU and step; 0 = the workload's (cfg2: 64, cfg5: 1024)")
     ap.add_argument("--alpha", type=float, default=1.0)
@@ -67,9 +69,9 @@ def parse_args():
                          "reported separately, never part of the timed step")
     args = ap.parse_args()
     if not args.vocab:
-        args.vocab = 151665 if args.workload == "cfg5" else 128256
+        args.vocab = {"cfg5": 151665, "cfg0": 50257}.get(args.workload, 128256)
     if not args.batch:
-        args.batch = {"cfg2": 64, "cfg5": 1024, "async1024": 1024, "smc4096": 4096}[args.workload]
+        args.batch = {"cfg2": 64, "cfg0": 1, "cfg5": 1024, "async1024": 1024, "smc4096": 4096}[args.workload]
     return args
 
 
@@ -79,6 +81,11 @@ def peaks():
         with open(path) as f:
             return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def metric_name(args):
+    return {"cfg5": "trie weight_sum+weight_max distributions/sec at 151,665 vocab (config 5)",
+            "cfg0": "one-distribution weight_sum+weight_max calls/sec at 50,257 vocab (config 0)"}.get(args.workload, METRIC)
 
 
 def workload_name(args):
@@ -136,7 +143,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    if args.workload not in ("cfg2", "cfg5"):
+    if args.workload not in ("cfg2", "cfg5", "cfg0"):
         print(json.dumps({"impl": "reference", "unavailable": f"the reference arm covers the trie-mass workloads (cfg2, cfg5), not {args.workload}"}), flush=True)
         return
     import oracle
@@ -146,7 +153,7 @@ def run_reference(args):
     t0 = time.perf_counter()
     trie = oracle.OracleTrie(synth.synth_vocab_bytes(args.vocab))  # pure-Python restatement of base.py:13-122
     build_s = time.perf_counter() - t0
-    threads = host_threads()
+    threads = host_threads()  # OpenMP over the rows of a step: a one-row step (cfg0) runs on one thread, like the numba loop
     ws_steps = [synth.dirichlet_rows(args.batch, args.vocab, alpha=args.alpha, seed=100 + k) for k in range(2)]
     # bounded: at most ~60 s of timed steps
     probe, _ = cpu_steps(trie, ws_steps, threads, 1, 1)
@@ -161,7 +168,7 @@ def run_reference(args):
                     f"in C, fp64), OpenMP over the rows of a step with {used} threads (host has {os.cpu_count()} logical cpus, "
                     f"OMP_NUM_THREADS ignored); layout from oracle.OracleTrie ({build_s:.1f} s)"}
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "impl": "reference", "metric": metric_name(args), "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": K, "warmup": W, "ms_per_step": 1e3 * per_step,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_name(args), "vocab": args.vocab, "nodes": trie.n_nodes, "batch_per_gpu": args.batch,
@@ -603,7 +610,7 @@ def run_mass(args, job):
     if os.path.exists(tpath) and V == 128256 and B == 64:
         with open(tpath) as f:
             traffic = json.load(f)["traffic_bytes_per_launch"]
-    metric = METRIC if not cfg5 else "trie weight_sum+weight_max distributions/sec at 151,665 vocab (config 5)"
+    metric = metric_name(args)
     line = {
         "metric": metric, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -751,6 +758,77 @@ def run_smc(args, job):
     print(json.dumps(line), flush=True)
 
 
+# ---- BASELINE.json configs[0]: one distribution, GPT-2-sized vocabulary ---------------------------------------------------
+def run_single(args, job):
+    torch = job.torch
+    from genlm_backend_b200 import ParallelTokenCharacterTrie, TokenCharacterTrie
+    from genlm_backend_b200.synthetic import synth_vocab, dirichlet_rows
+
+    V, K, W = args.vocab, max(args.steps, 50), max(args.warmup, 3)
+    dec = synth_vocab(V)
+    row = torch.tensor(dirichlet_rows(1, V, alpha=args.alpha, seed=1)[0])
+    drow = row.to(job.dev)
+
+    def lat(fn):
+        t_end = time.perf_counter() + 0.3  # call latency depends on the clocks: let them ramp before timing
+        n = 0
+        while n < W or time.perf_counter() < t_end:
+            fn()
+            n += 1
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(K):
+            t0 = time.perf_counter()
+            fn()
+            ts.append(time.perf_counter() - t0)
+        return float(np.median(ts)), float(np.percentile(ts, 90))
+
+    res = {}
+    for name, cls in (("parallel", ParallelTokenCharacterTrie), ("sequential", TokenCharacterTrie)):
+        t0 = time.perf_counter()
+        trie = cls(dec)
+        build_s = time.perf_counter() - t0
+        both_cuda = lat(lambda: (trie.weight_sum(drow), trie.weight_max(drow)))
+        both_cpu = lat(lambda: (trie.weight_sum(row), trie.weight_max(row)))
+        res[name] = {"build_s": build_s, "sum_plus_max_cuda_row_us": both_cuda[0] * 1e6, "sum_plus_max_cuda_row_p90_us": both_cuda[1] * 1e6,
+                     "sum_plus_max_cpu_row_us": both_cpu[0] * 1e6, "sum_plus_max_cpu_row_p90_us": both_cpu[1] * 1e6,
+                     "result_dtype": str(trie.weight_sum(row).dtype)}
+        N = len(trie)
+        lay = trie._layout
+        idx = trie.idx_to_leaf
+    job.finish()
+    if job.rank != 0:
+        return
+    import oracle
+
+    o = oracle.OracleLayout(idx, lay["child_ptr"], lay["child_idx"])
+    w = row.numpy()[None, :]
+    o.weight_sum(w, threads=1)
+    ts = []
+    for _ in range(20):
+        t0 = time.perf_counter()
+        o.weight_sum(w, threads=1)
+        o.weight_max(w, threads=1)
+        ts.append(time.perf_counter() - t0)
+    cpu_s = float(np.median(ts))
+    par = res["parallel"]
+    line = {
+        "metric": metric_name(args),
+        "value": 1e6 / par["sum_plus_max_cuda_row_us"], "unit": UNIT, "n_gpus": 1, "steps": K, "warmup": W,
+        "ms_per_step": par["sum_plus_max_cuda_row_us"] / 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"weight_sum + weight_max of one Dirichlet({args.alpha:g}) distribution, synthetic byte vocab V={V} (N={N}), "
+                               "ParallelTokenCharacterTrie, numpy results; value: the row is a CUDA tensor, e2e: a CPU tensor; median wall clock of a call pair"},
+        "e2e": {"value": 1e6 / par["sum_plus_max_cpu_row_us"], "unit": UNIT, "h2d_bytes_per_step": 2 * V * 4, "d2h_bytes_per_step": 2 * N * 4,
+                "api": "ParallelTokenCharacterTrie.weight_sum(cpu tensor) + weight_max(cpu tensor) -> numpy"},
+        "gpu_launches": 6 * K, "classes": res,
+        "cpu_baseline": {"value": 1.0 / cpu_s, "unit": UNIT, "cores": 1, "kind": "port",
+                         "sample": "20 x (weight_sum + weight_max) of the same row, oracle/trie_oracle.c (numba loops of base.py:346-393 in C, fp64), "
+                                   "one thread: the reference processes a row on one thread"},
+    }
+    print(json.dumps(line), flush=True)
+
+
 # ---- BASELINE.json configs[2]: AsyncTokenCharacterTrie, 1,024 concurrent requests sharded over the ranks ----------------
 def run_async(args, job):
     import asyncio
@@ -815,6 +893,8 @@ def main():
     job = Job()
     if args.workload in ("cfg2", "cfg5"):
         run_mass(args, job)
+    elif args.workload == "cfg0":
+        run_single(args, job)
     elif args.workload == "smc4096":
         run_smc(args, job)
     else:

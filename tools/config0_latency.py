@@ -38,6 +38,8 @@ for cls in (ParallelTokenCharacterTrie, TokenCharacterTrie):
     build = time.perf_counter() - t0
     print(f"{cls.__name__}: build {build * 1e3:.0f} ms, N = {len(trie)}")
     for name, fn in (("weight_sum(cpu tensor)", lambda: trie.weight_sum(ws)), ("weight_max(cpu tensor)", lambda: trie.weight_max(ws)),
-                     ("weight_sum(cuda tensor)", lambda: trie.weight_sum(ws_dev))):
+                     ("weight_sum(cuda tensor)", lambda: trie.weight_sum(ws_dev)), ("weight_max(cuda tensor)", lambda: trie.weight_max(ws_dev)),
+                     ("sum + max (cuda tensor)", lambda: (trie.weight_sum(ws_dev), trie.weight_max(ws_dev))),
+                     ("sum + max (cpu tensor)", lambda: (trie.weight_sum(ws), trie.weight_max(ws)))):
         m, p90 = lat(fn)
         print(f"  {name:26s} median {m:8.1f} us   p90 {p90:8.1f} us")
