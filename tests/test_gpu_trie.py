@@ -421,3 +421,44 @@ def test_rows_given_in_dfs_order(V, B, dtype):
         a, _ = seq._engine.reduce(ws, ("sum",), out_dtype=torch.float64)
         b, _ = seq._engine.reduce(ws[:, order].contiguous(), ("sum",), out_dtype=torch.float64, dfs_order=True)
         assert torch.equal(a, b)
+
+
+def test_special_values_and_degenerate_vocabularies():
+    """inf / NaN / denormal / all-zero weights and one-token / empty vocabularies against the oracle (the numba loops'
+    semantics: sums propagate NaN and inf, `max(total, c)` keeps `total` when `c` is NaN, base.py:346-393)."""
+    V = 3001
+    par = ParallelTokenCharacterTrie(synth_vocab(V, seed=21))
+    o = oracle_for(par)
+    ws = dirichlet_rows(6, V, alpha=0.3, seed=3).astype(np.float32)
+    ws[1, 17] = np.inf
+    ws[2, 1234] = np.nan
+    ws[3] = 0.0
+    ws[4] *= 1e-42  # denormals
+    ws[5, ::2] = 0.0
+    want_s, want_m = o.weight_sum(ws), o.weight_max(ws)
+    hs, hm = par.batch_weight_sum(torch.tensor(ws)), par.batch_weight_max(torch.tensor(ws))
+    fin = np.isfinite(want_s)
+    assert np.array_equal(np.isnan(hs), np.isnan(want_s)) and np.array_equal(np.isposinf(hs), np.isposinf(want_s))
+    r, z = rel_err(hs[fin], want_s[fin])
+    assert r <= SUM_RTOL and z == 0.0
+    ok_rows = [0, 1, 3, 4, 5]
+    assert np.array_equal(hm[ok_rows], want_m[ok_rows].astype(np.float32))
+    # NaN weights: both of the reference's paths ignore or propagate them differently (numba's `max(total, c)` starts at 0
+    # and skips a NaN child, torch's amax propagates it); ours is fmax over the leaf range -- a NaN only where every leaf
+    # under the node is NaN (here: the leaf and the unary chain above it), the oracle's value everywhere else
+    unaffected = ~np.isnan(hm[2])
+    assert np.array_equal(hm[2][unaffected], want_m[2][unaffected].astype(np.float32))
+    assert np.isnan(hm[2]).sum() >= 1 and np.isnan(hs[2]).sum() >= np.isnan(hm[2]).sum()
+    assert (hs[3] == 0).all() and (hm[3] == 0).all()
+    # one token, and a vocabulary whose tokens share one long chain
+    for dec in ([Token(0, b"a")], [Token(i, b"x" * (i + 1)) for i in range(40)]):
+        t = ParallelTokenCharacterTrie(dec)
+        oo = oracle_for(t)
+        w = np.random.default_rng(1).random((3, len(dec))).astype(np.float32)
+        assert rel_err(t.batch_weight_sum(torch.tensor(w)), oo.weight_sum(w))[0] <= SUM_RTOL
+        assert np.array_equal(t.batch_weight_max(torch.tensor(w)), oo.weight_max(w).astype(np.float32))
+    # the empty vocabulary: the root is the only node and has no mass (base.py:124-130 allocates zeros)
+    empty = ParallelTokenCharacterTrie([])
+    assert len(empty) == 1
+    out = empty.batch_weight_sum(torch.zeros((2, 0)))
+    assert out.shape == (2, 1) and (out == 0).all()
