@@ -926,6 +926,8 @@ static int resident_ctas(const void* kernel, int threads, size_t smem) {
     auto it = cache.find(key);
     if (it != cache.end()) return it->second;
     int n = 0;
+    // the query honours the kernel's dynamic shared-memory limit: raise it first, or a size above it reports 0
+    if (allow_smem_impl(kernel, smem) != cudaSuccess) (void)cudaGetLastError();
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, threads, smem) != cudaSuccess || n < 1) {
         (void)cudaGetLastError();
         n = 1;
@@ -1021,10 +1023,11 @@ static int reduce_typed(const PlanView& v, const void* ws, int in_type, int64_t 
     }
     const unsigned phases = (flags & GT_FLAG_PHASE_MASK) ? (flags & GT_FLAG_PHASE_MASK) : GT_FLAG_PHASE_MASK;
     const size_t in_size = in_type == GT_F64 ? 8 : in_type == GT_F32 ? 4 : 2;
+    const int64_t chunk_rows = sc.chunk_rows;
     for (int64_t s0 = 0; s0 < n_rows; s0 += sc.span_rows) {  // span groups
         const int64_t s1 = std::min<int64_t>(n_rows, s0 + sc.span_rows);
-        for (int64_t r0 = s0; r0 < s1; r0 += sc.chunk_rows) {  // chunks
-            const int rows = (int)std::min<int64_t>(sc.chunk_rows, s1 - r0);
+        for (int64_t r0 = s0; r0 < s1; r0 += chunk_rows) {  // chunks
+            const int rows = (int)std::min<int64_t>(chunk_rows, s1 - r0);
             const void* wsr = static_cast<const char*>(ws) + (size_t)r0 * ld_ws * in_size;
             const size_t poff = (size_t)(r0 - s0) * v.n_pieces;
             const int rc = launch_mass<VT, R>(v, wsr, in_type, ld_ws, flags, sc.z, sc.part_sum + poff, sc.part_max + poff,
