@@ -1,7 +1,7 @@
 """Condenses an Nsight Compute report (.ncu-rep, read here without a GPU) into the text summary kept under profiles/:
 key raw metrics per kernel launch, warp-stall totals, and the hottest SASS instructions by stall samples.
 
-    python tools/ncu_summary.py gpurun_out/prof_tile.ncu-rep [launch index ...] > profiles/r01_tile_kernel_ncu.txt
+    python tools/ncu_summary.py gpurun_out/prof_tile.ncu-rep [launch index ...] > profiles/r02_step_kernels_ncu.txt
 """
 import csv
 import re
