@@ -10,6 +10,8 @@ Same signatures, same float32 numpy results in the reference's node order.  Addi
 of defaults): ``*_tensor`` methods that keep results on the device, ``log_input=True`` to fuse the
 ``exp`` of log-probabilities, and ``devices=[...]`` to shard batch rows over several GPUs.
 """
+import os
+
 import numpy as np
 import torch
 
@@ -23,6 +25,34 @@ _PIPE_FIRST = 8
 _PIPE_SLOTS = 3
 # batches of at most this many rows take the single-stream latency path
 _SMALL_BATCH = 8
+
+
+# CPU rows are gathered into the pinned staging buffer by a few threads: one thread copies ~10 GB/s, which would make the
+# host copy (0.5 MB per row at 128k tokens) the bottleneck of a 1,024-request batch (torch's copy releases the GIL)
+_COPY_THREADS = int(os.environ.get("GT_COPY_THREADS", "4"))
+_copy_pool = None
+
+
+def _copy_block(stage, rows, a, b):
+    for i in range(a, b):
+        stage[i].copy_(rows[i])
+
+
+def _gather_rows(rows, stage):
+    """``stage[i] = rows[i]`` for a list of 1-D CPU tensors."""
+    global _copy_pool
+    n = len(rows)
+    if n < 2 * _COPY_THREADS:
+        _copy_block(stage, rows, 0, n)
+        return
+    if _copy_pool is None:
+        from concurrent.futures import ThreadPoolExecutor
+
+        _copy_pool = ThreadPoolExecutor(max_workers=_COPY_THREADS, thread_name_prefix="trie-stage")
+    step = -(-n // _COPY_THREADS)
+    futs = [_copy_pool.submit(_copy_block, stage, rows, a, min(n, a + step)) for a in range(0, n, step)]
+    for f in futs:
+        f.result()
 
 
 def _pipe_slices(lo, hi):
@@ -274,7 +304,7 @@ class ParallelTokenCharacterTrie(TokenCharacterTrie):
                 with torch.cuda.device(index), torch.cuda.stream(st):
                     if host_rows is not None:
                         stage, staged = self._stage_buffer(index, k % _PIPE_SLOTS, _PIPE_ROWS)
-                        torch.stack(host_rows[r0:r1], out=stage[: r1 - r0])
+                        _gather_rows(host_rows[r0:r1], stage)
                         chunk = stage[: r1 - r0].to(dev, non_blocking=True)
                         staged.record(st)
                     else:
