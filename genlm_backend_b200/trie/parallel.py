@@ -11,6 +11,7 @@ of defaults): ``*_tensor`` methods that keep results on the device, ``log_input=
 ``exp`` of log-probabilities, and ``devices=[...]`` to shard batch rows over several GPUs.
 """
 import os
+import threading
 
 import numpy as np
 import torch
@@ -86,6 +87,9 @@ class ParallelTokenCharacterTrie(TokenCharacterTrie):
         self._reach = None
         self._streams = {}
         self._stage = {}  # (device, pipeline slot) -> (pinned [rows, V] staging buffer, event of its last H2D copy)
+        # the pipeline streams and staging buffers are per trie: one host-returning batch at a time (the async wrapper's
+        # worker thread and a direct caller may both be at it)
+        self._host_lock = threading.Lock()
         # position of each leaf's weight in the input rows (the identity: idx_to_leaf[:, 0])
         self.positions = torch.tensor(self.idx_to_leaf[:, 0], dtype=torch.long, device=self.device)
 
@@ -287,6 +291,10 @@ class ParallelTokenCharacterTrie(TokenCharacterTrie):
             return {op: ([] if as_rows else np.empty((0, N), dtype=np.float32)) for op in ops}
         if B <= _SMALL_BATCH:
             return self._small_to_host(ws, host_rows, ops, log_input, as_rows)
+        with self._host_lock:
+            return self._pipelined_to_host(ws, host_rows, ops, log_input, as_rows, B, N, devices)
+
+    def _pipelined_to_host(self, ws, host_rows, ops, log_input, as_rows, B, N, devices):
         whole = None if as_rows else {op: torch.empty((B, N), dtype=torch.float32, pin_memory=True) for op in ops}
         row_lists = {op: [None] * B for op in ops} if as_rows else None
         used = []

@@ -390,11 +390,13 @@ def test_concurrent_streams_and_threads_do_not_share_scratch():
             for _ in range(3):
                 out[i] = trie.batch_weight_sum(batches[i])  # host-returning path, its own pipeline streams per call
 
-    # the host-returning path shares one set of pipeline streams and staging buffers per trie: one thread at a time
-    for i in range(len(batches)):
-        t = threading.Thread(target=worker, args=(i,))
+    # the host-returning path shares one set of pipeline streams and staging buffers per trie: a lock serialises callers
+    threads = [threading.Thread(target=worker, args=(i,)) for i in range(len(batches))]
+    for t in threads:
         t.start()
+    for t in threads:
         t.join()
+    for i in range(len(batches)):
         assert rel_err(out[i], want[i][0])[0] <= SUM_RTOL
 
 
